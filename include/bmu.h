@@ -1,0 +1,170 @@
+/* bmu.h -- C ABI of the B200 best-matching-unit engine for SOM_PAK / LVQ_PAK.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The
+ * reference reaches its hot path one sample at a time through the function pointers of
+ * struct teach_params (reference lvq_pak.h:131-148,186-204):
+ *     WINNER_FUNCTION  find_winner_euc / find_winner_knn   (lvq_pak.c:41-94, 152-221)
+ *     VECTOR_ADAPT     adapt_vector                        (lvq_pak.c:339-351)
+ *     NEIGH_ADAPT      bubble_adapt / gaussian_adapt       (som_rout.c:472-549)
+ * A GPU cannot be fed one sample at a time, so the entry points below replace the loops
+ * that call those pointers (one level up):
+ *     bmu_search*        <- the per-sample loops of find_qerror (som_rout.c:710-721),
+ *                           compute_accuracy (accuracy.c:82), compute_classifications
+ *                           (classify.c:66), compute_knnaccuracy (knntest.c:98), find_labels
+ *                           (vcal.c:109), compute_visual_data (visual.c:113), compute_cmatr
+ *                           (cmatr.c:84), scan_data_traj (planes.c:242), correct_by_knn
+ *                           (lvq_rout.c:61), elimin.c:81, setlabel.c:73
+ *     bmu_som_train*     <- som_training             (som_rout.c:556-671)
+ *     bmu_lvq_train*     <- lvq1/olvq1/lvq2/lvq3_training (lvq_rout.c:498-916)
+ *     bmu_qerror2        <- find_qerror2 + bubble/gaussian_qerror (som_rout.c:734-891)
+ *     bmu_search_stats*  <- the sums/counts those callers accumulate, for the multi-GPU
+ *                           all-reduce
+ * Results are bit-identical to the reference for winner indices and squared distances
+ * (exact FP32: sub, mul, add with a rounding after every operation, summed in component
+ * order; first minimum wins for k = 1, (distance asc, index desc) for k >= 2).
+ *
+ * There is NO CPU fallback: every entry point returns BMU_ERR_NODEV / BMU_ERR_CUDA when no
+ * sm_100 device is usable.  All functions return 0 on success, a BMU_ERR_* code otherwise;
+ * bmu_last_error() gives the message.  Entry points are called from one host thread.
+ */
+#ifndef BMU_H
+#define BMU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMU_OK 0
+#define BMU_ERR_CUDA 1   /* a CUDA call failed (message in bmu_last_error)            */
+#define BMU_ERR_ARG 2    /* bad argument                                              */
+#define BMU_ERR_NOMEM 3  /* host or device allocation failed                          */
+#define BMU_ERR_NODEV 4  /* no CUDA device / not an sm_100 device                     */
+
+#define BMU_KMAX 16      /* largest k of bmu_search (reference uses k <= 10, elimin.c:30) */
+
+/* values of the reference's enums (lvq_pak.h:206-224) so that hosts can pass theirs through */
+#define BMU_TOPOL_HEXA 3
+#define BMU_TOPOL_RECT 4
+#define BMU_NEIGH_BUBBLE 1
+#define BMU_NEIGH_GAUSSIAN 2
+#define BMU_ALPHA_LINEAR 1
+#define BMU_ALPHA_INVERSE_T 2
+#define BMU_LVQ1 1
+#define BMU_LVQ2 2
+#define BMU_LVQ3 3
+#define BMU_OLVQ1 4
+
+/* which kernel family a search may use (bmu_set_search_path); AUTO picks per shape */
+#define BMU_PATH_AUTO 0
+#define BMU_PATH_EXACT 1   /* K1: direct FP32 difference-squared kernels only             */
+#define BMU_PATH_FILTER 2  /* K2: tcgen05 GEMM filter + exact FP32 re-rank (+K1 fallback) */
+
+/* ---- library / device ------------------------------------------------------------ */
+int bmu_init(int device);                 /* select device, create streams; idempotent  */
+void bmu_shutdown(void);
+const char *bmu_last_error(void);
+int bmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
+int bmu_set_search_path(int path);
+/* number of kernels this library has launched since bmu_init (bench.py: gpu_launches) */
+long bmu_launch_count(void);
+/* counters of the last bmu_search* call: rows answered by [0] the tile kernel K1-fast,
+ * [1] the warp-per-sample exact kernel, [2] the sequential-emulation kernel (non-finite or
+ * sub-2^-40 inputs), [3] the K2 filter with a passed certificate, [4] K2 rows re-done by K1 */
+int bmu_last_search_breakdown(long out[5]);
+
+/* ---- codebook (replicated on every GPU; reference: struct entries *codes) --------- */
+typedef struct bmu_codebook bmu_codebook;
+bmu_codebook *bmu_codebook_create(const float *codes, long M, int D);        /* host ptr  */
+bmu_codebook *bmu_codebook_create_dev(const float *d_codes, long M, int D);  /* device ptr */
+int bmu_codebook_update(bmu_codebook *cb, const float *codes);               /* host ptr  */
+void bmu_codebook_destroy(bmu_codebook *cb);
+
+/* ---- batch winner search ---------------------------------------------------------- */
+/* data: N x D row-major; mask: NULL or N x D bytes (non-zero = component ignored, only the
+ * SAMPLE's mask counts, lvq_pak.c:65-69); idx/diff: N x k; nfound: N (the reference's return
+ * value: 0 = every component masked, else k).  Unfilled slots: idx -1, diff -1.0 (k == 1)
+ * or FLT_MAX (k >= 2), exactly what the reference leaves in struct winner_info.
+ * Host-pointer version: copies in chunks overlapped with compute (this is bench.py's e2e). */
+int bmu_search(bmu_codebook *cb, const float *data, const unsigned char *mask, long N, int k,
+               int32_t *idx, float *diff, int32_t *nfound);
+/* device-pointer version, asynchronous on `stream` (a cudaStream_t, NULL = default) */
+int bmu_search_dev(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask, long N,
+                   int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound, void *stream);
+
+/* per-shard partial statistics of a finished search, to be summed over GPUs by ONE small
+ * all-reduce.  d_stats[0] = sum sqrt(diff[:,0]) over found rows (double; the
+ * byte-exact float sum of som_rout.c:715 is replayed on the host in data order),
+ * d_stats[1] = number of found rows; d_hist (nullable): M int64 BMU hit counts;
+ * d_confusion (nullable): n_labels x n_labels int64, [sample label][winner label], labels
+ * from d_sample_label[N] / d_code_label[M] in 0..n_labels-1.  Accumulates (+=). */
+int bmu_search_stats_dev(const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound,
+                         long N, int k, long M, double *d_stats, long long *d_hist,
+                         const int32_t *d_sample_label, const int32_t *d_code_label,
+                         int n_labels, long long *d_confusion, void *stream);
+
+/* ---- online training (sequential; one GPU) ---------------------------------------- */
+/* Schedules are produced on the host with the reference's own formulas (bmu_som_schedule /
+ * bmu_lvq_schedule below) and passed as per-step arrays, so that the device never has to
+ * reproduce libm's pow() and the sample order is the reference's -rand order:
+ *   sample[t]  index of the data row used at step t (list order, wrap, shuffle resolved)
+ *   talp[t]    learning rate of step t   (lvq_pak.c:903-921, som_rout.c:617-624)
+ *   trad[t]    neighbourhood radius      (som_rout.c:615)
+ * fixed_xy: NULL or N x 2 int16 (x,y) with x < 0 = no fixed point (som_rout.c:628-632).
+ * codes (M x D, M = xdim*ydim) is updated in place. */
+int bmu_som_train(float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
+                  const float *data, const unsigned char *mask, long N,
+                  const int16_t *fixed_xy, const int32_t *sample, const float *talp,
+                  const float *trad, long nsteps);
+
+/* algo BMU_LVQ1/2/3/OLVQ1 (lvq_rout.c:498-916).  win_thr = (1-win)/(1+win) in float
+ * (lvq_rout.c:770); unit_alpha: OLVQ1 per-unit rates, M floats in/out (NULL otherwise);
+ * alpha_cap: OLVQ1 cap (lvq_rout.c:670-672).  talp unused for OLVQ1 (may be NULL). */
+int bmu_lvq_train(int algo, float *codes, const int32_t *code_label, long M, int D,
+                  const float *data, const unsigned char *mask, const int32_t *data_label,
+                  long N, const int32_t *sample, const float *talp, long nsteps,
+                  float win_thr, float epsilon, float alpha_cap, float *unit_alpha);
+
+/* resident trainer: keeps data + codebook on the device between chunks of steps, so a host
+ * can stop at snapshot boundaries (som_rout.c:650-658) without re-uploading anything */
+typedef struct bmu_trainer bmu_trainer;
+bmu_trainer *bmu_trainer_create(const float *codes, long M, int D, const float *data,
+                                const unsigned char *mask, long N);
+int bmu_trainer_set_som(bmu_trainer *t, int xdim, int ydim, int topol, int neigh,
+                        const int16_t *fixed_xy);
+int bmu_trainer_set_lvq(bmu_trainer *t, int algo, const int32_t *code_label,
+                        const int32_t *data_label, float win_thr, float epsilon,
+                        float alpha_cap, const float *unit_alpha);
+/* run steps [0, nsteps) of the given per-step arrays (host pointers) */
+int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
+                      const float *trad, long nsteps);
+int bmu_trainer_get_codes(bmu_trainer *t, float *codes);
+int bmu_trainer_get_unit_alpha(bmu_trainer *t, float *unit_alpha);
+/* device time of the last bmu_trainer_steps call in milliseconds (CUDA events) */
+float bmu_trainer_last_ms(bmu_trainer *t);
+void bmu_trainer_destroy(bmu_trainer *t);
+
+/* ---- neighbourhood-weighted quantization error (qerror -qetype 1) ------------------ */
+/* per-sample value of bubble_qerror / gaussian_qerror (som_rout.c:734-819) around the BMU;
+ * out[n] for found rows, 0 for all-masked rows.  The host sums out[] in data order. */
+int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, float radius,
+                const float *data, const unsigned char *mask, long N, float *out);
+
+/* ---- host-side helpers (pure C arithmetic, no device) ------------------------------ */
+/* lvq_pak.c:459-473 + datafile.c:1152-1188: order[i] = row used at list position i after
+ * `-rand seed` (seed != 0; the reference maps seed 0 to time()). */
+void bmu_rand_order(long n, int seed, int32_t *order);
+/* fill sample/talp/trad for steps [le0, le1) of a run of `length` steps.  order: NULL =
+ * identity; weight: NULL or N shorts (vsom -weights, som_rout.c:622-624). */
+void bmu_som_schedule(long le0, long le1, long length, float alpha, float radius,
+                      int alpha_type, long N, const int32_t *order, const int16_t *weight,
+                      int32_t *sample, float *talp, float *trad);
+void bmu_lvq_schedule(long le0, long le1, long length, float alpha, int alpha_type, long N,
+                      const int32_t *order, int32_t *sample, float *talp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMU_H */

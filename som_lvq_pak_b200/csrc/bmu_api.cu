@@ -1,0 +1,421 @@
+// bmu_api.cu -- the C ABI declared in include/bmu.h: contexts, codebooks, the batch winner
+// search entry points (host- and device-pointer), per-shard statistics and the pure-C host
+// helpers (sample order, schedules).  No CPU fallback: without a usable sm_100 device every
+// entry point fails with BMU_ERR_NODEV / BMU_ERR_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/bmu.h"
+#include "common.cuh"
+#include "k1_search.h"
+#include "k2_filter.h"
+#include "k3_train.h"
+#include "api_internal.h"
+
+using namespace bmu;
+
+// ------------------------------------------------------------------ context
+namespace bmu {
+char g_err[512] = "";
+int g_dev = -1;
+int g_sms = 0;
+size_t g_smem_optin = 0;
+cudaStream_t g_compute = nullptr, g_copy = nullptr, g_out = nullptr;
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int ensure_init() {
+  if (g_dev >= 0) return BMU_OK;
+  return bmu_init(0);
+}
+int Scratch::ensure(size_t need) {
+  if (need <= bytes) return BMU_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+  size_t want = need + need / 8;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    if (cudaMalloc(&p, need) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BMU_ERR_NOMEM, "cudaMalloc of %zu bytes failed", need);
+    }
+    want = need;
+  }
+  bytes = want;
+  return BMU_OK;
+}
+void Scratch::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+}  // namespace bmu
+
+namespace {
+
+int g_path = BMU_PATH_AUTO;
+long g_breakdown[5] = {0, 0, 0, 0, 0};
+
+struct SearchScratch {
+  Scratch xT, flags, listW, listS, counters, k2;
+};
+SearchScratch g_ss[2];          // two sets so that chunked host searches can overlap
+Scratch g_stage_in[2], g_stage_mask[2], g_stage_idx[2], g_stage_diff[2], g_stage_nf[2];
+
+}  // namespace
+
+extern "C" {
+
+int bmu_init(int device) {
+  if (g_dev == device && g_compute) return BMU_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(BMU_ERR_NODEV, "no CUDA device: %s (this library has no CPU fallback)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(BMU_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(BMU_ERR_NODEV, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, p.major, p.minor);
+  if (g_compute) bmu_shutdown();
+  g_dev = device;
+  g_sms = p.multiProcessorCount;
+  g_smem_optin = p.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&g_compute, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g_out, cudaStreamNonBlocking));
+  return BMU_OK;
+}
+
+void bmu_shutdown(void) {
+  if (g_dev < 0) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; i++) {
+    g_ss[i].xT.release(); g_ss[i].flags.release(); g_ss[i].listW.release();
+    g_ss[i].listS.release(); g_ss[i].counters.release(); g_ss[i].k2.release();
+    g_stage_in[i].release(); g_stage_mask[i].release(); g_stage_idx[i].release();
+    g_stage_diff[i].release(); g_stage_nf[i].release();
+  }
+  if (g_compute) cudaStreamDestroy(g_compute);
+  if (g_copy) cudaStreamDestroy(g_copy);
+  if (g_out) cudaStreamDestroy(g_out);
+  g_compute = g_copy = g_out = nullptr;
+  g_dev = -1;
+}
+
+const char *bmu_last_error(void) { return g_err; }
+
+int bmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, g_dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+  return BMU_OK;
+}
+
+int bmu_set_search_path(int path) {
+  if (path < BMU_PATH_AUTO || path > BMU_PATH_FILTER) return fail(BMU_ERR_ARG, "bad path %d", path);
+  g_path = path;
+  return BMU_OK;
+}
+
+long bmu_launch_count(void) { return k1_launch_count(); }
+
+int bmu_last_search_breakdown(long out[5]) {
+  for (int i = 0; i < 5; i++) out[i] = g_breakdown[i];
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ codebook
+static bmu_codebook *codebook_from_dev(const float *d_src, const float *h_src, long M, int D) {
+  if (ensure_init()) return nullptr;
+  if (M <= 0 || D <= 0 || M > 0x7fffff00L) {
+    fail(BMU_ERR_ARG, "bad codebook shape M=%ld D=%d", M, D);
+    return nullptr;
+  }
+  bmu_codebook *cb = (bmu_codebook *)calloc(1, sizeof(bmu_codebook));
+  if (!cb) { fail(BMU_ERR_NOMEM, "calloc"); return nullptr; }
+  cb->M = M;
+  cb->D = D;
+  size_t bytes = (size_t)M * D * sizeof(float);
+  bool ok = cudaMalloc(&cb->d_codes, bytes) == cudaSuccess &&
+            cudaMalloc(&cb->d_cT, k1_cT_floats(M, D) * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&cb->d_flags, sizeof(unsigned)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    fail(BMU_ERR_NOMEM, "cudaMalloc for a %ld x %d codebook failed", M, D);
+    bmu_codebook_destroy(cb);
+    return nullptr;
+  }
+  cudaError_t e = h_src ? cudaMemcpyAsync(cb->d_codes, h_src, bytes, cudaMemcpyHostToDevice, g_compute)
+                        : cudaMemcpyAsync(cb->d_codes, d_src, bytes, cudaMemcpyDeviceToDevice, g_compute);
+  if (e == cudaSuccess) e = k1_prepare_codebook(cb->d_codes, M, D, cb->d_cT, cb->d_flags, g_compute);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+  if (e != cudaSuccess) {
+    fail(BMU_ERR_CUDA, "codebook upload failed: %s", cudaGetErrorString(e));
+    bmu_codebook_destroy(cb);
+    return nullptr;
+  }
+  return cb;
+}
+
+bmu_codebook *bmu_codebook_create(const float *codes, long M, int D) {
+  if (!codes) { fail(BMU_ERR_ARG, "codes is NULL"); return nullptr; }
+  return codebook_from_dev(nullptr, codes, M, D);
+}
+
+bmu_codebook *bmu_codebook_create_dev(const float *d_codes, long M, int D) {
+  if (!d_codes) { fail(BMU_ERR_ARG, "d_codes is NULL"); return nullptr; }
+  return codebook_from_dev(d_codes, nullptr, M, D);
+}
+
+int bmu_codebook_update(bmu_codebook *cb, const float *codes) {
+  if (!cb || !codes) return fail(BMU_ERR_ARG, "NULL argument");
+  CK(cudaMemcpyAsync(cb->d_codes, codes, (size_t)cb->M * cb->D * sizeof(float),
+                     cudaMemcpyHostToDevice, g_compute));
+  CK(k1_prepare_codebook(cb->d_codes, cb->M, cb->D, cb->d_cT, cb->d_flags, g_compute));
+  CK(cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute));
+  CK(cudaStreamSynchronize(g_compute));
+  k2_codebook_invalidate(&cb->k2);
+  return BMU_OK;
+}
+
+void bmu_codebook_destroy(bmu_codebook *cb) {
+  if (!cb) return;
+  if (cb->d_codes) cudaFree(cb->d_codes);
+  if (cb->d_cT) cudaFree(cb->d_cT);
+  if (cb->d_flags) cudaFree(cb->d_flags);
+  k2_codebook_free(&cb->k2);
+  free(cb);
+}
+
+// ------------------------------------------------------------------ search
+static int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask,
+                           long N, int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound,
+                           cudaStream_t st, SearchScratch &ss) {
+  if (!cb || !d_data || !d_idx || !d_diff || !d_nfound) return fail(BMU_ERR_ARG, "NULL argument");
+  if (k < 1 || k > BMU_KMAX) return fail(BMU_ERR_ARG, "k=%d outside 1..%d", k, BMU_KMAX);
+  if (N < 0 || N > 0x7fffff00L) return fail(BMU_ERR_ARG, "bad N=%ld", N);
+  if (N == 0) return BMU_OK;
+  const int D = cb->D;
+  int rc;
+  const bool use_k2 = k2_eligible(g_path, cb->M, D, N, k, cb->h_flags);
+  const bool need_tiles = (k == 1) && !cb->h_flags && !use_k2;
+  if (need_tiles && (rc = ss.xT.ensure(k1_xT_floats(N, D) * sizeof(float)))) return rc;
+  if ((rc = ss.flags.ensure((size_t)N))) return rc;
+  if ((rc = ss.listW.ensure((size_t)N * sizeof(int)))) return rc;
+  if ((rc = ss.listS.ensure((size_t)N * sizeof(int)))) return rc;
+  if ((rc = ss.counters.ensure(16 * sizeof(int)))) return rc;
+
+  K1Args a;
+  a.data = d_data; a.mask = d_mask; a.codes = cb->d_codes; a.cT = cb->d_cT;
+  a.cb_flags = cb->d_flags; a.N = N; a.M = cb->M; a.D = D; a.k = k;
+  a.skip_fast = need_tiles ? 0 : 1;
+  a.num_sms = g_sms;
+  a.xT = (float *)ss.xT.p; a.flags = (unsigned char *)ss.flags.p;
+  a.listW = (int *)ss.listW.p; a.listS = (int *)ss.listS.p; a.counters = (int *)ss.counters.p;
+  a.idx = d_idx; a.diff = d_diff; a.nfound = d_nfound;
+  if (use_k2) {
+    cudaError_t e = k2_search(&cb->k2, a, &ss.k2.p, &ss.k2.bytes, st);
+    if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k2_search: %s", cudaGetErrorString(e));
+    return BMU_OK;
+  }
+  cudaError_t e = k1_search(a, st);
+  if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k1_search: %s", cudaGetErrorString(e));
+  return BMU_OK;
+}
+
+int bmu_search_dev(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask, long N,
+                   int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound, void *stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  return search_dev_impl(cb, d_data, d_mask, N, k, d_idx, d_diff, d_nfound, (cudaStream_t)stream,
+                         g_ss[0]);
+}
+
+// Host-pointer search: rows are processed in chunks on three streams; chunk c+1 is copied in
+// (g_copy) while chunk c is searched (g_compute) and chunk c-1's results drain (g_out).
+int bmu_search(bmu_codebook *cb, const float *data, const unsigned char *mask, long N, int k,
+               int32_t *idx, float *diff, int32_t *nfound) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!cb || !data || !idx || !diff || !nfound) return fail(BMU_ERR_ARG, "NULL argument");
+  if (k < 1 || k > BMU_KMAX) return fail(BMU_ERR_ARG, "k=%d outside 1..%d", k, BMU_KMAX);
+  if (N <= 0) return N == 0 ? BMU_OK : fail(BMU_ERR_ARG, "bad N");
+  const int D = cb->D;
+  // chunk: about 256 MB of input, a multiple of the 128-row tile
+  long chunk = (256L << 20) / ((long)D * 4);
+  chunk = (chunk / K1_TS) * K1_TS;
+  if (chunk < K1_TS) chunk = K1_TS;
+  if (chunk > N) chunk = N;
+  for (int b = 0; b < 2; b++) {
+    if ((rc = g_stage_in[b].ensure((size_t)chunk * D * 4))) return rc;
+    if (mask && (rc = g_stage_mask[b].ensure((size_t)chunk * D))) return rc;
+    if ((rc = g_stage_idx[b].ensure((size_t)chunk * k * 4))) return rc;
+    if ((rc = g_stage_diff[b].ensure((size_t)chunk * k * 4))) return rc;
+    if ((rc = g_stage_nf[b].ensure((size_t)chunk * 4))) return rc;
+  }
+  cudaEvent_t in_done[2], work_done[2], out_done[2];
+  for (int b = 0; b < 2; b++) {
+    CK(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&work_done[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+  }
+  const long nchunks = (N + chunk - 1) / chunk;
+  int status = BMU_OK;
+  for (long c = 0; c < nchunks && status == BMU_OK; c++) {
+    const int b = (int)(c & 1);
+    const long n0 = c * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
+    // the staging buffers of slot b are free once chunk c-2 has been searched and drained
+    if (c >= 2) CK(cudaStreamWaitEvent(g_copy, work_done[b], 0));
+    CK(cudaMemcpyAsync(g_stage_in[b].p, data + n0 * (long)D, (size_t)n * D * 4,
+                       cudaMemcpyHostToDevice, g_copy));
+    if (mask)
+      CK(cudaMemcpyAsync(g_stage_mask[b].p, mask + n0 * (long)D, (size_t)n * D,
+                         cudaMemcpyHostToDevice, g_copy));
+    CK(cudaEventRecord(in_done[b], g_copy));
+    CK(cudaStreamWaitEvent(g_compute, in_done[b], 0));
+    if (c >= 2) CK(cudaStreamWaitEvent(g_compute, out_done[b], 0));
+    status = search_dev_impl(cb, (const float *)g_stage_in[b].p,
+                             mask ? (const unsigned char *)g_stage_mask[b].p : nullptr, n, k,
+                             (int32_t *)g_stage_idx[b].p, (float *)g_stage_diff[b].p,
+                             (int32_t *)g_stage_nf[b].p, g_compute, g_ss[b]);
+    if (status) break;
+    CK(cudaEventRecord(work_done[b], g_compute));
+    CK(cudaStreamWaitEvent(g_out, work_done[b], 0));
+    CK(cudaMemcpyAsync(idx + n0 * (long)k, g_stage_idx[b].p, (size_t)n * k * 4,
+                       cudaMemcpyDeviceToHost, g_out));
+    CK(cudaMemcpyAsync(diff + n0 * (long)k, g_stage_diff[b].p, (size_t)n * k * 4,
+                       cudaMemcpyDeviceToHost, g_out));
+    CK(cudaMemcpyAsync(nfound + n0, g_stage_nf[b].p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_out));
+    CK(cudaEventRecord(out_done[b], g_out));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(g_compute), e2 = cudaStreamSynchronize(g_out);
+  cudaStreamSynchronize(g_copy);
+  for (int b = 0; b < 2; b++) {
+    cudaEventDestroy(in_done[b]); cudaEventDestroy(work_done[b]); cudaEventDestroy(out_done[b]);
+  }
+  if (status) return status;
+  if (e1 != cudaSuccess) return fail(BMU_ERR_CUDA, "search failed: %s", cudaGetErrorString(e1));
+  if (e2 != cudaSuccess) return fail(BMU_ERR_CUDA, "search copy failed: %s", cudaGetErrorString(e2));
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ statistics
+__global__ void stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
+                             const int32_t *__restrict__ nfound, long N, int k, long M,
+                             double *__restrict__ stats, unsigned long long *__restrict__ hist,
+                             const int32_t *__restrict__ slabel, const int32_t *__restrict__ clabel,
+                             int L, unsigned long long *__restrict__ conf) {
+  double s = 0.0;
+  unsigned long long cnt = 0;
+  for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < N; n += (long)gridDim.x * blockDim.x) {
+    const int j = idx[n * k];
+    if (nfound[n] == 0 || j < 0) continue;
+    s += sqrt((double)diff[n * k]);
+    cnt++;
+    if (hist && j < M) atomicAdd(&hist[j], 1ull);
+    if (conf) {
+      const int a = slabel[n], b = clabel[j];
+      if (a >= 0 && a < L && b >= 0 && b < L) atomicAdd(&conf[(long)a * L + b], 1ull);
+    }
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&stats[0], s);
+    atomicAdd(&stats[1], (double)cnt);
+  }
+}
+
+int bmu_search_stats_dev(const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound,
+                         long N, int k, long M, double *d_stats, long long *d_hist,
+                         const int32_t *d_sample_label, const int32_t *d_code_label,
+                         int n_labels, long long *d_confusion, void *stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!d_idx || !d_diff || !d_nfound || !d_stats) return fail(BMU_ERR_ARG, "NULL argument");
+  if (d_confusion && (!d_sample_label || !d_code_label || n_labels <= 0))
+    return fail(BMU_ERR_ARG, "confusion counts need labels");
+  if (N <= 0) return BMU_OK;
+  int grid = g_sms * 4;
+  stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      d_idx, d_diff, d_nfound, N, k, M, d_stats, (unsigned long long *)d_hist, d_sample_label,
+      d_code_label, n_labels, (unsigned long long *)d_confusion);
+  k1_count_launch(1);
+  CK(cudaGetLastError());
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ host helpers
+// Sample order of `-rand seed`: the reference's LCG (lvq_pak.c:459-473) drives one pass of
+// swaps (datafile.c:1169-1175).
+void bmu_rand_order(long n, int seed, int32_t *order) {
+  unsigned long state = (unsigned long)seed;
+  for (long i = 0; i < n; i++) order[i] = (int32_t)i;
+  for (long i = 0; i < n; i++) {
+    state = (state * 23UL) % 100000001UL;
+    long j = (long)(int)(state % 32767UL) % n;
+    int32_t t = order[i];
+    order[i] = order[j];
+    order[j] = t;
+  }
+}
+
+static float alpha_at(long le, long length, float alpha, int alpha_type) {
+  if (alpha_type == BMU_ALPHA_INVERSE_T) {           // lvq_pak.c:914-921
+    float c = (float)length / 100.0f;
+    return alpha * c / (c + (float)le);
+  }
+  return alpha * (float)(length - le) / (float)length;   // lvq_pak.c:903-906
+}
+
+void bmu_som_schedule(long le0, long le1, long length, float alpha, float radius,
+                      int alpha_type, long N, const int32_t *order, const int16_t *weight,
+                      int32_t *sample, float *talp, float *trad) {
+  for (long le = le0; le < le1; le++) {
+    const long pos = le % N;                                // cyclic list order, som_rout.c:602-610
+    const long s = order ? order[pos] : pos;
+    float a = alpha_at(le, length, alpha, alpha_type);
+    if (weight && weight[s] > 0)                            // som_rout.c:622-624
+      a = (float)(1.0 - (double)(float)pow(1.0 - (double)a, (double)(float)weight[s]));
+    sample[le - le0] = (int32_t)s;
+    talp[le - le0] = a;
+    // som_rout.c:615, a double expression rounded once on assignment
+    trad[le - le0] = (float)(1.0 + ((double)radius - 1.0) * (double)(float)(length - le) /
+                                       (double)(float)length);
+  }
+}
+
+void bmu_lvq_schedule(long le0, long le1, long length, float alpha, int alpha_type, long N,
+                      const int32_t *order, int32_t *sample, float *talp) {
+  for (long le = le0; le < le1; le++) {
+    const long pos = le % N;
+    sample[le - le0] = (int32_t)(order ? order[pos] : pos);
+    if (talp) talp[le - le0] = alpha_at(le, length, alpha, alpha_type);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// bmu_train_api.cu -- C ABI for online training (bmu_trainer_*, bmu_som_train,
+// bmu_lvq_train) on top of the persistent kernel K3, and bmu_qerror2.
+#include <stdlib.h>
+#include <string.h>
+
+#include "api_internal.h"
+#include "common.cuh"
+#include "k1_search.h"
+#include "k3_train.h"
+
+using namespace bmu;
+
+struct bmu_trainer {
+  long M, N;
+  int D;
+  float *d_codes = nullptr, *d_data = nullptr, *d_unit_alpha = nullptr, *d_gslice = nullptr;
+  unsigned char *d_valid = nullptr;
+  short *d_fixed = nullptr;
+  int *d_code_label = nullptr, *d_data_label = nullptr;
+  unsigned long long *d_slots = nullptr;
+  bool has_mask = false;
+  int mode = -1;
+  int xdim = 0, ydim = 0, topol = 0;
+  float win_thr = 0, epsilon = 0, alpha_cap = 0;
+  K3Plan plan{};
+  Scratch sched_sample, sched_talp, sched_trad;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.0f;
+};
+
+namespace {
+template <typename T>
+int dev_upload(T **dst, const T *src, size_t count) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (cudaMalloc((void **)dst, count * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BMU_ERR_NOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+  }
+  CK(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, g_compute));
+  return BMU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+bmu_trainer *bmu_trainer_create(const float *codes, long M, int D, const float *data,
+                                const unsigned char *mask, long N) {
+  if (ensure_init()) return nullptr;
+  if (!codes || !data || M <= 0 || N <= 0 || D <= 0 || M > 0xFFFFFEL) {
+    fail(BMU_ERR_ARG, "bad trainer arguments (M=%ld N=%ld D=%d)", M, N, D);
+    return nullptr;
+  }
+  bmu_trainer *t = new bmu_trainer();
+  t->M = M; t->N = N; t->D = D;
+  int rc = dev_upload(&t->d_codes, codes, (size_t)M * D);
+  if (!rc) rc = dev_upload(&t->d_data, data, (size_t)N * D);
+  if (!rc && mask) {
+    // masks travel inside the data as a NaN sentinel (k3_train.h); only done if any bit is set
+    bool any = false;
+    for (size_t i = 0; i < (size_t)N * D && !any; i++) any = mask[i] != 0;
+    if (any) {
+      unsigned char *d_mask = nullptr;
+      rc = dev_upload(&d_mask, mask, (size_t)N * D);
+      if (!rc && cudaMalloc((void **)&t->d_valid, (size_t)N) != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail(BMU_ERR_NOMEM, "cudaMalloc failed");
+      }
+      if (!rc) {
+        cudaError_t e = k3_encode_mask(t->d_data, d_mask, t->d_valid, N, D, g_compute);
+        k1_count_launch(1);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+        if (e != cudaSuccess) rc = fail(BMU_ERR_CUDA, "mask encoding: %s", cudaGetErrorString(e));
+      }
+      if (d_mask) cudaFree(d_mask);
+      t->has_mask = true;
+    }
+  }
+  if (!rc) {
+    t->plan = k3_plan(M, D, g_sms, g_smem_optin);
+    if (cudaMalloc((void **)&t->d_slots, sizeof(unsigned long long) * 4 * t->plan.grid) != cudaSuccess ||
+        (t->plan.gslice_floats &&
+         cudaMalloc((void **)&t->d_gslice, t->plan.gslice_floats * sizeof(float)) != cudaSuccess)) {
+      cudaGetLastError();
+      rc = fail(BMU_ERR_NOMEM, "cudaMalloc failed");
+    }
+  }
+  if (!rc && (cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess))
+    rc = fail(BMU_ERR_CUDA, "cudaEventCreate failed");
+  if (!rc && cudaStreamSynchronize(g_compute) != cudaSuccess) rc = fail(BMU_ERR_CUDA, "upload failed");
+  if (rc) { bmu_trainer_destroy(t); return nullptr; }
+  return t;
+}
+
+int bmu_trainer_set_som(bmu_trainer *t, int xdim, int ydim, int topol, int neigh,
+                        const int16_t *fixed_xy) {
+  if (!t) return fail(BMU_ERR_ARG, "NULL trainer");
+  if ((long)xdim * ydim != t->M) return fail(BMU_ERR_ARG, "xdim*ydim=%ld != M=%ld", (long)xdim * ydim, t->M);
+  if (topol != BMU_TOPOL_HEXA && topol != BMU_TOPOL_RECT) return fail(BMU_ERR_ARG, "bad topology %d", topol);
+  if (neigh != BMU_NEIGH_BUBBLE && neigh != BMU_NEIGH_GAUSSIAN) return fail(BMU_ERR_ARG, "bad neighbourhood %d", neigh);
+  t->mode = neigh == BMU_NEIGH_GAUSSIAN ? K3_SOM_GAUSSIAN : K3_SOM_BUBBLE;
+  t->xdim = xdim; t->ydim = ydim; t->topol = topol;
+  if (t->d_fixed) { cudaFree(t->d_fixed); t->d_fixed = nullptr; }
+  if (fixed_xy) {
+    int rc = dev_upload(&t->d_fixed, (const short *)fixed_xy, (size_t)t->N * 2);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_compute));
+  }
+  return BMU_OK;
+}
+
+int bmu_trainer_set_lvq(bmu_trainer *t, int algo, const int32_t *code_label,
+                        const int32_t *data_label, float win_thr, float epsilon,
+                        float alpha_cap, const float *unit_alpha) {
+  if (!t || !code_label || !data_label) return fail(BMU_ERR_ARG, "NULL argument");
+  switch (algo) {
+    case BMU_LVQ1: t->mode = K3_LVQ1; break;
+    case BMU_LVQ2: t->mode = K3_LVQ2; break;
+    case BMU_LVQ3: t->mode = K3_LVQ3; break;
+    case BMU_OLVQ1: t->mode = K3_OLVQ1; break;
+    default: return fail(BMU_ERR_ARG, "bad LVQ algorithm %d", algo);
+  }
+  if (algo == BMU_OLVQ1 && !unit_alpha) return fail(BMU_ERR_ARG, "OLVQ1 needs unit_alpha");
+  if ((algo == BMU_LVQ2 || algo == BMU_LVQ3) && t->M < 2) return fail(BMU_ERR_ARG, "LVQ2/3 need M >= 2");
+  t->win_thr = win_thr; t->epsilon = epsilon; t->alpha_cap = alpha_cap;
+  int rc = dev_upload(&t->d_code_label, (const int *)code_label, (size_t)t->M);
+  if (!rc) rc = dev_upload(&t->d_data_label, (const int *)data_label, (size_t)t->N);
+  if (!rc && unit_alpha) rc = dev_upload(&t->d_unit_alpha, unit_alpha, (size_t)t->M);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(g_compute));
+  return BMU_OK;
+}
+
+int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
+                      const float *trad, long nsteps) {
+  if (!t || !sample) return fail(BMU_ERR_ARG, "NULL argument");
+  if (t->mode < 0) return fail(BMU_ERR_ARG, "trainer mode not set (bmu_trainer_set_som/_lvq)");
+  if (nsteps <= 0) return BMU_OK;
+  const bool som = t->mode <= K3_SOM_GAUSSIAN;
+  if (som && (!talp || !trad)) return fail(BMU_ERR_ARG, "SOM training needs talp and trad");
+  if (!som && t->mode != K3_OLVQ1 && !talp) return fail(BMU_ERR_ARG, "LVQ training needs talp");
+  for (long i = 0; i < nsteps; i++)
+    if (sample[i] < 0 || sample[i] >= t->N) return fail(BMU_ERR_ARG, "sample[%ld]=%d out of range", i, sample[i]);
+  int rc;
+  if ((rc = t->sched_sample.ensure((size_t)nsteps * 4))) return rc;
+  CK(cudaMemcpyAsync(t->sched_sample.p, sample, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
+  if (talp) {
+    if ((rc = t->sched_talp.ensure((size_t)nsteps * 4))) return rc;
+    CK(cudaMemcpyAsync(t->sched_talp.p, talp, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
+  }
+  if (trad) {
+    if ((rc = t->sched_trad.ensure((size_t)nsteps * 4))) return rc;
+    CK(cudaMemcpyAsync(t->sched_trad.p, trad, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
+  }
+  K3Params p{};
+  p.codes = t->d_codes; p.data = t->d_data; p.valid = t->d_valid;
+  p.N = t->N; p.M = t->M; p.D = t->D; p.mode = t->mode;
+  p.xdim = t->xdim; p.ydim = t->ydim; p.topol = t->topol; p.fixed_xy = t->d_fixed;
+  p.code_label = t->d_code_label; p.data_label = t->d_data_label;
+  p.win_thr = t->win_thr; p.epsilon = t->epsilon; p.alpha_cap = t->alpha_cap;
+  p.unit_alpha = t->d_unit_alpha;
+  p.sample = (const int *)t->sched_sample.p;
+  p.talp = talp ? (const float *)t->sched_talp.p : nullptr;
+  p.trad = trad ? (const float *)t->sched_trad.p : nullptr;
+  p.nsteps = nsteps;
+  p.slots = t->d_slots; p.gslice = t->d_gslice;
+  p.U = t->plan.U; p.Us = t->plan.Us; p.slice_in_smem = t->plan.slice_in_smem;
+  CK(cudaEventRecord(t->ev0, g_compute));
+  cudaError_t e = k3_launch(p, t->plan, t->has_mask, g_compute);
+  k1_count_launch(1);
+  if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k3_launch: %s", cudaGetErrorString(e));
+  CK(cudaEventRecord(t->ev1, g_compute));
+  CK(cudaStreamSynchronize(g_compute));
+  CK(cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1));
+  return BMU_OK;
+}
+
+int bmu_trainer_get_codes(bmu_trainer *t, float *codes) {
+  if (!t || !codes) return fail(BMU_ERR_ARG, "NULL argument");
+  CK(cudaMemcpyAsync(codes, t->d_codes, (size_t)t->M * t->D * 4, cudaMemcpyDeviceToHost, g_compute));
+  CK(cudaStreamSynchronize(g_compute));
+  return BMU_OK;
+}
+
+int bmu_trainer_get_unit_alpha(bmu_trainer *t, float *unit_alpha) {
+  if (!t || !unit_alpha || !t->d_unit_alpha) return fail(BMU_ERR_ARG, "no unit_alpha state");
+  CK(cudaMemcpyAsync(unit_alpha, t->d_unit_alpha, (size_t)t->M * 4, cudaMemcpyDeviceToHost, g_compute));
+  CK(cudaStreamSynchronize(g_compute));
+  return BMU_OK;
+}
+
+float bmu_trainer_last_ms(bmu_trainer *t) { return t ? t->last_ms : 0.0f; }
+
+void bmu_trainer_destroy(bmu_trainer *t) {
+  if (!t) return;
+  void *ptrs[] = {t->d_codes, t->d_data, t->d_unit_alpha, t->d_gslice, t->d_valid, t->d_fixed,
+                  t->d_code_label, t->d_data_label, t->d_slots};
+  for (void *q : ptrs) if (q) cudaFree(q);
+  t->sched_sample.release(); t->sched_talp.release(); t->sched_trad.release();
+  if (t->ev0) cudaEventDestroy(t->ev0);
+  if (t->ev1) cudaEventDestroy(t->ev1);
+  delete t;
+}
+
+int bmu_som_train(float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
+                  const float *data, const unsigned char *mask, long N,
+                  const int16_t *fixed_xy, const int32_t *sample, const float *talp,
+                  const float *trad, long nsteps) {
+  bmu_trainer *t = bmu_trainer_create(codes, M, D, data, mask, N);
+  if (!t) return BMU_ERR_CUDA;
+  int rc = bmu_trainer_set_som(t, xdim, ydim, topol, neigh, fixed_xy);
+  if (!rc) rc = bmu_trainer_steps(t, sample, talp, trad, nsteps);
+  if (!rc) rc = bmu_trainer_get_codes(t, codes);
+  bmu_trainer_destroy(t);
+  return rc;
+}
+
+int bmu_lvq_train(int algo, float *codes, const int32_t *code_label, long M, int D,
+                  const float *data, const unsigned char *mask, const int32_t *data_label,
+                  long N, const int32_t *sample, const float *talp, long nsteps,
+                  float win_thr, float epsilon, float alpha_cap, float *unit_alpha) {
+  bmu_trainer *t = bmu_trainer_create(codes, M, D, data, mask, N);
+  if (!t) return BMU_ERR_CUDA;
+  int rc = bmu_trainer_set_lvq(t, algo, code_label, data_label, win_thr, epsilon, alpha_cap, unit_alpha);
+  if (!rc) rc = bmu_trainer_steps(t, sample, talp, nullptr, nsteps);
+  if (!rc) rc = bmu_trainer_get_codes(t, codes);
+  if (!rc && algo == BMU_OLVQ1) rc = bmu_trainer_get_unit_alpha(t, unit_alpha);
+  bmu_trainer_destroy(t);
+  return rc;
+}
+
+int bmu_qerror2(bmu_codebook *, int, int, int, int, float, const float *, const unsigned char *,
+                long, float *) {
+  return fail(BMU_ERR_ARG, "bmu_qerror2 is not implemented yet");
+}
+
+}  // extern "C"

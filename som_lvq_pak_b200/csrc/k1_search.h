@@ -1,0 +1,42 @@
+// k1_search.h -- internal interface of the exact winner-search kernels (k1_search.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define K1_TS 128       // samples per CTA tile
+#define K1_TC 128       // code vectors per CTA tile
+#define K1_DC 64        // components per shared-memory stage
+#define BMU_KMAX_ 16
+
+namespace bmu {
+
+struct K1Args {
+  const float *data;            // N x D row-major (device)
+  const unsigned char *mask;    // N x D or nullptr (device)
+  const float *codes;           // M x D row-major (device)
+  const float *cT;              // tile layout of the codebook (k1_prepare_codebook)
+  const unsigned *cb_flags;     // device: ROW_* bits of the whole codebook
+  long N, M;
+  int D, k;
+  int skip_fast;                // host copy of (*cb_flags != 0)
+  int num_sms;
+  // scratch
+  float *xT;                    // k1_xT_floats(N, D) floats (only touched when k == 1)
+  unsigned char *flags;         // N
+  int *listW, *listS;           // N each
+  int *counters;                // 4 ints
+  // outputs
+  int32_t *idx;
+  float *diff;
+  int32_t *nfound;
+};
+
+size_t k1_cT_floats(long M, int D);
+size_t k1_xT_floats(long N, int D);
+cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT,
+                                unsigned *d_cb_flags, cudaStream_t st);
+cudaError_t k1_search(const K1Args &a, cudaStream_t st);
+long k1_launch_count();
+void k1_count_launch(int n);
+
+}  // namespace bmu

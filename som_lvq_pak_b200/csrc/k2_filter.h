@@ -1,0 +1,24 @@
+// k2_filter.h -- internal interface of K2: tcgen05 GEMM filter + exact FP32 re-rank
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "k1_search.h"
+
+namespace bmu {
+
+struct K2Codebook {
+  void *d_ops = nullptr;        // bf16 split operands of the codebook, UMMA tile layout
+  float *d_norm = nullptr;      // per code: ||m||^2 and error-bound terms
+  size_t ops_bytes = 0;
+  int valid = 0;
+  int Kpad = 0;
+};
+
+bool k2_eligible(int path, long M, int D, long N, int k, unsigned cb_flags);
+void k2_codebook_invalidate(K2Codebook *c);
+void k2_codebook_free(K2Codebook *c);
+// scratch: grow-only device buffer owned by the caller
+cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *scratch_bytes,
+                      cudaStream_t st);
+
+}  // namespace bmu

@@ -1,0 +1,258 @@
+"""Host-side mirror (Python) of the reference's plugin interface for the BMU path.
+
+The reference hands its hot path around as function pointers in struct teach_params
+(reference lvq_pak.h:186-204): `winner` (find_winner_euc / find_winner_knn), `vector_adapt`,
+`neigh_adapt`, `alpha_func`.  Here the same operations are exposed at the granularity a GPU
+can be fed at -- whole data sets -- with the same names, argument meaning and error
+behaviour, all of them calling the CUDA library through the C ABI of include/bmu.h.
+numpy arrays stand in for `struct entries`; nothing in this module computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+TOPOL_HEXA, TOPOL_RECT = 3, 4
+NEIGH_BUBBLE, NEIGH_GAUSSIAN = 1, 2
+ALPHA_LINEAR, ALPHA_INVERSE_T = 1, 2
+LVQ1, LVQ2, LVQ3, OLVQ1 = 1, 2, 3, 4
+PATH_AUTO, PATH_EXACT, PATH_FILTER = 0, 1, 2
+KMAX = 16
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _opt(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def init(device=0):
+    _lib.check(_lib.load().bmu_init(device))
+
+
+def device_info():
+    sm, ma, mi, sh = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
+    _lib.check(_lib.load().bmu_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(sh)))
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "smem_optin": sh.value}
+
+
+def set_search_path(path):
+    _lib.check(_lib.load().bmu_set_search_path(path))
+
+
+def launch_count():
+    return _lib.load().bmu_launch_count()
+
+
+class Codebook:
+    """A codebook resident on the GPU (reference: struct entries *codes)."""
+
+    def __init__(self, codes):
+        codes = _f32(codes)
+        if codes.ndim != 2:
+            raise ValueError("codes must be M x D")
+        self.M, self.D = codes.shape
+        self._h = _lib.load().bmu_codebook_create(_ptr(codes), self.M, self.D)
+        if not self._h:
+            raise RuntimeError("bmu_codebook_create: " + _lib.load().bmu_last_error().decode())
+
+    def update(self, codes):
+        codes = _f32(codes)
+        assert codes.shape == (self.M, self.D)
+        _lib.check(_lib.load().bmu_codebook_update(self._h, _ptr(codes)))
+
+    def close(self):
+        if self._h:
+            _lib.load().bmu_codebook_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- WINNER_FUNCTION over a whole data set (lvq_pak.c:41-94 / 152-221)
+    def find_winners(self, data, knn=1, mask=None):
+        """returns (index N x knn int32, diff N x knn float32 [squared], nfound N int32)"""
+        data = _f32(data)
+        if data.ndim != 2 or data.shape[1] != self.D:
+            raise ValueError("data must be N x %d" % self.D)
+        mask = _opt(mask, np.uint8)
+        N = data.shape[0]
+        idx = np.empty((N, knn), np.int32)
+        diff = np.empty((N, knn), np.float32)
+        nf = np.empty(N, np.int32)
+        _lib.check(_lib.load().bmu_search(self._h, _ptr(data), _ptr(mask), N, knn, _ptr(idx),
+                                          _ptr(diff), _ptr(nf)))
+        return idx, diff, nf
+
+    def search_dev(self, d_data, N, knn, d_idx, d_diff, d_nfound, d_mask=None, stream=None):
+        """device-pointer variant: arguments are integer device addresses (e.g. tensor.data_ptr())"""
+        _lib.check(_lib.load().bmu_search_dev(self._h, d_data, d_mask, N, knn, d_idx, d_diff,
+                                              d_nfound, stream))
+
+
+def find_winner_euc(codes, data, mask=None):
+    cb = Codebook(codes)
+    try:
+        return cb.find_winners(data, 1, mask)
+    finally:
+        cb.close()
+
+
+def find_winner_knn(codes, data, knn, mask=None):
+    cb = Codebook(codes)
+    try:
+        return cb.find_winners(data, knn, mask)
+    finally:
+        cb.close()
+
+
+# ---------------------------------------------------------------------------- host helpers
+def rand_order(n, seed):
+    """list order after `-rand seed` (datafile.c:1152-1188 driven by lvq_pak.c:459-473)"""
+    order = np.empty(n, np.int32)
+    _lib.load().bmu_rand_order(n, seed, _ptr(order))
+    return order
+
+
+def som_schedule(le0, le1, length, alpha, radius, alpha_type, N, order=None, weight=None):
+    n = le1 - le0
+    sample = np.empty(n, np.int32)
+    talp = np.empty(n, np.float32)
+    trad = np.empty(n, np.float32)
+    order = _opt(order, np.int32)
+    weight = _opt(weight, np.int16)
+    _lib.load().bmu_som_schedule(le0, le1, length, alpha, radius, alpha_type, N, _ptr(order),
+                                 _ptr(weight), _ptr(sample), _ptr(talp), _ptr(trad))
+    return sample, talp, trad
+
+
+def lvq_schedule(le0, le1, length, alpha, alpha_type, N, order=None):
+    n = le1 - le0
+    sample = np.empty(n, np.int32)
+    talp = np.empty(n, np.float32)
+    order = _opt(order, np.int32)
+    _lib.load().bmu_lvq_schedule(le0, le1, length, alpha, alpha_type, N, _ptr(order), _ptr(sample),
+                                 _ptr(talp))
+    return sample, talp
+
+
+# ---------------------------------------------------------------------------- training
+class Trainer:
+    """Device-resident codebook + data for chunked training (snapshot boundaries)."""
+
+    def __init__(self, codes, data, mask=None):
+        codes, data = _f32(codes), _f32(data)
+        mask = _opt(mask, np.uint8)
+        self.M, self.D = codes.shape
+        self.N = data.shape[0]
+        self._h = _lib.load().bmu_trainer_create(_ptr(codes), self.M, self.D, _ptr(data),
+                                                 _ptr(mask), self.N)
+        if not self._h:
+            raise RuntimeError("bmu_trainer_create: " + _lib.load().bmu_last_error().decode())
+
+    def set_som(self, xdim, ydim, topol, neigh, fixed_xy=None):
+        fixed_xy = _opt(fixed_xy, np.int16)
+        _lib.check(_lib.load().bmu_trainer_set_som(self._h, xdim, ydim, topol, neigh, _ptr(fixed_xy)))
+
+    def set_lvq(self, algo, code_label, data_label, win_thr=0.0, epsilon=0.0, alpha_cap=0.0,
+                unit_alpha=None):
+        cl = np.ascontiguousarray(code_label, np.int32)
+        dl = np.ascontiguousarray(data_label, np.int32)
+        ua = _opt(unit_alpha, np.float32)
+        _lib.check(_lib.load().bmu_trainer_set_lvq(self._h, algo, _ptr(cl), _ptr(dl), win_thr,
+                                                   epsilon, alpha_cap, _ptr(ua)))
+
+    def steps(self, sample, talp=None, trad=None):
+        sample = np.ascontiguousarray(sample, np.int32)
+        talp, trad = _opt(talp, np.float32), _opt(trad, np.float32)
+        _lib.check(_lib.load().bmu_trainer_steps(self._h, _ptr(sample), _ptr(talp), _ptr(trad),
+                                                 sample.shape[0]))
+
+    def codes(self):
+        out = np.empty((self.M, self.D), np.float32)
+        _lib.check(_lib.load().bmu_trainer_get_codes(self._h, _ptr(out)))
+        return out
+
+    def unit_alpha(self):
+        out = np.empty(self.M, np.float32)
+        _lib.check(_lib.load().bmu_trainer_get_unit_alpha(self._h, _ptr(out)))
+        return out
+
+    def last_ms(self):
+        return float(_lib.load().bmu_trainer_last_ms(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.load().bmu_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def som_training(codes, data, xdim, ydim, topol, neigh, length, alpha, radius,
+                 alpha_type=ALPHA_LINEAR, rand_seed=None, mask=None, weight=None, fixed_xy=None,
+                 snapshot_interval=0, snapshot_cb=None):
+    """som_training (som_rout.c:556-671).  rand_seed None = list order (no -rand).  With a
+    snapshot interval the run is cut at the reference's snapshot steps (`le % interval == 0
+    and le > 0`, evaluated after step le: som_rout.c:650) and snapshot_cb(le, codes) is called."""
+    data = _f32(data)
+    N = data.shape[0]
+    order = None if rand_seed is None else rand_order(N, rand_seed)
+    tr = Trainer(codes, data, mask)
+    try:
+        tr.set_som(xdim, ydim, topol, neigh, fixed_xy)
+        snaps = []
+        if snapshot_interval and snapshot_cb:
+            snaps = list(range(snapshot_interval, length, snapshot_interval))
+        le0 = 0
+        for le in snaps + [None]:
+            le1 = length if le is None else le + 1
+            if le1 > le0:
+                s, ta, tr_ = som_schedule(le0, le1, length, alpha, radius, alpha_type, N, order, weight)
+                tr.steps(s, ta, tr_)
+            if le is not None:
+                snapshot_cb(le, tr.codes())
+            le0 = le1
+        return tr.codes()
+    finally:
+        tr.close()
+
+
+def lvq_training(algo, codes, code_label, data, data_label, length, alpha,
+                 alpha_type=ALPHA_LINEAR, winlen=0.3, epsilon=0.1, rand_seed=None, mask=None,
+                 unit_alpha=None):
+    """lvq1/olvq1/lvq2/lvq3_training (lvq_rout.c:498-916).  Returns codes (and the per-unit
+    rates for OLVQ1).  For OLVQ1 `alpha` is both the initial per-unit rate (when unit_alpha is
+    None) and the cap, as in lvq_rout.c:614-627,670-672."""
+    data = _f32(data)
+    N = data.shape[0]
+    M = np.asarray(codes).shape[0]
+    order = None if rand_seed is None else rand_order(N, rand_seed)
+    w = np.float32(winlen)
+    win_thr = float(np.float32(np.float32(1) - w) / np.float32(np.float32(1) + w))   # lvq_rout.c:770
+    ua = None
+    if algo == OLVQ1:
+        ua = np.full(M, alpha, np.float32) if unit_alpha is None else _f32(unit_alpha)
+    tr = Trainer(codes, data, mask)
+    try:
+        tr.set_lvq(algo, code_label, data_label, win_thr, epsilon, alpha, ua)
+        s, ta = lvq_schedule(0, length, length, alpha, alpha_type, N, order)
+        tr.steps(s, ta, None)
+        out = tr.codes()
+        return (out, tr.unit_alpha()) if algo == OLVQ1 else out
+    finally:
+        tr.close()

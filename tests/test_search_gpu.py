@@ -1,0 +1,109 @@
+"""GPU parity of the batch winner search (through the C ABI, host-pointer entry point)
+against (a) the golden vectors generated from the unmodified reference and (b) the CPU
+oracle on seeded inputs.  Bar: bit-exact indices, squared distances and return values."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = ["lowdim", "c3like", "odd", "c4like", "tiny", "wide"]
+TAGS = {"u": ("codes", "data", None), "q": ("qcodes", "qdata", None),
+        "m": ("qcodes", "qdata", "mask"), "nf": ("nfcodes", "nfdata", None)}
+
+
+def check(engine, codes, data, k, mask, exp, what):
+    idx, diff, nf = engine.find_winner_knn(codes, data, k, mask)
+    assert_bits_equal(idx, exp[0], what + " idx")
+    assert_bits_equal(diff, exp[1], what + " diff")
+    assert_bits_equal(nf, exp[2], what + " ret")
+
+
+@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("k", [1, 2, 5, 10])
+def test_search_golden(engine, golden, shape, k, path):
+    g = golden.search
+    engine.set_search_path(path)
+    try:
+        for tag, (c, d, m) in TAGS.items():
+            key = "%s_%s_k%d" % (shape, tag, k)
+            if key + "_idx" not in g:
+                continue
+            check(engine, g[shape + "_" + c], g[shape + "_" + d], k,
+                  None if m is None else g[shape + "_" + m],
+                  (g[key + "_idx"], g[key + "_diff"], g[key + "_ret"]), key)
+    finally:
+        engine.set_search_path(0)
+
+
+@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("M,D,N", [(96, 5, 3840), (200, 20, 1962), (1000, 64, 4096), (10000, 64, 1500),
+                                   (4096, 512, 300), (129, 7, 130), (1, 3, 10), (300, 100, 257)])
+def test_search_vs_oracle_random(engine, oracle, M, D, N, path):
+    rng = np.random.default_rng(M * 131 + D)
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    engine.set_search_path(path)
+    try:
+        for k in (1, 5):
+            check(engine, codes, data, k, None, oracle.search(codes, data, k), "rand k=%d" % k)
+    finally:
+        engine.set_search_path(0)
+
+
+@pytest.mark.parametrize("path", [1, 0])
+def test_search_adversarial(engine, oracle, path):
+    """exact ties, duplicated code vectors, masks, subnormal-scale values, huge values"""
+    rng = np.random.default_rng(7)
+    M, D, N = 500, 64, 1000
+    codes = (rng.integers(0, 3, (M, D)) / 2).astype(np.float32)
+    data = (rng.integers(0, 3, (N, D)) / 2).astype(np.float32)
+    codes[100:200] = codes[0:100]              # duplicates: lowest index must win for k=1
+    data[:50] = codes[100:150]                 # zero distance to two codes each
+    engine.set_search_path(path)
+    try:
+        for k in (1, 2, 7, 16):
+            check(engine, codes, data, k, None, oracle.search(codes, data, k), "ties k=%d" % k)
+        mask = (rng.random((N, D)) < 0.5).astype(np.uint8)
+        mask[10] = 1
+        mask[11] = 0
+        for k in (1, 3):
+            check(engine, codes, data, k, mask, oracle.search(codes, data, k, mask), "mask k=%d" % k)
+        # magnitudes that make squares subnormal / overflow: must leave the packed (.ftz) kernel
+        tiny = data.copy()
+        tiny[::3] *= np.float32(1e-30)
+        tc = codes.copy()
+        tc[::5] *= np.float32(1e-30)
+        for k in (1, 4):
+            check(engine, tc, tiny, k, None, oracle.search(tc, tiny, k), "tiny k=%d" % k)
+        huge = data.copy()
+        huge[::4] *= np.float32(3e19)
+        for k in (1, 4):
+            check(engine, codes, huge, k, None, oracle.search(codes, huge, k), "huge k=%d" % k)
+        # k larger than the codebook
+        check(engine, codes[:3], data[:40], 8, None, oracle.search(codes[:3], data[:40], 8), "k>M")
+    finally:
+        engine.set_search_path(0)
+
+
+def test_search_chunked_host_path(engine, oracle):
+    """N large enough that bmu_search cuts the rows into several overlapped chunks"""
+    rng = np.random.default_rng(3)
+    M, D = 64, 512
+    N = 300000                                  # 614 MB of input -> 3 chunks of 256 MB
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    idx, diff, nf = engine.find_winner_euc(codes, data)
+    sub = np.r_[0:2000, 131000:133000, N - 2000:N]
+    e = oracle.search(codes, data[sub], 1)
+    assert_bits_equal(idx[sub], e[0])
+    assert_bits_equal(diff[sub], e[1])
+    assert (nf == 1).all()
+    # size-independent property: every reported distance is the distance to the reported code
+    # and no code is closer (checked in float64 on a sample with a margin)
+    s = rng.integers(0, N, 500)
+    d64 = ((data[s, None, :].astype(np.float64) - codes[None].astype(np.float64)) ** 2).sum(-1)
+    assert np.allclose(d64[np.arange(500), idx[s, 0]], diff[s, 0], rtol=1e-5)
+    assert (d64.min(1) >= diff[s, 0] * (1 - 1e-5)).all()
