@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- BMU searches/s of the batch winner search on synthetic data (BASELINE.json
+configs[2]: 10 M vectors x 64-dim vs a 100x100 map, qerror + visual style consumers).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's C code on host cores
+
+One "step" = one pass of the hot path over one batch: every rank searches its own shard of
+`rows` vectors against the replicated codebook (no data-path collective), reduces its
+qerror sum / found count / BMU histogram on the device, and the small statistics vector is
+combined by ONE NCCL all-reduce.  Weak scaling: rows per GPU is fixed.
+
+JSON keys follow the driver contract; `value` is device-resident (inputs already in HBM),
+`e2e` goes through bmu_search() with pinned HOST buffers (H2D + D2H inside the timed region).
+The oracle/ directory is only used for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: rows per GPU, D, M, xdim, k
+    "c3": dict(rows=10_000_000, D=64, M=10_000, xdim=100, k=1,
+               desc="synthetic batch winner search: 10M x 64-dim vs 100x100 map (BASELINE.json configs[2])"),
+    "c4": dict(rows=1_000_000, D=512, M=4096, xdim=64, k=1,
+               desc="synthetic high-dim: 1M x 512-dim vs 4096-unit codebook (BASELINE.json configs[3])"),
+}
+
+MASK64 = (1 << 64) - 1
+
+
+# ------------------------------------------------------------------ synthetic data
+def _s64(v):
+    v &= MASK64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def synth_torch(seed, start, count, device):
+    """counter-based generator: splitmix64(seed, index) -> 24-bit uniform in [0,1)"""
+    import torch
+    z = torch.arange(start, start + count, dtype=torch.int64, device=device)
+    z = (z + _s64(seed * 0x632BE59BD9B4E019)) * _s64(0x9E3779B97F4A7C15)
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _s64(0x94D049BB133111EB)
+    z = z ^ ((z >> 31) & ((1 << 33) - 1))
+    return ((z >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / (1 << 24))
+
+
+def synth_numpy(seed, start, count):
+    with np.errstate(over="ignore"):
+        z = np.arange(start, start + count, dtype=np.uint64)
+        z = (z + np.uint64((seed * 0x632BE59BD9B4E019) & MASK64)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(40)) & np.uint64(0xFFFFFF)).astype(np.float32) * np.float32(1.0 / (1 << 24))
+
+
+def synth_rows_torch(seed, row0, rows, D, device):
+    import torch
+    out = torch.empty((rows, D), dtype=torch.float32, device=device)
+    step = 1 << 20
+    for r in range(0, rows, step):
+        n = min(step, rows - r)
+        out[r:r + n] = synth_torch(seed, (row0 + r) * D, n * D, device).view(n, D)
+    return out
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 6:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, t[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------ CPU legs (oracle/ is allowed here only)
+def _cpu_worker(args):
+    kind, codes, data, k = args
+    from oracle.pyoracle import Oracle, Reference
+    if kind == "reference":
+        t, _ = Reference().search_time_only(codes, data, k)
+        return t
+    o = Oracle()
+    t0 = time.perf_counter()
+    o.search(codes, data, k)
+    return time.perf_counter() - t0
+
+
+def cpu_searches_per_s(w, rows_per_core, cores, k):
+    """time the reference's own find_winner_euc/knn (oracle/_ref when it was built, else the
+    oracle port) on `cores` forked processes over disjoint slices of the same workload"""
+    import multiprocessing as mp
+    from oracle.pyoracle import Reference, build
+    kind = "reference" if Reference.available() else "port"
+    if kind == "port":
+        build(ref=False)
+    codes = synth_numpy(2, 0, w["M"] * w["D"]).reshape(w["M"], w["D"])
+    jobs = []
+    for c in range(cores):
+        data = synth_numpy(1, c * rows_per_core * w["D"], rows_per_core * w["D"]).reshape(rows_per_core, w["D"])
+        jobs.append((kind, codes, data, k))
+    t0 = time.perf_counter()
+    if cores == 1:
+        times = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            times = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    # all slices run concurrently: throughput = total rows / slowest slice
+    return rows_per_core * cores / max(times), kind, wall
+
+
+def main_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # ~1.6 k searches/s/core at C3: bound one step to a few seconds
+    rows_per_core = args.ref_rows or max(64, int(4.0 * 1600 * (10_000 * 64) / (w["M"] * w["D"])))
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, kind, _ = cpu_searches_per_s(w, rows_per_core, cores, w["k"])
+        if it >= args.warmup:
+            vals.append(v)
+    value = float(len(vals) / sum(1.0 / v for v in vals))
+    line = {
+        "impl": "reference", "metric": "BMU searches/s", "value": value, "unit": "searches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * rows_per_core * cores / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "rows_per_step": rows_per_core * cores, "D": w["D"],
+                   "M": w["M"], "k": w["k"]},
+        "cpu_baseline": {"value": value, "unit": "searches/s", "cores": cores, "kind": kind,
+                         "sample": "%d rows per core x %d forked processes of the same synthetic workload per step"
+                                   % (rows_per_core, cores)},
+        "e2e": {"value": value, "unit": "searches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------ GPU arm
+def main_gpu(args, w):
+    import torch
+    import torch.distributed as dist
+    import som_lvq_pak_b200 as bmu
+    from som_lvq_pak_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the BMU engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    bmu.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    rows, D, M, k = args.rows or w["rows"], w["D"], w["M"], w["k"]
+    # codebook: generated on rank 0, replicated by one broadcast
+    codes = synth_rows_torch(2, 0, M, D, dev) if rank == 0 else torch.empty((M, D), device=dev)
+    if world > 1:
+        dist.broadcast(codes, 0)
+    torch.cuda.synchronize()
+    cb = lib.bmu_codebook_create_dev(codes.data_ptr(), M, D)
+    if not cb:
+        raise SystemExit("bmu_codebook_create_dev: " + lib.bmu_last_error().decode())
+    data = synth_rows_torch(1, rank * rows, rows, D, dev)
+    idx = torch.empty((rows, k), dtype=torch.int32, device=dev)
+    diff = torch.empty((rows, k), dtype=torch.float32, device=dev)
+    nf = torch.empty(rows, dtype=torch.int32, device=dev)
+    stats = torch.zeros(2 + M, dtype=torch.float64, device=dev)      # [sum sqrt, n_found, hist...]
+    hist = torch.zeros(M, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        hist.zero_()
+        stats.zero_()
+        _lib.check(lib.bmu_search_dev(cb, data.data_ptr(), None, rows, k, idx.data_ptr(),
+                                      diff.data_ptr(), nf.data_ptr(), stream))
+        _lib.check(lib.bmu_search_stats_dev(idx.data_ptr(), diff.data_ptr(), nf.data_ptr(), rows, k,
+                                            M, stats.data_ptr(), hist.data_ptr(), None, None, 0,
+                                            None, stream))
+        if world > 1:
+            stats[2:] = hist.to(torch.float64)      # counts < 2^53: exact in float64
+            dist.all_reduce(stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    kms = (ctypes.c_float * 4)()
+
+    launches0 = lib.bmu_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.bmu_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    # duration of the dominant kernel, measured live with CUDA events on the launching stream
+    # (events bracket every kernel inside the library; read for the last timed step)
+    lib.bmu_last_search_kernel_ms(kms)
+    kernel_ms = [float(x) for x in kms]
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    else:
+        launches = int(launches)
+    value = world * rows * args.steps / (ms * 1e-3)
+    qsum, nfound = float(stats[0]), int(stats[1])
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (pinned), copies in the timed region
+    h_data = torch.empty((rows, D), dtype=torch.float32, pin_memory=True)
+    h_data.copy_(data)
+    h_idx = torch.empty((rows, k), dtype=torch.int32, pin_memory=True)
+    h_diff = torch.empty((rows, k), dtype=torch.float32, pin_memory=True)
+    h_nf = torch.empty(rows, dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        _lib.check(lib.bmu_search(cb, h_data.data_ptr(), None, rows, k, h_idx.data_ptr(),
+                                  h_diff.data_ptr(), h_nf.data_ptr()))
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * rows * e2e_steps / float(te[0])
+    same = bool((h_idx.to(dev) == idx).all()) and bool((h_diff.to(dev) == diff).all())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        info = bmu.device_info()
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        fp32_peak = info["sm_count"] * 128 * sm_max * 1e6 / 1e12          # T lane-ops/s, nominal
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        k_ms = kernel_ms[1] if kernel_ms[1] > 0 else kernel_ms[2]
+        kname = "k1_fast_kernel" if kernel_ms[1] > 0 else "k1_warp_kernel"
+        flop = 3.0 * M * D * rows                                          # 3*M*D per search
+        achieved = flop / (k_ms * 1e-3) / 1e12
+        hbm_bytes = rows * (4.0 * D + 12.0 * k)
+        line = {
+            "metric": "BMU searches/s", "value": value, "unit": "searches/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "rows_per_gpu": rows, "D": D, "M": M, "k": k,
+                       "parallelism": "data-sharded x%d, codebook replicated, 1 all-reduce of %d doubles per step"
+                                      % (world, 2 + M),
+                       "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB)" % (rows * D * 4 / 1e9),
+                       "search_path": "exact (K1)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "searches/s", "h2d_bytes_per_step": rows * D * 4,
+                    "d2h_bytes_per_step": rows * k * 8 + rows * 4, "steps": e2e_steps,
+                    "matches_device_resident_run": same},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp32_issue", "kernel": kname, "achieved": achieved, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                "kernel_ms": k_ms, "step_kernels_ms": {"data_prep": kernel_ms[0], "k1_fast": kernel_ms[1],
+                                                        "k1_warp": kernel_ms[2], "k1_seq": kernel_ms[3]},
+                "note": "exact path is bounded by the non-FMA FP32 issue rate, not HBM (SURVEY.md 8d): 3*M*D "
+                        "lane-ops per search; peak = SMs*128*sm_max_clock (nominal; tools/ubench/fp32_issue "
+                        "measured 36.8 T lane-ops/s on this pool)",
+                "hbm": {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
+            },
+            "result_check": {"mean_qerror": qsum / max(nfound, 1), "n_found": nfound},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            rpc = args.ref_rows or max(64, int(10.0 * 1600 * (10_000 * 64) / (M * D)))
+            v, kind, wall = cpu_searches_per_s(w, rpc, cores, k)
+            line["cpu_baseline"] = {"value": v, "unit": "searches/s", "cores": cores, "kind": kind,
+                                    "sample": "first %d rows per core x %d forked processes, same codebook "
+                                              "(reference find_winner_euc, gcc -O3), %.1f s wall"
+                                              % (rpc, cores, wall)}
+        print(json.dumps(line))
+    lib.bmu_codebook_destroy(cb)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
+    ap.add_argument("--ref-rows", type=int, default=0, help="override CPU sample rows per core")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return main_reference(args, w)
+    return main_gpu(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

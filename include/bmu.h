@@ -74,6 +74,9 @@ long bmu_launch_count(void);
  * [1] the warp-per-sample exact kernel, [2] the sequential-emulation kernel (non-finite or
  * sub-2^-40 inputs), [3] the K2 filter with a passed certificate, [4] K2 rows re-done by K1 */
 int bmu_last_search_breakdown(long out[5]);
+/* device time (ms, CUDA events on the launching stream) of the kernels of the last exact
+ * search: [0] data_prep, [1] k1_fast, [2] k1_warp, [3] k1_seq.  Synchronises on that call. */
+int bmu_last_search_kernel_ms(float out[4]);
 
 /* ---- codebook (replicated on every GPU; reference: struct entries *codes) --------- */
 typedef struct bmu_codebook bmu_codebook;

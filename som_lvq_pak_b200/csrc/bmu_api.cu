@@ -139,6 +139,11 @@ int bmu_set_search_path(int path) {
 
 long bmu_launch_count(void) { return k1_launch_count(); }
 
+int bmu_last_search_kernel_ms(float out[4]) {
+  CK(k1_last_kernel_ms(out));
+  return BMU_OK;
+}
+
 int bmu_last_search_breakdown(long out[5]) {
   for (int i = 0; i < 5; i++) out[i] = g_breakdown[i];
   return BMU_OK;

@@ -441,9 +441,28 @@ cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT
   return cudaGetLastError();
 }
 
+// CUDA events around each kernel of the last k1_search call, on the launching stream
+static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static bool g_ev_valid = false;
+
+cudaError_t k1_last_kernel_ms(float out[4]) {
+  for (int i = 0; i < 4; i++) out[i] = 0.0f;
+  if (!g_ev_valid) return cudaSuccess;
+  cudaError_t e = cudaEventSynchronize(g_ev[4]);
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < 4; i++) {
+    e = cudaEventElapsedTime(&out[i], g_ev[i], g_ev[i + 1]);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   static bool attr_set = false;
   cudaError_t e;
+  if (!g_ev[0])
+    for (int i = 0; i < 5; i++)
+      if ((e = cudaEventCreate(&g_ev[i])) != cudaSuccess) return e;
   if (!attr_set) {
     e = cudaFuncSetAttribute(k1_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)FastSmem::BYTES);
@@ -455,11 +474,13 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st);
   if (e != cudaSuccess) return e;
   const int want_tiles = (a.k == 1 && !a.skip_fast) ? 1 : 0;
+  cudaEventRecord(g_ev[0], st);
   data_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, a.cb_flags,
                                                      a.xT, a.flags, a.listW, a.listS, a.counters,
                                                      a.idx, a.diff, a.nfound, want_tiles);
   g_launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  cudaEventRecord(g_ev[1], st);
   if (want_tiles) {
     int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
     k1_fast_kernel<<<grid, 288, FastSmem::BYTES, st>>>(a.xT, a.cT, a.N, a.M, a.D, a.flags, a.idx,
@@ -467,6 +488,7 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  cudaEventRecord(g_ev[2], st);
   {
     long warps = a.k == 1 ? 8L * a.num_sms * 4 : a.N;   // k==1: only stragglers end up here
     if (warps > 8L * a.num_sms * 8) warps = 8L * a.num_sms * 8;
@@ -477,9 +499,12 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  cudaEventRecord(g_ev[3], st);
   k1_seq_kernel<<<a.num_sms * 2, 128, 0, st>>>(a.data, a.mask, a.codes, a.M, a.D, a.k, a.listS,
                                                a.counters + 1, a.idx, a.diff, a.nfound);
   g_launches++;
+  cudaEventRecord(g_ev[4], st);
+  g_ev_valid = true;
   return cudaGetLastError();
 }
 
