@@ -166,6 +166,10 @@ void bmu_som_schedule(long le0, long le1, long length, float alpha, float radius
                       int32_t *sample, float *talp, float *trad);
 void bmu_lvq_schedule(long le0, long le1, long length, float alpha, int alpha_type, long N,
                       const int32_t *order, int32_t *sample, float *talp);
+/* find_qerror's accumulator (som_rout.c:697,715): float q += sqrt((double)diff) over the found
+ * rows IN DATA ORDER -- the order-dependent float sum that makes qerror's stdout byte-exact.
+ * diff is N x k (first column used). */
+float bmu_replay_qerror(const float *diff, const int32_t *nfound, long N, int k);
 
 #ifdef __cplusplus
 }

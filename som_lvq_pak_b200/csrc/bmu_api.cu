@@ -423,4 +423,13 @@ void bmu_lvq_schedule(long le0, long le1, long length, float alpha, int alpha_ty
   }
 }
 
+float bmu_replay_qerror(const float *diff, const int32_t *nfound, long N, int k) {
+  float q = 0.0f;
+  for (long n = 0; n < N; n++) {
+    if (nfound[n] == 0) continue;
+    q = (float)((double)q + sqrt((double)diff[n * (long)k]));
+  }
+  return q;
+}
+
 }  // extern "C"

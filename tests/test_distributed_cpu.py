@@ -1,0 +1,87 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the sharded batch search -- shard
+bounds, the packed statistics all-reduce and the in-order gather for the host replay.
+The per-shard winners come from the oracle here (no GPU); on the GPU box the same functions
+run over NCCL inside bench.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def test_shard_bounds_cover_rows():
+    from som_lvq_pak_b200.distributed import shard_bounds
+    for n in (0, 1, 127, 128, 129, 1000, 10_000_000, 1962):
+        for world in (1, 2, 3, 4, 8):
+            b = [shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            for (l0, h0), (l1, h1) in zip(b, b[1:]):
+                assert h0 == l1 and l0 <= h0
+            sizes = [h - l for l, h in b]
+            assert max(sizes) - min(sizes) <= 256
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.pyoracle import Oracle
+    from som_lvq_pak_b200 import distributed as D
+    o = Oracle()
+    rng = np.random.default_rng(5)
+    M, dim, N, L = 40, 6, 1000, 4
+    codes = rng.random((M, dim), dtype=np.float32)
+    data = rng.random((N, dim), dtype=np.float32)
+    cl = rng.integers(0, L, M)
+    dl = rng.integers(0, L, N)
+    # "broadcast" of the codebook: rank 0's copy wins
+    ct = torch.from_numpy(codes.copy() if rank == 0 else np.zeros_like(codes))
+    dist.broadcast(ct, 0)
+    lo, hi = D.shard_bounds(N, rank, world)
+    idx, diff, ret = o.search(ct.numpy(), data[lo:hi], 1)
+    hist = np.bincount(idx[:, 0], minlength=M)
+    conf = np.zeros((L, L), np.int64)
+    np.add.at(conf, (dl[lo:hi], cl[idx[:, 0]]), 1)
+    vec = D.pack_stats(np.sqrt(diff[:, 0].astype(np.float64)).sum(), len(idx), hist, conf)
+    tot = D.unpack_stats(D.allreduce_stats(vec).numpy(), M, L)
+    allidx = D.gather_rows(torch.from_numpy(idx), N)
+    if rank == 0:
+        gidx, gdiff, _ = o.search(codes, data, 1)
+        assert tot["n_found"] == N
+        assert np.array_equal(tot["hist"], np.bincount(gidx[:, 0], minlength=M))
+        gconf = np.zeros((L, L), np.int64)
+        np.add.at(gconf, (dl, cl[gidx[:, 0]]), 1)
+        assert np.array_equal(tot["confusion"], gconf)
+        assert abs(tot["qsum"] - np.sqrt(gdiff[:, 0].astype(np.float64)).sum()) < 1e-9
+        assert np.array_equal(allidx.numpy(), gidx)
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_replay_qerror_is_the_sequential_float_sum():
+    import som_lvq_pak_b200 as b
+    from som_lvq_pak_b200 import _lib
+    rng = np.random.default_rng(1)
+    diff = rng.random((5000, 1), dtype=np.float32) * 30
+    nf = np.ones(5000, np.int32)
+    nf[::17] = 0
+    q = np.float32(0)
+    for d, f in zip(diff[:, 0], nf):
+        if f:
+            q = np.float32(np.float64(q) + np.sqrt(np.float64(d)))
+    got = _lib.load().bmu_replay_qerror(diff.ctypes.data, nf.ctypes.data, 5000, 1)
+    assert np.float32(got) == q
