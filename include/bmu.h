@@ -70,13 +70,16 @@ int bmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_op
 int bmu_set_search_path(int path);
 /* number of kernels this library has launched since bmu_init (bench.py: gpu_launches) */
 long bmu_launch_count(void);
-/* counters of the last bmu_search* call: rows answered by [0] the tile kernel K1-fast,
- * [1] the warp-per-sample exact kernel, [2] the sequential-emulation kernel (non-finite or
- * sub-2^-40 inputs), [3] the K2 filter with a passed certificate, [4] K2 rows re-done by K1 */
+/* counters of the last bmu_search_dev call (of the last chunk for bmu_search): [0] rows in the
+ * call, [1] rows answered by the warp-per-sample exact kernel (masked / tiny-magnitude rows,
+ * k >= 2 on the exact path, K2 certificate failures), [2] rows answered by the sequential
+ * emulation kernel (NaN/Inf), [3] rows certified by the K2 filter, [4] K2 rows whose
+ * certificate failed (re-done exactly, included in [1]).  Synchronises the device. */
 int bmu_last_search_breakdown(long out[5]);
-/* device time (ms, CUDA events on the launching stream) of the kernels of the last exact
- * search: [0] data_prep, [1] k1_fast, [2] k1_warp, [3] k1_seq.  Synchronises on that call. */
-int bmu_last_search_kernel_ms(float out[4]);
+/* device time (ms, CUDA events on the launching stream) of the kernels of the last search of
+ * each family: K1 [0] data_prep, [1] k1_fast, [2] k1_warp, [3] k1_seq; K2 [4] row_prep,
+ * [5] gemm + fused top-k, [6] exact re-rank, [7] K1 fallback lists.  Synchronises. */
+int bmu_last_search_kernel_ms(float out[8]);
 
 /* ---- codebook (replicated on every GPU; reference: struct entries *codes) --------- */
 typedef struct bmu_codebook bmu_codebook;

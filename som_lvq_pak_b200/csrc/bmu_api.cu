@@ -63,7 +63,9 @@ void Scratch::release() {
 namespace {
 
 int g_path = BMU_PATH_AUTO;
-long g_breakdown[5] = {0, 0, 0, 0, 0};
+const int *g_last_counters = nullptr;     // device counters of the last search call
+long g_last_rows = 0;
+int g_last_used_k2 = 0;
 
 struct SearchScratch {
   Scratch xT, flags, listW, listS, counters, k2;
@@ -139,13 +141,23 @@ int bmu_set_search_path(int path) {
 
 long bmu_launch_count(void) { return k1_launch_count(); }
 
-int bmu_last_search_kernel_ms(float out[4]) {
+int bmu_last_search_kernel_ms(float out[8]) {
   CK(k1_last_kernel_ms(out));
+  CK(k2_last_kernel_ms(out + 4));
   return BMU_OK;
 }
 
 int bmu_last_search_breakdown(long out[5]) {
-  for (int i = 0; i < 5; i++) out[i] = g_breakdown[i];
+  for (int i = 0; i < 5; i++) out[i] = 0;
+  if (!g_last_counters) return BMU_OK;
+  int h[4];
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h, g_last_counters, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = g_last_rows;
+  out[1] = h[0];
+  out[2] = h[1];
+  out[3] = g_last_used_k2 ? h[2] : 0;
+  out[4] = g_last_used_k2 ? h[3] : 0;
   return BMU_OK;
 }
 
@@ -240,6 +252,9 @@ static int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned
   a.xT = (float *)ss.xT.p; a.flags = (unsigned char *)ss.flags.p;
   a.listW = (int *)ss.listW.p; a.listS = (int *)ss.listS.p; a.counters = (int *)ss.counters.p;
   a.idx = d_idx; a.diff = d_diff; a.nfound = d_nfound;
+  g_last_counters = a.counters;
+  g_last_rows = N;
+  g_last_used_k2 = use_k2 ? 1 : 0;
   if (use_k2) {
     cudaError_t e = k2_search(&cb->k2, a, &ss.k2.p, &ss.k2.bytes, st);
     if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k2_search: %s", cudaGetErrorString(e));

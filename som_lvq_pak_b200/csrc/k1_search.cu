@@ -489,23 +489,37 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   cudaEventRecord(g_ev[2], st);
-  {
-    long warps = a.k == 1 ? 8L * a.num_sms * 4 : a.N;   // k==1: only stragglers end up here
-    if (warps > 8L * a.num_sms * 8) warps = 8L * a.num_sms * 8;
-    if (warps < 8) warps = 8;
-    int grid = (int)((warps + 7) / 8);
-    k1_warp_kernel<<<grid, 256, 0, st>>>(a.data, a.mask, a.cT, a.M, a.D, a.k, a.listW,
-                                         a.counters + 0, a.idx, a.diff, a.nfound);
-    g_launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
+  if ((e = k1_run_warp_list(a, st)) != cudaSuccess) return e;
   cudaEventRecord(g_ev[3], st);
+  if ((e = k1_run_seq_list(a, st)) != cudaSuccess) return e;
+  cudaEventRecord(g_ev[4], st);
+  g_ev_valid = true;
+  return cudaSuccess;
+}
+
+// rows in listW (count in counters[0]): masked / tiny rows, k >= 2 rows, K2 certificate failures
+cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
+  long warps = a.N < 8L * a.num_sms * 8 ? a.N : 8L * a.num_sms * 8;   // persistent over the list
+  if (warps < 8) warps = 8;
+  int grid = (int)((warps + 7) / 8);
+  k1_warp_kernel<<<grid, 256, 0, st>>>(a.data, a.mask, a.cT, a.M, a.D, a.k, a.listW,
+                                       a.counters + 0, a.idx, a.diff, a.nfound);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// rows in listS (count in counters[1]): NaN / Inf inputs
+cudaError_t k1_run_seq_list(const K1Args &a, cudaStream_t st) {
   k1_seq_kernel<<<a.num_sms * 2, 128, 0, st>>>(a.data, a.mask, a.codes, a.M, a.D, a.k, a.listS,
                                                a.counters + 1, a.idx, a.diff, a.nfound);
   g_launches++;
-  cudaEventRecord(g_ev[4], st);
-  g_ev_valid = true;
   return cudaGetLastError();
+}
+
+cudaError_t k1_run_lists(const K1Args &a, cudaStream_t st) {
+  cudaError_t e = k1_run_warp_list(a, st);
+  if (e != cudaSuccess) return e;
+  return k1_run_seq_list(a, st);
 }
 
 }  // namespace bmu

@@ -36,6 +36,9 @@ size_t k1_xT_floats(long N, int D);
 cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT,
                                 unsigned *d_cb_flags, cudaStream_t st);
 cudaError_t k1_search(const K1Args &a, cudaStream_t st);
+cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st);
+cudaError_t k1_run_seq_list(const K1Args &a, cudaStream_t st);
+cudaError_t k1_run_lists(const K1Args &a, cudaStream_t st);
 // device time of [data_prep, k1_fast, k1_warp, k1_seq] of the last k1_search call (ms)
 cudaError_t k1_last_kernel_ms(float out[4]);
 long k1_launch_count();

@@ -11,13 +11,15 @@ struct K2Codebook {
   float *d_norm = nullptr;      // per code: ||m||^2 and error-bound terms
   size_t ops_bytes = 0;
   int valid = 0;
-  int Kpad = 0;
+  int Kp = 0;
 };
 
 bool k2_eligible(int path, long M, int D, long N, int k, unsigned cb_flags);
 void k2_codebook_invalidate(K2Codebook *c);
 void k2_codebook_free(K2Codebook *c);
 // scratch: grow-only device buffer owned by the caller
+// device time of [row_prep, gemm, rerank, fallback lists] of the last k2_search call (ms)
+cudaError_t k2_last_kernel_ms(float out[4]);
 cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *scratch_bytes,
                       cudaStream_t st);
 

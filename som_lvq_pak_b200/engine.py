@@ -51,6 +51,19 @@ def launch_count():
     return _lib.load().bmu_launch_count()
 
 
+def last_search_breakdown():
+    out = (C.c_long * 5)()
+    _lib.check(_lib.load().bmu_last_search_breakdown(out))
+    return dict(zip(("rows", "warp_rows", "seq_rows", "k2_certified", "k2_failed"), [int(v) for v in out]))
+
+
+def last_search_kernel_ms():
+    out = (C.c_float * 8)()
+    _lib.check(_lib.load().bmu_last_search_kernel_ms(out))
+    names = ("k1_data_prep", "k1_fast", "k1_warp", "k1_seq", "k2_row_prep", "k2_gemm", "k2_rerank", "k2_lists")
+    return dict(zip(names, [float(v) for v in out]))
+
+
 class Codebook:
     """A codebook resident on the GPU (reference: struct entries *codes)."""
 

@@ -20,7 +20,7 @@ def check(engine, codes, data, k, mask, exp, what):
     assert_bits_equal(nf, exp[2], what + " ret")
 
 
-@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("path", [1, 0, 2])
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("k", [1, 2, 5, 10])
 def test_search_golden(engine, golden, shape, k, path):
@@ -38,7 +38,7 @@ def test_search_golden(engine, golden, shape, k, path):
         engine.set_search_path(0)
 
 
-@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("path", [1, 0, 2])
 @pytest.mark.parametrize("M,D,N", [(96, 5, 3840), (200, 20, 1962), (1000, 64, 4096), (10000, 64, 1500),
                                    (4096, 512, 300), (129, 7, 130), (1, 3, 10), (300, 100, 257)])
 def test_search_vs_oracle_random(engine, oracle, M, D, N, path):
@@ -53,7 +53,7 @@ def test_search_vs_oracle_random(engine, oracle, M, D, N, path):
         engine.set_search_path(0)
 
 
-@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("path", [1, 0, 2])
 def test_search_adversarial(engine, oracle, path):
     """exact ties, duplicated code vectors, masks, subnormal-scale values, huge values"""
     rng = np.random.default_rng(7)
@@ -107,3 +107,22 @@ def test_search_chunked_host_path(engine, oracle):
     d64 = ((data[s, None, :].astype(np.float64) - codes[None].astype(np.float64)) ** 2).sum(-1)
     assert np.allclose(d64[np.arange(500), idx[s, 0]], diff[s, 0], rtol=1e-5)
     assert (d64.min(1) >= diff[s, 0] * (1 - 1e-5)).all()
+
+
+def test_filter_path_certifies_most_rows(engine, oracle):
+    """the tensor-core filter must actually answer the rows (not silently fall back to K1)"""
+    rng = np.random.default_rng(21)
+    for M, D, N, k in [(10000, 64, 8192, 1), (4096, 512, 2048, 1), (4096, 512, 1024, 5), (2000, 20, 4096, 1)]:
+        codes = rng.random((M, D), dtype=np.float32) + np.float32(3.0)      # offset: centring matters
+        data = rng.random((N, D), dtype=np.float32) + np.float32(3.0)
+        engine.set_search_path(2)
+        try:
+            idx, diff, nf = engine.find_winner_knn(codes, data, k)
+            bd = engine.last_search_breakdown()
+        finally:
+            engine.set_search_path(0)
+        e = oracle.search(codes, data, k)
+        assert_bits_equal(idx, e[0], "k2 idx M=%d D=%d k=%d" % (M, D, k))
+        assert_bits_equal(diff, e[1], "k2 diff")
+        assert bd["k2_certified"] >= 0.97 * N, bd
+        assert bd["k2_certified"] + bd["k2_failed"] == N, bd
