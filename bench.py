@@ -210,6 +210,7 @@ def main_gpu(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    _lib.check(lib.bmu_set_search_path({"auto": 0, "exact": 1, "filter": 2}[args.path]))
 
     rows, D, M, k = args.rows or w["rows"], w["D"], w["M"], w["k"]
     # codebook: generated on rank 0, replicated by one broadcast
@@ -248,7 +249,7 @@ def main_gpu(args, w):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    kms = (ctypes.c_float * 4)()
+    kms = (ctypes.c_float * 8)()
 
     launches0 = lib.bmu_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -314,11 +315,42 @@ def main_gpu(args, w):
         sm_max = peaks.get("sm_max_mhz", 1965.0)
         fp32_peak = info["sm_count"] * 128 * sm_max * 1e6 / 1e12          # T lane-ops/s, nominal
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        k_ms = kernel_ms[1] if kernel_ms[1] > 0 else kernel_ms[2]
-        kname = "k1_fast_kernel" if kernel_ms[1] > 0 else "k1_warp_kernel"
-        flop = 3.0 * M * D * rows                                          # 3*M*D per search
-        achieved = flop / (k_ms * 1e-3) / 1e12
+        bd = bmu.last_search_breakdown()
+        used_k2 = bd["k2_certified"] + bd["k2_failed"] > 0
+        names = ("k1_data_prep", "k1_fast", "k1_warp", "k1_seq", "k2_row_prep", "k2_gemm", "k2_rerank", "k2_lists")
+        step_ms = {n: v for n, v in zip(names, kernel_ms) if (n.startswith("k2") == used_k2)}
         hbm_bytes = rows * (4.0 * D + 12.0 * k)
+        if used_k2:
+            k_ms, kname = kernel_ms[5], "k2_gemm_kernel"
+            flop = 2.0 * M * D * rows                                      # 2*M*D per search
+            achieved = flop / (k_ms * 1e-3) / 1e12
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            kp = (3 * ((D + 7) // 8 * 8) + 3 + 15) // 16 * 16
+            roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "step_kernels_ms": step_ms,
+                    "note": "algorithmic 2*M*D flop per search vs the measured sustained bf16 peak (%s); the "
+                            "kernel issues %.2fx that many MMA flops (3-term bf16 split + norm columns, K %d -> %d), "
+                            "so the tensor pipe itself runs at %.3f of peak"
+                            % ("measured" if "bf16_tflops_sustained" in peaks else "fallback", kp / D, D, kp,
+                               achieved * kp / D / peak),
+                    "mma_issued_tflops": achieved * kp / D,
+                    "rows_certified": bd["k2_certified"], "rows_redone_exactly": bd["k2_failed"]}
+            search_path = "filter (K2 tcgen05 GEMM + exact re-rank, K1 for uncertified rows)"
+        else:
+            k_ms = kernel_ms[1] if kernel_ms[1] > 0 else kernel_ms[2]
+            kname = "k1_fast_kernel" if kernel_ms[1] > 0 else "k1_warp_kernel"
+            flop = 3.0 * M * D * rows                                      # 3*M*D per search
+            achieved = flop / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "fp32_issue", "kernel": kname, "achieved": achieved, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None, "kernel_ms": k_ms,
+                    "step_kernels_ms": step_ms,
+                    "note": "exact path is bounded by the non-FMA FP32 issue rate, not HBM (SURVEY.md 8d): 3*M*D "
+                            "lane-ops per search; peak = SMs*128*sm_max_clock (nominal; tools/ubench/fp32_issue "
+                            "measured 36.8 T lane-ops/s on this pool)"}
+            search_path = "exact (K1)"
+        roof["hbm"] = {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                       "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}
         line = {
             "metric": "BMU searches/s", "value": value, "unit": "searches/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -328,24 +360,13 @@ def main_gpu(args, w):
                        "parallelism": "data-sharded x%d, codebook replicated, 1 all-reduce of %d doubles per step"
                                       % (world, 2 + M),
                        "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB)" % (rows * D * 4 / 1e9),
-                       "search_path": "exact (K1)"},
+                       "search_path": search_path},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "searches/s", "h2d_bytes_per_step": rows * D * 4,
                     "d2h_bytes_per_step": rows * k * 8 + rows * 4, "steps": e2e_steps,
                     "matches_device_resident_run": same},
             "gpu_launches": launches,
-            "roofline": {
-                "bound": "fp32_issue", "kernel": kname, "achieved": achieved, "peak": fp32_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
-                "kernel_ms": k_ms, "step_kernels_ms": {"data_prep": kernel_ms[0], "k1_fast": kernel_ms[1],
-                                                        "k1_warp": kernel_ms[2], "k1_seq": kernel_ms[3]},
-                "note": "exact path is bounded by the non-FMA FP32 issue rate, not HBM (SURVEY.md 8d): 3*M*D "
-                        "lane-ops per search; peak = SMs*128*sm_max_clock (nominal; tools/ubench/fp32_issue "
-                        "measured 36.8 T lane-ops/s on this pool)",
-                "hbm": {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"},
-            },
+            "roofline": roof,
             "result_check": {"mean_qerror": qsum / max(nfound, 1), "n_found": nfound},
         }
         if world == 1 and not args.no_cpu:
@@ -373,6 +394,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--ref-rows", type=int, default=0, help="override CPU sample rows per core")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--path", default="auto", choices=["auto", "exact", "filter"],
+                    help="search kernels: auto (default), exact = K1 only, filter = K2 forced")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -296,15 +296,24 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
                const float *__restrict__ cT, long M, int D, int k, const int *__restrict__ list,
                const int *__restrict__ count, int32_t *__restrict__ idx,
                float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  const int lane = threadIdx.x & 31;
-  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ float sl_d[8][BMU_KMAX_];
+  __shared__ int sl_i[8][BMU_KMAX_];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cnt = *count;
   const int nct = (int)((M + K1_TC - 1) / K1_TC);
   const bool knn_rule = k > 1;
+  // short lists (K2 certificate failures, a few masked rows): S warps of a CTA share one row
+  // and split its code tiles, so that the tail does not run at one warp per SM
+  int S = 1;
+  const long total_warps = (long)gridDim.x * 8;
+  while (S < 8 && S * 2 <= nct && (long)cnt * S * 2 <= total_warps) S *= 2;
+  const int rows_per_cta = 8 / S;
+  const int rloc = warp / S, sub = warp % S;
 
-  for (int w = wglobal; w < cnt; w += nwarps) {
-    const long n = list[w];
+  for (long base = (long)blockIdx.x * rows_per_cta; base < cnt; base += (long)gridDim.x * rows_per_cta) {
+    const long w = base + rloc;
+    const bool valid = w < cnt;
+    const long n = valid ? list[w] : 0;
     const float *x = data + n * (long)D;
     const unsigned char *mk = mask ? mask + n * (long)D : nullptr;
     float ld[BMU_KMAX_];
@@ -312,17 +321,30 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
 #pragma unroll
     for (int t = 0; t < BMU_KMAX_; t++) { ld[t] = FLT_MAX; li[t] = -1; }
 
-    for (int ct = 0; ct < nct; ct++) {
-      const float *cbase = cT + (long)ct * D * K1_TC;
+    if (valid)
+    for (int ct = sub; ct < nct; ct += S) {
+      const float *cbase = cT + (long)ct * D * K1_TC + lane;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int i = 0; i < D; i++) {
-        if (mk && mk[i]) continue;       // warp-uniform
-        const float xi = __ldg(x + i);
-        const float *cr = cbase + (long)i * K1_TC + lane;
-        a0 = sq_acc(a0, cr[0], xi);
-        a1 = sq_acc(a1, cr[32], xi);
-        a2 = sq_acc(a2, cr[64], xi);
-        a3 = sq_acc(a3, cr[96], xi);
+      if (mk) {
+        for (int i = 0; i < D; i++) {
+          if (mk[i]) continue;           // warp-uniform
+          const float xi = __ldg(x + i);
+          const float *cr = cbase + (long)i * K1_TC;
+          a0 = sq_acc(a0, cr[0], xi);
+          a1 = sq_acc(a1, cr[32], xi);
+          a2 = sq_acc(a2, cr[64], xi);
+          a3 = sq_acc(a3, cr[96], xi);
+        }
+      } else {
+#pragma unroll 4
+        for (int i = 0; i < D; i++) {
+          const float xi = __ldg(x + i);
+          const float *cr = cbase + (long)i * K1_TC;
+          a0 = sq_acc(a0, cr[0], xi);
+          a1 = sq_acc(a1, cr[32], xi);
+          a2 = sq_acc(a2, cr[64], xi);
+          a3 = sq_acc(a3, cr[96], xi);
+        }
       }
       float av[4] = {a0, a1, a2, a3};
 #pragma unroll
@@ -361,7 +383,23 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
         if (take) { bd = od; bj = oj; }
       }
       if (bj >= 0 && bj == j) head++;     // exactly one lane owns code bj
-      if (lane == 0) {
+      if (lane == 0) { sl_d[warp][t] = bd; sl_i[warp][t] = bj; }
+    }
+    __syncthreads();
+    if (valid && sub == 0 && lane == 0) {
+      // merge the S sorted lists of this row's warps
+      int hp[8];
+      for (int q = 0; q < S; q++) hp[q] = 0;
+      for (int t = 0; t < k; t++) {
+        float bd = FLT_MAX; int bj = -1, bq = -1;
+        for (int q = 0; q < S; q++) {
+          if (hp[q] >= k) continue;
+          const float od = sl_d[warp + q][hp[q]];
+          const int oj = sl_i[warp + q][hp[q]];
+          if (oj < 0) continue;
+          if (bj < 0 || od < bd || (od == bd && (knn_rule ? oj > bj : oj < bj))) { bd = od; bj = oj; bq = q; }
+        }
+        if (bq >= 0) hp[bq]++;
         if (k == 1) {
           idx[n] = bj;
           diff[n] = bj >= 0 ? bd : -1.0f;
@@ -370,8 +408,9 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
           diff[n * k + t] = bj >= 0 ? bd : FLT_MAX;
         }
       }
+      nfound[n] = k;
     }
-    if (lane == 0) nfound[n] = k;
+    __syncthreads();
   }
 }
 

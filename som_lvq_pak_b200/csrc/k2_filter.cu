@@ -135,77 +135,135 @@ __device__ __forceinline__ unsigned k2_classify(float v) {
   return f;
 }
 
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);      // .x = lo (low 16 bits), .y = hi
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+constexpr int K2_PS = 32;     // components per row-prep slab
+
 __global__ void __launch_bounds__(256)
 k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restrict__ mask, long N,
                    int D, int k, const float *__restrict__ mean, __nv_bfloat16 *__restrict__ Aimg,
                    RowStats *__restrict__ rs, unsigned char *__restrict__ flags,
                    int *__restrict__ listW, int *__restrict__ listS, int *__restrict__ counters,
                    int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
+  // staged through shared memory so that both the row reads and the image writes are coalesced
+  __shared__ float xs[K2_TM][K2_PS + 1];                      // centred inputs of the slab
+  __shared__ unsigned char ms[K2_TM][K2_PS];                  // mask bytes of the slab
+  __shared__ __align__(16) uint4 img_s[3][K2_PS / 8][K2_TM];  // three image regions of the slab
+  // row-combine scratch aliases the image staging buffer (used only after the slab loop)
+  double (*red)[3] = reinterpret_cast<double (*)[3]>(&img_s[0][0][0]);
+  int (*redi)[2] = reinterpret_cast<int (*)[2]>(&img_s[1][0][0]);
   const int Dp = k2_dp(D), Kp = k2_kp(D);
   const long tile = blockIdx.x;
   const long n0 = tile * K2_TM;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __nv_bfloat16 *img = Aimg + tile * (long)K2_TM * Kp;        // [kc][128][8]
-  // zero the image of this tile (pads, rows beyond N, masked rows)
-  {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    uint4 *p = reinterpret_cast<uint4 *>(img);
-    for (long t = threadIdx.x; t < (long)K2_TM * Kp / 8; t += 256) p[t] = z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (K2_TM - 1), half = tid >> 7;           // thread = (row, 16-component half)
+  uint4 *img = reinterpret_cast<uint4 *>(Aimg + tile * (long)K2_TM * Kp);   // [kc][128] uint4
+  const long nrow = n0 + row;
+  double n2 = 0.0, nlo2 = 0.0, nr2 = 0.0;
+  unsigned f = 0;
+  int nmasked = 0;
+
+  for (int d0 = 0; d0 < Dp; d0 += K2_PS) {
+    __syncthreads();
+    // phase 1: coalesced load of 128 rows x 32 components, centred
+    for (int r = warp; r < K2_TM; r += 8) {
+      const long n = n0 + r;
+      const int i = d0 + lane;
+      float v = 0.0f;
+      unsigned char mk = 1;                                     // beyond D / N counts as "masked" (zero)
+      if (n < N && i < D) {
+        v = data[n * (long)D + i];
+        mk = mask ? mask[n * (long)D + i] : 0;
+      }
+      xs[r][lane] = v;
+      ms[r][lane] = mk;
+    }
+    __syncthreads();
+    // phase 2: split; each thread packs 2 x 8 components of one row
+#pragma unroll
+    for (int grp = 0; grp < 2; grp++) {
+      uint32_t hi_w[4], lo_w[4];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        float hv[2], lv[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int il = half * 16 + grp * 8 + p * 2 + q;
+          const int i = d0 + il;
+          hv[q] = 0.0f; lv[q] = 0.0f;
+          if (i < D && nrow < N) {
+            if (ms[row][il]) { nmasked++; }
+            else {
+              const float v = xs[row][il];
+              f |= k2_classify(v);
+              const float c = __fsub_rn(v, mean[i]);
+              const __nv_bfloat16 h = __float2bfloat16(c);
+              const float lo_f = __fsub_rn(c, __bfloat162float(h));
+              const __nv_bfloat16 l = __float2bfloat16(lo_f);
+              const float res = __fsub_rn(lo_f, __bfloat162float(l));
+              hv[q] = __bfloat162float(h);
+              lv[q] = __bfloat162float(l);
+              n2 += (double)c * c;
+              nlo2 += (double)lv[q] * lv[q];
+              nr2 += (double)res * res;
+            }
+          }
+        }
+        hi_w[p] = bf16x2_bits(hv[0], hv[1]);
+        lo_w[p] = bf16x2_bits(lv[0], lv[1]);
+      }
+      const int ch = half * 2 + grp;                            // chunk of 8 inside the slab
+      const uint4 hq = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+      const uint4 lq = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+      img_s[0][ch][row] = hq;       // x_hi against -2 m_hi
+      img_s[1][ch][row] = hq;       // x_hi against -2 m_lo
+      img_s[2][ch][row] = lq;       // x_lo against -2 m_hi
+    }
+    __syncthreads();
+    // phase 3: the three regions are contiguous runs of (chunks x 128) uint4 in the image
+    const int nch = min(K2_PS, Dp - d0) / 8;
+    for (int t = tid; t < 3 * nch * K2_TM; t += 256) {
+      const int reg = t / (nch * K2_TM), rem = t % (nch * K2_TM);
+      const int ch = rem / K2_TM, r = rem % K2_TM;
+      img[((long)(reg * Dp + d0) / 8 + ch) * K2_TM + r] = img_s[reg][ch][r];
+    }
   }
+  // tail: the column(s) of ones that pick up ||m'||^2, then zero padding up to Kp
+  for (int t = tid; t < (Kp - 3 * Dp) / 8 * K2_TM; t += 256) {
+    const int ch = t / K2_TM, r = t % K2_TM;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ch == 0 && n0 + r < N) { v.x = bf16x2_bits(1.0f, 1.0f); v.y = bf16x2_bits(1.0f, 0.0f); }
+    img[((long)(3 * Dp) / 8 + ch) * K2_TM + r] = v;
+  }
+  // combine the two halves of every row
   __syncthreads();
-  for (int r = warp; r < K2_TM; r += 8) {
-    const long n = n0 + r;
-    if (n >= N) break;
-    const float *row = data + n * (long)D;
-    const unsigned char *mrow = mask ? mask + n * (long)D : nullptr;
-    unsigned f = 0;
-    int nmasked = 0;
-    double n2 = 0.0, nlo2 = 0.0, nr2 = 0.0;
-    auto put = [&](int kk, float v) { img[((long)(kk >> 3) * K2_TM + r) * 8 + (kk & 7)] = __float2bfloat16(v); };
-    for (int i = lane; i < D; i += 32) {
-      if (mrow && mrow[i]) { nmasked++; continue; }
-      const float v = row[i];
-      f |= k2_classify(v);
-      float c = __fsub_rn(v, mean[i]);
-      __nv_bfloat16 h = __float2bfloat16(c);
-      float lo_f = __fsub_rn(c, __bfloat162float(h));
-      __nv_bfloat16 l = __float2bfloat16(lo_f);
-      float res = __fsub_rn(lo_f, __bfloat162float(l));
-      put(i, __bfloat162float(h));
-      put(Dp + i, __bfloat162float(h));
-      put(2 * Dp + i, __bfloat162float(l));
-      n2 += (double)c * c;
-      nlo2 += (double)__bfloat162float(l) * __bfloat162float(l);
-      nr2 += (double)res * res;
-    }
-    f = __reduce_or_sync(0xffffffffu, f);
-    nmasked = __reduce_add_sync(0xffffffffu, nmasked);
-    for (int off = 16; off >= 1; off >>= 1) {
-      n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-      nlo2 += __shfl_xor_sync(0xffffffffu, nlo2, off);
-      nr2 += __shfl_xor_sync(0xffffffffu, nr2, off);
-    }
+  if (half == 1) { red[row][0] = n2; red[row][1] = nlo2; red[row][2] = nr2; redi[row][0] = (int)f; redi[row][1] = nmasked; }
+  __syncthreads();
+  if (half == 0 && nrow < N) {
+    n2 += red[row][0]; nlo2 += red[row][1]; nr2 += red[row][2];
+    f |= (unsigned)redi[row][0]; nmasked += redi[row][1];
     if (nmasked > 0) f |= ROW_MASKED;
     if (nmasked == D) f |= ROW_ALLMASKED;
-    if (lane < 3) put(3 * Dp + lane, 1.0f);         // the column of ones that picks up ||m'||^2
-    if (lane == 0) {
-      flags[n] = (unsigned char)f;
-      RowStats s;
-      const float up = 1.0001f;
-      s.nx2 = n2;
-      s.nx = (float)sqrt(n2) * up;
-      s.nxlo = (float)sqrt(nlo2) * up;
-      s.nrx = (float)sqrt(nr2) * up;
-      s.pad = 0.0f;
-      rs[n] = s;
-      if (f & ROW_ALLMASKED) {
-        nfound[n] = 0;
-        for (int t = 0; t < k; t++) { idx[n * k + t] = -1; diff[n * k + t] = (k == 1) ? -1.0f : FLT_MAX; }
-      } else if (f & ROW_NONFINITE) {
-        listS[atomicAdd(&counters[1], 1)] = (int)n;
-      } else if (f & (ROW_TINY | ROW_MASKED)) {
-        listW[atomicAdd(&counters[0], 1)] = (int)n;
-      }
+    const long n = nrow;
+    flags[n] = (unsigned char)f;
+    RowStats s;
+    const float up = 1.0001f;
+    s.nx2 = n2;
+    s.nx = (float)sqrt(n2) * up;
+    s.nxlo = (float)sqrt(nlo2) * up;
+    s.nrx = (float)sqrt(nr2) * up;
+    s.pad = 0.0f;
+    rs[n] = s;
+    if (f & ROW_ALLMASKED) {
+      nfound[n] = 0;
+      for (int t = 0; t < k; t++) { idx[n * k + t] = -1; diff[n * k + t] = (k == 1) ? -1.0f : FLT_MAX; }
+    } else if (f & ROW_NONFINITE) {
+      listS[atomicAdd(&counters[1], 1)] = (int)n;
+    } else if (f & (ROW_TINY | ROW_MASKED)) {
+      listW[atomicAdd(&counters[0], 1)] = (int)n;
     }
   }
 }
@@ -429,30 +487,59 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
 }
 
 // ---------------------------------------------------------------- exact re-rank + certificate
-template <int TG>
+// LPR lanes per row (power of two >= TG): lane g of a row's group computes the exact distance
+// of candidate g, so the loads of x are shared by the group and every lane streams one code
+// row; the group leader then orders the candidates and evaluates the certificate.
+template <int TG, int LPR>
 __global__ void __launch_bounds__(256)
 k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M, int D,
                  int k, int Kp, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
                  const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
                  const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
                  int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  const long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  if (flags[n] != 0) return;                     // answered by K1 (lists built in row prep)
-  const float *x = data + n * (long)D;
+  constexpr int RPW = 32 / LPR;                         // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int g = lane % LPR;
+  const long warp_id = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long n = warp_id * RPW + lane / LPR;
+  const bool row_ok = n < N && flags[n] == 0;           // other rows are answered by K1
+  float myd = INFINITY;
+  int myj = -1;
+  if (row_ok && g < TG) {
+    const int j = cand[n * TG + g];
+    if (j >= 0 && j < M) {
+      const float *x = data + n * (long)D;
+      const float *c = codes + (long)j * D;
+      float acc = 0.0f;
+      if ((D & 3) == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        const float4 *c4 = reinterpret_cast<const float4 *>(c);
+#pragma unroll 4
+        for (int i = 0; i < D / 4; i++) {
+          const float4 xv = x4[i], cv = __ldg(c4 + i);
+          acc = sq_acc(acc, cv.x, xv.x);               // the reference's sum, component order
+          acc = sq_acc(acc, cv.y, xv.y);
+          acc = sq_acc(acc, cv.z, xv.z);
+          acc = sq_acc(acc, cv.w, xv.w);
+        }
+      } else {
+        for (int i = 0; i < D; i++) acc = sq_acc(acc, __ldg(c + i), x[i]);
+      }
+      myd = acc;
+      myj = j;
+    }
+  }
+  // gather the group's results on every lane (only the leader uses them)
   float cd[TG];
   int ci[TG];
   int nc = 0;
 #pragma unroll
   for (int t = 0; t < TG; t++) {
-    const int j = cand[n * TG + t];
-    cd[t] = INFINITY; ci[t] = -1;
-    if (j < 0 || j >= M) continue;
-    const float *c = codes + (long)j * D;
-    float acc = 0.0f;
-    for (int i = 0; i < D; i++) acc = sq_acc(acc, c[i], x[i]);     // the reference's sum
-    cd[t] = acc; ci[t] = j; nc++;
+    cd[t] = __shfl_sync(0xffffffffu, myd, (lane / LPR) * LPR + t);
+    ci[t] = __shfl_sync(0xffffffffu, myj, (lane / LPR) * LPR + t);
+    if (ci[t] >= 0) nc++; else cd[t] = INFINITY;
   }
+  if (!row_ok || g != 0) return;
   // order by the reference's rule: k == 1 -> (diff asc, idx asc), k >= 2 -> (diff asc, idx desc)
   const bool knn_rule = k > 1;
 #pragma unroll
@@ -578,7 +665,9 @@ static cudaError_t k2_run(K2Codebook *c, const K1Args &a, const K2Scratch &s, cu
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
-  k2_rerank_kernel<TG><<<(unsigned)((a.N + 255) / 256), 256, 0, st>>>(
+  constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
+  const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
+  k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
       a.data, a.codes, a.N, a.M, a.D, a.k, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
       a.listW, a.counters, a.idx, a.diff, a.nfound);
   k1_count_launch(1);
