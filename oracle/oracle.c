@@ -183,10 +183,20 @@ int orc_som_train(float *codes, long M, int D, int xdim, int ydim, int topol, in
                   const short *fixed_xy, long N, const int *order,
                   long length, float alpha, float radius, int alpha_type)
 {
+  return orc_som_train_prefix(codes, M, D, xdim, ydim, topol, neigh, data, mask, weight, fixed_xy,
+                              N, order, length, length, alpha, radius, alpha_type);
+}
+
+/* the first `nsteps` steps of a run of `length` steps (schedules depend on length) */
+int orc_som_train_prefix(float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
+                         const float *data, const unsigned char *mask, const short *weight,
+                         const short *fixed_xy, long N, const int *order,
+                         long length, long nsteps, float alpha, float radius, int alpha_type)
+{
   long le, pos = 0, u;
   (void)ydim;
   if (N <= 0) return 1;
-  for (le = 0; le < length; le++, pos++) {
+  for (le = 0; le < nsteps; le++, pos++) {
     long s;
     const float *x;
     const unsigned char *mk;

@@ -56,6 +56,11 @@ int orc_som_train(float *codes, long M, int D, int xdim, int ydim, int topol, in
                   const short *fixed_xy, long N, const int *order,
                   long length, float alpha, float radius, int alpha_type);
 
+int orc_som_train_prefix(float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
+                         const float *data, const unsigned char *mask, const short *weight,
+                         const short *fixed_xy, long N, const int *order,
+                         long length, long nsteps, float alpha, float radius, int alpha_type);
+
 /* som_rout.c:678-731 (qetype 0) and 734-891 (qetype 1) */
 float orc_qerror(const float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
                  const float *data, const unsigned char *mask, long N, int qetype, float radius);

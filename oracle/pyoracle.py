@@ -138,6 +138,22 @@ class Oracle(_Lib):
             raise RuntimeError("orc_som_train failed")
         return codes
 
+    def som_train_prefix(self, codes, data, xdim, ydim, topol, neigh, length, nsteps, alpha, radius,
+                         alpha_type=1, order=None):
+        codes = _f32(codes).copy()
+        data = _f32(data)
+        M, D = codes.shape
+        order = None if order is None else np.ascontiguousarray(order, np.int32)
+        f = self.lib.orc_som_train_prefix
+        f.restype = C.c_int
+        rc = f(_p(codes, _f), C.c_long(M), C.c_int(D), C.c_int(xdim), C.c_int(ydim), C.c_int(topol),
+               C.c_int(neigh), _p(data, _f), None, None, None, C.c_long(data.shape[0]), _p(order, _i),
+               C.c_long(length), C.c_long(nsteps), C.c_float(alpha), C.c_float(radius),
+               C.c_int(alpha_type))
+        if rc:
+            raise RuntimeError("orc_som_train_prefix failed")
+        return codes
+
     def lvq_train(self, algo, codes, code_label, data, data_label, length, alpha,
                   alpha_type=1, winlen=0.3, epsilon=0.1, order=None, mask=None,
                   unit_alpha=None):

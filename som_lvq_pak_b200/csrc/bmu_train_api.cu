@@ -77,7 +77,7 @@ bmu_trainer *bmu_trainer_create(const float *codes, long M, int D, const float *
   }
   if (!rc) {
     t->plan = k3_plan(M, D, g_sms, g_smem_optin);
-    if (cudaMalloc((void **)&t->d_slots, sizeof(unsigned long long) * 4 * t->plan.grid) != cudaSuccess ||
+    if (cudaMalloc((void **)&t->d_slots, sizeof(unsigned long long) * 2 * 16 * t->plan.grid) != cudaSuccess ||
         (t->plan.gslice_floats &&
          cudaMalloc((void **)&t->d_gslice, t->plan.gslice_floats * sizeof(float)) != cudaSuccess)) {
       cudaGetLastError();

@@ -20,6 +20,7 @@
 namespace bmu {
 
 #define K3_NOKEY 0xFFFFFFFFFFFFFF00ull
+#define K3_SLOT_STRIDE 16          // u64 per CTA slot: one 128-byte line each, spread over L2 slices
 
 __device__ __forceinline__ u64 make_key(float d, int idx, bool maxidx) {
   unsigned f = (unsigned)(maxidx ? (0xFFFFFF - idx) : idx) & 0xFFFFFFu;
@@ -30,6 +31,15 @@ __device__ __forceinline__ int key_idx(u64 k, bool maxidx) {
   int f = (int)((k >> 8) & 0xFFFFFFu);
   return maxidx ? (0xFFFFFF - f) : f;
 }
+// warp-wide minimum of a 64-bit key with two REDUX.MIN.U32 (hardware warp reduction) instead
+// of five rounds of two dependent shuffles
+__device__ __forceinline__ u64 warp_min_u64(u64 k) {
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return ((u64)mh << 32) | ml;
+}
+
 // merge two sorted pairs (a1<=a2), (b1<=b2) into the two smallest
 __device__ __forceinline__ void merge2(u64 &a1, u64 &a2, u64 b1, u64 b2) {
   u64 lo = a1 < b1 ? a1 : b1;
@@ -37,6 +47,20 @@ __device__ __forceinline__ void merge2(u64 &a1, u64 &a2, u64 b1, u64 b2) {
   u64 m = a2 < b2 ? a2 : b2;
   a1 = lo;
   a2 = hi < m ? hi : m;
+}
+
+// Maps up to 1024 x 1024: dx^2 (a multiple of 1/4 below 2^20) and 0.75*dy^2 are exact in FP32,
+// so is their sum, and (float)sqrt((double)r) == the correctly rounded sqrtf(r) (a double
+// carries more than 2*24+2 bits).  The result equals the reference expression bit for bit.
+__device__ __forceinline__ float hexa_dist_small(int bx, int by, int tx, int ty) {
+  float dx = (float)(bx - tx);
+  if (((by - ty) & 1) != 0) dx += ((by & 1) == 0) ? -0.5f : 0.5f;
+  const float dy = (float)(by - ty);
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(__fmul_rn(0.75f, dy), dy)));
+}
+__device__ __forceinline__ float rect_dist_small(int bx, int by, int tx, int ty) {
+  const float dx = (float)(bx - tx), dy = (float)(by - ty);
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
 }
 
 // som_rout.c:434-455 -- the mixed float/double expression of the reference, op by op
@@ -82,32 +106,65 @@ __device__ __forceinline__ void stage_x(float *dst, const float *src, int D, int
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <bool HAS_MASK, bool TOP2>
+// Exact packed helpers for K3.  The codebook can decay towards zero during training, so the
+// .ftz trick of K1 is not admissible here: sub and mul are packed (FADD2, FMUL2), the
+// accumulating add stays scalar (ptxas does not fuse FMUL2 with a scalar FADD; verified in SASS).
+__device__ __forceinline__ void sq_acc2(float &acc_a, float &acc_b, u64 c2, u64 x2) {
+  const u64 d = sub2(c2, x2);
+  float lo, hi;
+  unpack2(mul2(d, d), lo, hi);
+  acc_a = __fadd_rn(acc_a, lo);
+  acc_b = __fadd_rn(acc_b, hi);
+}
+// c + a*(x-c) for a pair of units with per-unit rates
+__device__ __forceinline__ u64 adapt2(u64 c2, u64 x2, u64 a2) {
+  float cl, ch, pl, ph;
+  unpack2(c2, cl, ch);
+  unpack2(mul2(a2, sub2(x2, c2)), pl, ph);
+  return pack2(__fadd_rn(cl, pl), __fadd_rn(ch, ph));
+}
+
+template <bool HAS_MASK, bool TOP2, bool SLICE_SMEM>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int D = p.D, U = p.U, Us = p.Us;
+  const int D = p.D, U = p.U, Us = p.Us;                        // Us is even: unit pairs are 8-byte aligned
   const int Dpad = (D + 3) & ~3;
   float *xs = reinterpret_cast<float *>(smem_raw);                // [2][Dpad]
   u64 *wred = reinterpret_cast<u64 *>(xs + 2 * Dpad);            // [2][16] per-warp keys
   u64 *gw = wred + 32;                                            // [2] global winners
   float *ua_s = reinterpret_cast<float *>(gw + 2);                // [U] OLVQ1 rates
-  float *sl = p.slice_in_smem ? ua_s + ((U + 3) & ~3)
-                              : p.gslice + (long)blockIdx.x * D * Us;   // [D][Us]
+  float *sl;                                                      // [D][Us] component-major slice
+  if (SLICE_SMEM) sl = ua_s + ((U + 3) & ~3);
+  else sl = p.gslice + (size_t)blockIdx.x * D * Us;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x;
-  const long u0 = (long)blockIdx.x * U;
-  const int ucount = (int)max(0L, min((long)U, p.M - u0));
+  const int u0 = blockIdx.x * U;
+  const int ucount = max(0, min(U, (int)p.M - u0));
+  const int npair = (ucount + 1) >> 1;
   const int mode = p.mode;
   const bool is_som = mode <= K3_SOM_GAUSSIAN;
+  const bool small_map = p.xdim <= 1024 && p.ydim <= 1024 && p.xdim > 0;
 
-  // ---- load the slice, transposed to component-major
-  for (long t = tid; t < (long)ucount * D; t += K3_THREADS) {
-    int u = (int)(t / D), i = (int)(t % D);
-    sl[(long)i * Us + u] = p.codes[(u0 + u) * D + i];
+  // ---- load the slice, transposed to component-major (pad column zeroed)
+  for (int t = tid; t < D * Us; t += K3_THREADS) sl[t] = 0.0f;
+  __syncthreads();
+  for (int t = tid; t < ucount * D; t += K3_THREADS) {
+    int u = t / D, i = t - u * D;
+    sl[i * Us + u] = p.codes[(size_t)(u0 + u) * D + i];
   }
   if (mode == K3_OLVQ1)
     for (int u = tid; u < ucount; u += K3_THREADS) ua_s[u] = p.unit_alpha[u0 + u];
+
+  // lattice coordinates of this thread's first unit pair never change (som_rout.c:493-494)
+  int tx0[2] = {0, 0}, ty0[2] = {0, 0};
+  if (is_som && p.xdim > 0) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int gidx = u0 + 2 * tid + h;
+      tx0[h] = gidx % p.xdim; ty0[h] = gidx / p.xdim;
+    }
+  }
 
   int cur = 0;
   unsigned bstep = 0;                       // number of grid exchanges done so far
@@ -138,85 +195,122 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
 
     u64 g1 = K3_NOKEY, g2 = K3_NOKEY;
     if (!have_fixed) {
-      // ---- search: the reference's sum, component order, one rounding per operation
+      // ---- search: the reference's sum, component order, one rounding per operation;
+      //      one thread = two adjacent units (packed sub/mul, scalar accumulate)
       u64 k1 = K3_NOKEY, k2 = K3_NOKEY;
-      for (int u = tid; u < ucount; u += K3_THREADS) {
-        const float *col = sl + u;
-        float acc = 0.0f;
+      for (int up = tid; up < npair; up += K3_THREADS) {
+        const float *col = sl + 2 * up;
+        float acc_a = 0.0f, acc_b = 0.0f;
         if (HAS_MASK) {
           for (int i = 0; i < D; i++) {
-            float xi = x[i];
+            const float xi = x[i];
             if (xi != xi) continue;
-            acc = sq_acc(acc, col[(long)i * Us], xi);
+            sq_acc2(acc_a, acc_b, *reinterpret_cast<const u64 *>(col + i * Us), pack2(xi, xi));
           }
         } else {
-#pragma unroll 4
-          for (int i = 0; i < D; i++) acc = sq_acc(acc, col[(long)i * Us], x[i]);
+          int i = 0;
+          for (; i + 8 <= D; i += 8) {
+            // all loads of the batch first, so that their latency overlaps the dependent adds
+            u64 c[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) c[q] = *reinterpret_cast<const u64 *>(col + (i + q) * Us);
+            const float4 xa = *reinterpret_cast<const float4 *>(x + i);
+            const float4 xb = *reinterpret_cast<const float4 *>(x + i + 4);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) sq_acc2(acc_a, acc_b, c[q], pack2(xv[q], xv[q]));
+          }
+          for (; i < D; i++)
+            sq_acc2(acc_a, acc_b, *reinterpret_cast<const u64 *>(col + i * Us), pack2(x[i], x[i]));
         }
         // k == 1: only d < FLT_MAX can win (lvq_pak.c:57,79); k == 2: d <= FLT_MAX is inserted
-        const bool cand = TOP2 ? (acc <= FLT_MAX) : (acc < FLT_MAX);
-        if (cand) {
-          u64 key = make_key(acc, (int)(u0 + u), TOP2);
-          if (key < k1) { k2 = k1; k1 = key; }
-          else if (TOP2 && key < k2) k2 = key;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const float acc = h ? acc_b : acc_a;
+          const int u = 2 * up + h;
+          const bool cand = u < ucount && (TOP2 ? (acc <= FLT_MAX) : (acc < FLT_MAX));
+          if (cand) {
+            u64 key = make_key(acc, u0 + u, TOP2);
+            if (key < k1) { k2 = k1; k1 = key; }
+            else if (TOP2 && key < k2) k2 = key;
+          }
         }
       }
       // warp reduce, then across warps
+      if (TOP2) {
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        u64 o1 = __shfl_xor_sync(0xffffffffu, k1, off);
-        if (TOP2) {
+        for (int off = 16; off >= 1; off >>= 1) {
+          u64 o1 = __shfl_xor_sync(0xffffffffu, k1, off);
           u64 o2 = __shfl_xor_sync(0xffffffffu, k2, off);
           merge2(k1, k2, o1, o2);
-        } else {
-          k1 = o1 < k1 ? o1 : k1;
         }
+      } else {
+        k1 = warp_min_u64(k1);
       }
       if (lane == 0) { wred[warp] = k1; if (TOP2) wred[16 + warp] = k2; }
       __syncthreads();
       if (warp == 0) {
         u64 b1 = lane < K3_THREADS / 32 ? wred[lane] : K3_NOKEY;
         u64 b2 = (TOP2 && lane < K3_THREADS / 32) ? wred[16 + lane] : K3_NOKEY;
+        if (TOP2) {
 #pragma unroll
-        for (int off = 8; off >= 1; off >>= 1) {
-          u64 o1 = __shfl_xor_sync(0xffffffffu, b1, off);
-          if (TOP2) {
+          for (int off = 4; off >= 1; off >>= 1) {
+            u64 o1 = __shfl_xor_sync(0xffffffffu, b1, off);
             u64 o2 = __shfl_xor_sync(0xffffffffu, b2, off);
             merge2(b1, b2, o1, o2);
-          } else {
-            b1 = o1 < b1 ? o1 : b1;
           }
+        } else {
+          b1 = warp_min_u64(b1);
         }
         if (G > 1) {
-          // ---- grid exchange: tagged slot per CTA, double buffered by exchange parity
+          // ---- grid exchange: tagged slot per CTA, double buffered by exchange parity.
+          // All of a lane's slots are requested in one batch; only the late ones are re-polled.
           const u64 tag = (u64)((bstep + 1) & 0xFFu);
-          u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * 2;
+          u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
           if (lane == 0) {
-            st_relaxed_u64(slot + 2 * blockIdx.x, b1 | tag);
-            if (TOP2) st_relaxed_u64(slot + 2 * blockIdx.x + 1, b2 | tag);
+            st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, b1 | tag);
+            if (TOP2) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x + 1, b2 | tag);
+          }
+          constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
+          u64 v1[NQ], v2[NQ];
+          unsigned pending = 0;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            v1[q] = K3_NOKEY; v2[q] = K3_NOKEY;
+            if (lane + 32 * q < G) pending |= 1u << q;
+          }
+          while (pending) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+              if (pending & (1u << q)) {
+                v1[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q));
+                if (TOP2) v2[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q) + 1);
+              }
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+              if (pending & (1u << q)) {
+                const bool ok = (v1[q] & 0xFFu) == tag && (!TOP2 || (v2[q] & 0xFFu) == tag);
+                if (ok) pending &= ~(1u << q);
+              }
           }
           u64 m1 = K3_NOKEY, m2 = K3_NOKEY;
-          for (int c = lane; c < G; c += 32) {
-            u64 v1, v2 = K3_NOKEY;
-            do { v1 = ld_relaxed_u64(slot + 2 * c); } while ((v1 & 0xFFu) != tag);
-            v1 &= ~0xFFull;
-            if (TOP2) {
-              do { v2 = ld_relaxed_u64(slot + 2 * c + 1); } while ((v2 & 0xFFu) != tag);
-              v2 &= ~0xFFull;
-              merge2(m1, m2, v1, v2);
-            } else {
-              m1 = v1 < m1 ? v1 : m1;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            if (lane + 32 * q < G) {
+              const u64 a1 = v1[q] & ~0xFFull;
+              if (TOP2) merge2(m1, m2, a1, v2[q] & ~0xFFull);
+              else m1 = a1 < m1 ? a1 : m1;
             }
           }
+          if (TOP2) {
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            u64 o1 = __shfl_xor_sync(0xffffffffu, m1, off);
-            if (TOP2) {
+            for (int off = 16; off >= 1; off >>= 1) {
+              u64 o1 = __shfl_xor_sync(0xffffffffu, m1, off);
               u64 o2 = __shfl_xor_sync(0xffffffffu, m2, off);
               merge2(m1, m2, o1, o2);
-            } else {
-              m1 = o1 < m1 ? o1 : m1;
             }
+          } else {
+            m1 = warp_min_u64(m1);
           }
           b1 = m1; b2 = m2;
         }
@@ -236,23 +330,53 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
         int w = key_idx(g1, false);
         bx = w % p.xdim; by = w / p.xdim;                  // som_rout.c:641-642
       }
-      for (int u = tid; u < ucount; u += K3_THREADS) {
-        const int gidx = (int)(u0 + u);
-        const int tx = gidx % p.xdim, ty = gidx / p.xdim;  // som_rout.c:493-494
-        const float dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
-        float a;
-        if (mode == K3_SOM_GAUSSIAN) a = gauss_alpha_dev(talp, dd, trad);
-        else { if (!(dd <= trad)) continue; a = talp; }    // som_rout.c:496
-        float *col = sl + u;
-        if (HAS_MASK) {
-          for (int i = 0; i < D; i++) {
-            float xi = x[i];
-            if (xi != xi) continue;
-            col[(long)i * Us] = adapt1(col[(long)i * Us], xi, a);
+      for (int up = tid; up < npair; up += K3_THREADS) {
+        float a[2];
+        bool upd[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int gidx = u0 + 2 * up + h;
+          int tx, ty;
+          if (up == tid) { tx = tx0[h]; ty = ty0[h]; }
+          else { tx = gidx % p.xdim; ty = gidx / p.xdim; }   // som_rout.c:493-494
+          float dd;
+          if (small_map) dd = p.topol == 4 ? rect_dist_small(bx, by, tx, ty) : hexa_dist_small(bx, by, tx, ty);
+          else dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
+          upd[h] = 2 * up + h < ucount;
+          if (mode == K3_SOM_GAUSSIAN) a[h] = gauss_alpha_dev(talp, dd, trad);
+          else { a[h] = talp; upd[h] = upd[h] && (dd <= trad); }   // som_rout.c:496
+        }
+        if (!upd[0] && !upd[1]) continue;
+        const u64 a2 = pack2(a[0], a[1]);
+        float *col = sl + 2 * up;
+        const bool both = upd[0] && upd[1];
+        auto fix = [&](u64 oldv, u64 newv) {                 // leave the untouched unit bit-identical
+          if (both) return newv;
+          float ol, oh, nl, nh;
+          unpack2(oldv, ol, oh);
+          unpack2(newv, nl, nh);
+          return pack2(upd[0] ? nl : ol, upd[1] ? nh : oh);
+        };
+        int i = 0;
+        if (!HAS_MASK) {
+          for (; i + 8 <= D; i += 8) {
+            u64 c[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) c[q] = *reinterpret_cast<const u64 *>(col + (i + q) * Us);
+            const float4 xa = *reinterpret_cast<const float4 *>(x + i);
+            const float4 xb = *reinterpret_cast<const float4 *>(x + i + 4);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              *reinterpret_cast<u64 *>(col + (i + q) * Us) = fix(c[q], adapt2(c[q], pack2(xv[q], xv[q]), a2));
           }
-        } else {
-#pragma unroll 4
-          for (int i = 0; i < D; i++) col[(long)i * Us] = adapt1(col[(long)i * Us], x[i], a);
+        }
+        for (; i < D; i++) {
+          const float xi = x[i];
+          if (HAS_MASK && xi != xi) continue;
+          u64 *cp = reinterpret_cast<u64 *>(col + i * Us);
+          const u64 c2 = *cp;
+          *cp = fix(c2, adapt2(c2, pack2(xi, xi), a2));
         }
       }
     } else {
@@ -304,7 +428,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
         for (int i = tid; i < D; i += K3_THREADS) {
           float xi = x[i];
           if (HAS_MASK && xi != xi) continue;
-          col[(long)i * Us] = adapt1(col[(long)i * Us], xi, a1);
+          col[i * Us] = adapt1(col[i * Us], xi, a1);
         }
       }
       if (do2 && w2 >= u0 && w2 < u0 + ucount) {
@@ -312,7 +436,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
         for (int i = tid; i < D; i += K3_THREADS) {
           float xi = x[i];
           if (HAS_MASK && xi != xi) continue;
-          col[(long)i * Us] = adapt1(col[(long)i * Us], xi, a2);
+          col[i * Us] = adapt1(col[i * Us], xi, a2);
         }
       }
     }
@@ -321,9 +445,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
   // ---- write the slice back
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  for (long t = tid; t < (long)ucount * D; t += K3_THREADS) {
-    int u = (int)(t / D), i = (int)(t % D);
-    p.codes[(u0 + u) * D + i] = sl[(long)i * Us + u];
+  for (int t = tid; t < ucount * D; t += K3_THREADS) {
+    int u = t / D, i = t - u * D;
+    p.codes[(size_t)(u0 + u) * D + i] = sl[i * Us + u];
   }
   if (mode == K3_OLVQ1)
     for (int u = tid; u < ucount; u += K3_THREADS) p.unit_alpha[u0 + u] = ua_s[u];
@@ -363,12 +487,12 @@ K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
   double best_cost = 1e300;
   for (int G = 1; G <= num_sms; G = (G < num_sms && G * 2 > num_sms) ? num_sms : G * 2) {
     int U = (int)((M + G - 1) / G);
-    int Us = (U & 1) ? U : U + 1;
+    int Us = (U + 1) & ~1;                 // even: unit pairs stay 8-byte aligned
     size_t fixed = k3_fixed_smem(D, U);
     size_t slice = (size_t)D * Us * 4;
     bool fits = fixed + slice <= smem_optin;
     // rough cycles per step: rounds of units per thread x (search + update) + exchange
-    double rounds = (double)((U + K3_THREADS - 1) / K3_THREADS);
+    double rounds = (double)((U + 2 * K3_THREADS - 1) / (2 * K3_THREADS));
     double cost = rounds * D * 24.0 * (fits ? 1.0 : 6.0) + (G > 1 ? 1500.0 + 4.0 * G : 0.0);
     if (cost < best_cost) {
       best_cost = cost;
@@ -384,12 +508,17 @@ K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
 cudaError_t k3_launch(const K3Params &p, const K3Plan &plan, bool has_mask, cudaStream_t st) {
   const bool top2 = p.mode == K3_LVQ2 || p.mode == K3_LVQ3;
   void *fn;
-  if (has_mask) fn = top2 ? (void *)k3_kernel<true, true> : (void *)k3_kernel<true, false>;
-  else fn = top2 ? (void *)k3_kernel<false, true> : (void *)k3_kernel<false, false>;
+  if (plan.slice_in_smem) {
+    if (has_mask) fn = top2 ? (void *)k3_kernel<true, true, true> : (void *)k3_kernel<true, false, true>;
+    else fn = top2 ? (void *)k3_kernel<false, true, true> : (void *)k3_kernel<false, false, true>;
+  } else {
+    if (has_mask) fn = top2 ? (void *)k3_kernel<true, true, false> : (void *)k3_kernel<true, false, false>;
+    else fn = top2 ? (void *)k3_kernel<false, true, false> : (void *)k3_kernel<false, false, false>;
+  }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)plan.smem_bytes);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(p.slots, 0, sizeof(u64) * 4 * plan.grid, st);
+  e = cudaMemsetAsync(p.slots, 0, sizeof(u64) * 2 * K3_SLOT_STRIDE * plan.grid, st);
   if (e != cudaSuccess) return e;
   K3Params pp = p;
   void *args[] = {&pp};
