@@ -278,6 +278,7 @@ def main_gpu(args, w):
         launches = int(launches)
     value = world * rows * args.steps / (ms * 1e-3)
     qsum, nfound = float(stats[0]), int(stats[1])
+    bd = bmu.last_search_breakdown()
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (pinned), copies in the timed region
     h_data = torch.empty((rows, D), dtype=torch.float32, pin_memory=True)
@@ -315,7 +316,6 @@ def main_gpu(args, w):
         sm_max = peaks.get("sm_max_mhz", 1965.0)
         fp32_peak = info["sm_count"] * 128 * sm_max * 1e6 / 1e12          # T lane-ops/s, nominal
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        bd = bmu.last_search_breakdown()
         used_k2 = bd["k2_certified"] + bd["k2_failed"] > 0
         names = ("k1_data_prep", "k1_fast", "k1_warp", "k1_seq", "k2_row_prep", "k2_gemm", "k2_rerank", "k2_lists")
         step_ms = {n: v for n, v in zip(names, kernel_ms) if (n.startswith("k2") == used_k2)}
@@ -369,6 +369,8 @@ def main_gpu(args, w):
             "roofline": roof,
             "result_check": {"mean_qerror": qsum / max(nfound, 1), "n_found": nfound},
         }
+        if world == 1 and not args.no_vsom:
+            line["vsom"] = vsom_c5(bmu, args)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rpc = args.ref_rows or max(64, int(10.0 * 1600 * (10_000 * 64) / (M * D)))
@@ -384,6 +386,58 @@ def main_gpu(args, w):
     return 0
 
 
+def vsom_c5(bmu, args):
+    """second headline metric: vsom steps/s on BASELINE.json configs[4] (256x256 hexa gaussian map,
+    128-dim, rlen 1e6; SURVEY 8d parameters).  A bounded prefix of the 1e6-step schedule is run
+    on the GPU (CUDA events inside the library); the CPU leg runs the reference's own
+    som_training (oracle/_ref) on one core for a few steps (training is sequential)."""
+    N, D, xdim, ydim, length = 100_000, 128, 256, 256, 1_000_000
+    data = synth_numpy(4, 0, N * D).reshape(N, D)
+    codes = synth_numpy(5, 0, xdim * ydim * D).reshape(xdim * ydim, D)
+    order = bmu.rand_order(N, 3)
+    steps = args.vsom_steps
+    s, ta, tr = bmu.som_schedule(0, steps, length, 0.05, 100.0, bmu.ALPHA_LINEAR, N, order)
+    t = bmu.Trainer(codes, data)
+    t.set_som(xdim, ydim, bmu.TOPOL_HEXA, bmu.NEIGH_GAUSSIAN)
+    t.steps(s[:64], ta[:64], tr[:64])              # warm-up launch
+    t.close()
+    t = bmu.Trainer(codes, data)
+    t.set_som(xdim, ydim, bmu.TOPOL_HEXA, bmu.NEIGH_GAUSSIAN)
+    t0 = time.perf_counter()
+    t.steps(s, ta, tr)
+    wall = time.perf_counter() - t0
+    ms = t.last_ms()
+    t.close()
+    M = xdim * ydim
+    out = {"metric": "vsom steps/s", "value": steps / (ms * 1e-3), "unit": "steps/s",
+           "e2e_value": steps / wall, "steps": steps, "us_per_step": 1e3 * ms / steps,
+           "config": "256x256 hexa gaussian map, 128-dim, rlen 1e6 schedule (first %d steps), alpha 0.05 "
+                     "linear, radius 100, -rand 3 order, 100000 x 128 synthetic data" % steps,
+           "lane_ops_per_step": 6.0 * M * D, "achieved_tflops": 6.0 * M * D * steps / (ms * 1e-3) / 1e12}
+    if not args.no_cpu:
+        from oracle.pyoracle import Reference, Oracle
+        nref = 30
+        t0 = time.perf_counter()
+        if Reference.available():
+            Reference().som_train(codes, data, xdim, ydim, 3, 2, nref, 0.05, 100.0, 1, rand_seed=3)
+            kind = "reference"
+        else:
+            Oracle().som_train(codes, data, xdim, ydim, 3, 2, nref, 0.05, 100.0, 1, order=order)
+            kind = "port"
+        dt = time.perf_counter() - t0
+        # list building / copies are outside the loop of interest: subtract a 1-step run
+        t0 = time.perf_counter()
+        if kind == "reference":
+            Reference().som_train(codes, data, xdim, ydim, 3, 2, 1, 0.05, 100.0, 1, rand_seed=3)
+        else:
+            Oracle().som_train(codes, data, xdim, ydim, 3, 2, 1, 0.05, 100.0, 1, order=order)
+        dt1 = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (nref - 1) / max(dt - dt1, 1e-9), "unit": "steps/s", "cores": 1,
+                               "kind": kind, "sample": "%d steps of som_training (rlen %d) minus a 1-step run"
+                                                       % (nref, nref)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,6 +448,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--ref-rows", type=int, default=0, help="override CPU sample rows per core")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-vsom", action="store_true", help="skip the vsom (configs[4]) extra metric")
+    ap.add_argument("--vsom-steps", type=int, default=50000)
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "filter"],
                     help="search kernels: auto (default), exact = K1 only, filter = K2 forced")
     args = ap.parse_args()

@@ -33,6 +33,8 @@ constexpr int K2_KS = 64;    // K elements per pipeline stage (4 MMAs)
 constexpr int K2_NSTAGE = 4;
 constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp
+constexpr int K2_GROUP_MAX_KP = 0;    // group-minimum epilogue (k == 1) up to this Kp; 0 = off: its
+                                      // re-rank gathers 64 code rows per sample and costs more than it saves
 
 struct CbStats {     // maxima over the codebook (centred), device side
   float nm;          // max ||m'||
@@ -303,7 +305,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
         "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
 }
 
 struct K2Smem {
@@ -313,8 +315,42 @@ struct K2Smem {
   }
 };
 
-// TG: candidates kept per row, TT: smallest keys tracked per code tile
-template <int TG, int TT>
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// tcgen05.wait::ld with the destination registers as in/out operands: the compiler must not
+// schedule any use of v[] between the asynchronous tcgen05.ld and this wait
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
+}
+
+__device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
+  // 3-input minima (FMNMX3): 32 -> 11 -> 4 -> 2 -> 1
+  float a[11];
+#pragma unroll
+  for (int t = 0; t < 10; t++)
+    a[t] = fminf(fminf(__uint_as_float(v[3 * t]), __uint_as_float(v[3 * t + 1])), __uint_as_float(v[3 * t + 2]));
+  a[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  float b0 = fminf(fminf(a[0], a[1]), a[2]), b1 = fminf(fminf(a[3], a[4]), a[5]);
+  float b2 = fminf(fminf(a[6], a[7]), a[8]), b3 = fminf(a[9], a[10]);
+  return fminf(fminf(b0, b1), fminf(b2, b3));
+}
+
+// TG: candidates kept per row, TT: smallest keys tracked per code tile.
+// GROUP mode (k == 1): the epilogue only tracks the minimum of every group of 32 columns
+// (~0.8 ALU op per score instead of 4) and keeps the TG best GROUPS per row; all 32 codes of
+// those groups are re-ranked exactly, and every code outside them has a score >= the
+// (TG+1)-th smallest group minimum, which is what the certificate needs.
+template <int TG, int TT, bool GROUP>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__restrict__ Bimg, long N,
                long M, int Kp, int a_res, int32_t *__restrict__ cand, float *__restrict__ thr) {
@@ -415,6 +451,72 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
       }
     }
   } else {
+    if constexpr (GROUP) {
+    // ===================== epilogue, group mode: one row per thread =====================
+    unsigned acc_seq = 0;
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      float gk[TG + 1];
+      int gi[TG + 1];
+#pragma unroll
+      for (int t = 0; t <= TG; t++) { gk[t] = INFINITY; gi[t] = -1; }
+      for (int ct = 0; ct < nct; ct++, acc_seq++) {
+        const int buf = acc_seq & 1;
+        mbar_wait(&tfull[buf], (acc_seq >> 1) & 1);
+        tc_fence_after();
+        // tile-level top-(TG+1) group minima; the 3 low mantissa bits carry the group number
+        float tk[TG + 1];
+#pragma unroll
+        for (int t = 0; t <= TG; t++) tk[t] = INFINITY;
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(lane_base + buf * K2_TN, va);
+#pragma unroll
+        for (int g = 0; g < K2_TN / 32; g += 2) {
+          tmem_ld_wait32(va);
+          tmem_ld32_nowait(lane_base + buf * K2_TN + (g + 1) * 32, vb);     // overlap with the min tree
+          {
+            float key = __uint_as_float((__float_as_uint(min32(va)) & 0xFFFFFFF8u) | (uint32_t)g);
+#pragma unroll
+            for (int t = 0; t <= TG; t++) { float lo = fminf(tk[t], key); key = fmaxf(tk[t], key); tk[t] = lo; }
+          }
+          tmem_ld_wait32(vb);
+          if (g + 2 < K2_TN / 32) tmem_ld32_nowait(lane_base + buf * K2_TN + (g + 2) * 32, va);
+          {
+            float key = __uint_as_float((__float_as_uint(min32(vb)) & 0xFFFFFFF8u) | (uint32_t)(g + 1));
+#pragma unroll
+            for (int t = 0; t <= TG; t++) { float lo = fminf(tk[t], key); key = fmaxf(tk[t], key); tk[t] = lo; }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+#pragma unroll
+        for (int t = 0; t <= TG; t++) {
+          float key = tk[t];
+          int j = ct * (K2_TN / 32) + (int)(__float_as_uint(key) & 7u);      // global group index
+          if (key < gk[TG]) {
+            bool ins = false;
+#pragma unroll
+            for (int p = 0; p <= TG; p++) {
+              if (ins || key < gk[p]) {
+                float t2 = gk[p]; int i2 = gi[p];
+                gk[p] = key; gi[p] = j;
+                key = t2; j = i2;
+                ins = true;
+              }
+            }
+          }
+        }
+      }
+      const long n = tile * K2_TM + row;
+      if (n < N) {
+#pragma unroll
+        for (int t = 0; t < TG; t++) cand[n * TG + t] = gi[t];
+        thr[n] = gk[TG];           // every group that was not kept has a minimum >= this key
+      }
+    }
+    } else {
     // ===================== epilogue: one row per thread =====================
     unsigned acc_seq = 0;
     const int row = warp * 32 + lane;
@@ -431,21 +533,45 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
         float b[TT];
 #pragma unroll
         for (int t = 0; t < TT; t++) b[t] = INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < K2_TN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * K2_TN + c0, v);
+        // two register buffers: the tcgen05.ld of the next 32 columns is in flight while the
+        // current 32 are folded into the tile's TT smallest keys
+        uint32_t va[32], vb[32];
+        const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * K2_TN;
+        auto fold = [&](const uint32_t (&v)[32], int c0) {
+          if constexpr (TT == 2) {
+            // pairs: 2 LOP3 + min,max,min,max,min3 = 3.5 ALU ops per score instead of 4
 #pragma unroll
-          for (int c = 0; c < 32; c++) {
-            // 8 low mantissa bits <- column index inside the tile (perturbs the score by < 2^-15 |s|)
-            float key = __uint_as_float((v[c] & 0xFFFFFF00u) | (uint32_t)(c0 + c));
+            for (int c = 0; c < 32; c += 2) {
+              const float k0 = __uint_as_float((v[c] & 0xFFFFFF00u) | (uint32_t)(c0 + c));
+              const float k1 = __uint_as_float((v[c + 1] & 0xFFFFFF00u) | (uint32_t)(c0 + c + 1));
+              const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+              const float t = fmaxf(b[0], lo);
+              b[0] = fminf(b[0], lo);
+              b[1] = fminf(fminf(b[1], hi), t);
+            }
+          } else {
 #pragma unroll
-            for (int t = 0; t < TT; t++) {
-              float lo = fminf(b[t], key);
-              key = fmaxf(b[t], key);
-              b[t] = lo;
+            for (int c = 0; c < 32; c++) {
+              // 8 low mantissa bits <- column index inside the tile (perturbs the score by < 2^-15 |s|)
+              float key = __uint_as_float((v[c] & 0xFFFFFF00u) | (uint32_t)(c0 + c));
+#pragma unroll
+              for (int t = 0; t < TT; t++) {
+                float lo = fminf(b[t], key);
+                key = fmaxf(b[t], key);
+                b[t] = lo;
+              }
             }
           }
+        };
+        tmem_ld32_nowait(tbase, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < K2_TN; c0 += 64) {
+          tmem_ld_wait32(va);
+          tmem_ld32_nowait(tbase + c0 + 32, vb);
+          fold(va, c0);
+          tmem_ld_wait32(vb);
+          if (c0 + 64 < K2_TN) tmem_ld32_nowait(tbase + c0 + 64, va);
+          fold(vb, c0 + 32);
         }
         tc_fence_before();
         __syncwarp();
@@ -481,6 +607,7 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
       }
     }
   }
+    }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -592,6 +719,96 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
   nfound[n] = k;
 }
 
+// ---------------------------------------------------------------- group re-rank (k == 1)
+// One warp per row: lane l computes the exact distance to code 32*g + l of each candidate
+// group g, the warp takes the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and
+// lane 0 evaluates the certificate against the (NG+1)-th smallest group minimum.
+template <int NG>
+__global__ void __launch_bounds__(256)
+k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M,
+                       int D, int Kp, const unsigned char *__restrict__ flags,
+                       const RowStats *__restrict__ rs, const CbStats *__restrict__ cst,
+                       const int32_t *__restrict__ cand, const float *__restrict__ thr,
+                       int *__restrict__ listW, int *__restrict__ counters, int32_t *__restrict__ idx,
+                       float *__restrict__ diff, int32_t *__restrict__ nfound) {
+  const int lane = threadIdx.x & 31;
+  const long n = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  if (n >= N || flags[n] != 0) return;                 // warp-uniform
+  const float *x = data + n * (long)D;
+  u64 best = ~0ull;
+  int ncodes = 0;
+#pragma unroll
+  for (int gsel = 0; gsel < NG; gsel++) {
+    const int gid = cand[n * NG + gsel];
+    if (gid < 0) continue;
+    const long j = (long)gid * 32 + lane;
+    ncodes += (int)min(32L, max(0L, M - (long)gid * 32));
+    if (j >= M) continue;
+    const float *c = codes + j * D;
+    float acc = 0.0f;
+    if ((D & 3) == 0) {
+      const float4 *x4 = reinterpret_cast<const float4 *>(x);
+      const float4 *c4 = reinterpret_cast<const float4 *>(c);
+#pragma unroll 4
+      for (int i = 0; i < D / 4; i++) {
+        const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i);
+        acc = sq_acc(acc, cv.x, xv.x);
+        acc = sq_acc(acc, cv.y, xv.y);
+        acc = sq_acc(acc, cv.z, xv.z);
+        acc = sq_acc(acc, cv.w, xv.w);
+      }
+    } else {
+      for (int i = 0; i < D; i++) acc = sq_acc(acc, __ldg(c + i), __ldg(x + i));
+    }
+    // only d < FLT_MAX can win; non-negative floats order like their bit patterns
+    if (acc < FLT_MAX) {
+      const u64 key = ((u64)__float_as_uint(acc) << 32) | (unsigned)j;
+      best = key < best ? key : best;
+    }
+  }
+  {
+    const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    best = ((u64)mh << 32) | ml;
+  }
+  if (lane != 0) return;
+  const float dbest = __uint_as_float((unsigned)(best >> 32));
+  const int jbest = (int)(unsigned)best;
+  bool ok = false;
+  if (best != ~0ull) {
+    const RowStats s = rs[n];
+    const CbStats cs = *cst;
+    const double nx = s.nx, NM = cs.nm;
+    const double amag = 2.0 * nx * NM + (double)cs.nm2;
+    const double e_dot = 2.0 * ((double)s.nxlo * cs.nmlo + (double)s.nrx * NM + nx * (double)cs.nrm);
+    const double e_norm = ldexp((double)cs.nm2, -25);
+    const double e_acc = 2.0 * (double)(Kp / 16) * 17.0 * ldexp(amag, -23);
+    const double e_pack = ldexp(amag, -19);                 // 3 low mantissa bits carry the group number
+    const double E = (e_dot + e_norm + e_acc + e_pack) * 1.0001;
+    const double Lc = s.nx2 + (double)thr[n] - E;
+    const double eta = ldexp(nx + NM, -23);
+    if (Lc > 0.0) {
+      const double r = sqrt(Lc) - eta;
+      if (r > 0.0) {
+        const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;
+        const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6);
+        ok = (double)dbest < L;
+      }
+    }
+    if (ncodes >= M) ok = true;                             // every code was re-ranked
+  }
+  if (!ok) {
+    listW[atomicAdd(&counters[0], 1)] = (int)n;
+    atomicAdd(&counters[3], 1);
+    return;
+  }
+  atomicAdd(&counters[2], 1);
+  idx[n] = jbest;
+  diff[n] = dbest;
+  nfound[n] = 1;
+}
+
 // ---------------------------------------------------------------- host side
 struct K2Scratch {      // carved out of one grow-only device buffer
   __nv_bfloat16 *Aimg;
@@ -651,25 +868,31 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
 static cudaEvent_t g_k2ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 static bool g_k2ev_valid = false;
 
-template <int TG, int TT>
+template <int TG, int TT, bool GROUP>
 static cudaError_t k2_run(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   const int Kp = c->Kp;
   const bool a_res = Kp <= K2_ARES_MAX_KP;
   const size_t smem = K2Smem::bytes(Kp, a_res);
-  cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long ntiles = (a.N + K2_TM - 1) / K2_TM;
   const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
-  k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __nv_bfloat16 *)c->d_ops, a.N, a.M, Kp,
+  k2_gemm_kernel<TG, TT, GROUP><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __nv_bfloat16 *)c->d_ops, a.N, a.M, Kp,
                                                         a_res ? 1 : 0, s.cand, s.thr);
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
-  constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
-  const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
-  k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
-      a.data, a.codes, a.N, a.M, a.D, a.k, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
-      a.listW, a.counters, a.idx, a.diff, a.nfound);
+  if constexpr (GROUP) {
+    k2_rerank_group_kernel<TG><<<(unsigned)((a.N + 7) / 8), 256, 0, st>>>(
+        a.data, a.codes, a.N, a.M, a.D, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
+        a.listW, a.counters, a.idx, a.diff, a.nfound);
+  } else {
+    constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
+    const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
+    k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
+        a.data, a.codes, a.N, a.M, a.D, a.k, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
+        a.listW, a.counters, a.idx, a.diff, a.nfound);
+  }
   k1_count_launch(1);
   return cudaGetLastError();
 }
@@ -721,9 +944,12 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[1], st);
-  if (a.k == 1) e = k2_run<4, 2>(c, a, s, st);
-  else if (a.k <= 5) e = k2_run<10, 4>(c, a, s, st);
-  else e = k2_run<20, 4>(c, a, s, st);
+  // k == 1: group mode for short contractions (the 4-op/score epilogue would outlast the MMAs);
+  // long contractions keep the element mode, whose re-rank touches 4 instead of 64 code rows
+  if (a.k == 1 && Kp <= K2_GROUP_MAX_KP) e = k2_run<2, 2, true>(c, a, s, st);
+  else if (a.k == 1) e = k2_run<4, 2, false>(c, a, s, st);
+  else if (a.k <= 5) e = k2_run<10, 4, false>(c, a, s, st);
+  else e = k2_run<20, 4, false>(c, a, s, st);
   if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[3], st);
   // rows that failed the certificate + masked / tiny rows, then the non-finite rows
