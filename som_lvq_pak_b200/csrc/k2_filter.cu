@@ -2,25 +2,36 @@
 //
 // For large M*D the search  argmin_j ||x - m_j||^2  is dominated by the contraction x.m_j.
 // K2 computes an APPROXIMATE score  s~_j = ||m'_j||^2 - 2 x'.m'_j  (primes: vectors centred
-// on the codebook mean) on the 5th-generation tensor cores, keeps a few candidates per row
-// in the GEMM epilogue, and then decides the winner(s) with the reference's EXACT FP32 sum
-// (lvq_pak.c:63-73) over those candidates only.  A per-row certificate proves that no code
-// outside the candidate set can win or tie; rows whose certificate fails are answered by the
-// exact kernel K1 (k1_warp_kernel).  Results are therefore bit-identical to K1 / the reference.
+// on the codebook mean and scaled by a power of two) on the 5th-generation tensor cores,
+// keeps a few candidates per row in the GEMM epilogue, and then decides the winner(s) with
+// the reference's EXACT FP32 sum (lvq_pak.c:63-73) over those candidates only.  A per-row
+// certificate proves that no code outside the candidate set can win or tie; rows whose
+// certificate fails are answered by the exact kernel K1 (k1_warp_kernel).  Results are
+// therefore bit-identical to K1 / the reference whatever the data looks like; only the speed
+// depends on how well fp16 resolves the data.
 //
-//   operands   bf16 3-term split:  x'.m' ~ xh.mh + xh.ml + xl.mh   (K = 3*Dp + 3 -> Kp)
-//              the -2 factor and ||m'||^2 (3 bf16 terms against a column of ones) are folded
-//              into the B operand, so the accumulator IS the score: no FP32 op per element
-//   GEMM       tcgen05.mma.cta_group::1.kind::f16, M=128 x N=256 x K=16 per instruction,
-//              FP32 accumulators double-buffered in TMEM (2 x 256 columns), operands staged
-//              by cp.async.bulk (UBLKCP) from images pre-arranged in the canonical no-swizzle
-//              K-major core-matrix layout, mbarrier ring, one MMA-issuing thread
-//   epilogue   4 warps, tcgen05.ld 32x32b.x32 (one row per thread); column index packed into
-//              the 8 low mantissa bits, branch-free top-2/top-4 per code tile with FMNMX,
-//              merged into a per-row sorted candidate list
+//   operands   fp16, ONE term:  x'.m' ~ xh.mh  (K = Dp + 3 -> Kp); the per-row rounding
+//              residual ||x' - xh|| is measured in the prep kernel and enters the error bound E,
+//              so E is rigorous for every row.  The -2 factor and ||m'||^2 (3 fp16 terms against
+//              columns of ones) are folded into the B operand: the accumulator IS the score.
+//   scaling    s = 2^e with s^2 max||m'||^2 in [2^11, 2^13): products stay far from the fp16
+//              range limits; rows whose scaled values overflow fp16 go to K1.
+//   GEMM       tcgen05.mma.cta_group::1.kind::f16, M=128 x N=256 x K=16 per instruction, FP32
+//              accumulators double-buffered in TMEM (2 x 256 columns), operands staged by
+//              cp.async.bulk (UBLKCP) from images pre-arranged in the canonical no-swizzle
+//              K-major core-matrix layout, mbarrier rings, one MMA-issuing thread.
+//   k2_rec_kernel  (k == 1, short contractions): 4 row tiles share every staged code tile
+//              (L2 -> smem traffic / 4); 8 epilogue warps; "record" epilogue: a 3-input min
+//              tree per 32 columns (0.5 ALU op per score) and, only when a row's chunk minimum
+//              is below its running threshold best+delta, a slow path that inserts the columns
+//              below the threshold.  Everything never inserted is >= final best+delta.
+//   k2_gemm_kernel (k >= 2 or long contractions): K streamed in slabs; epilogue keeps the TT
+//              smallest keys per code tile with the column index packed into the low mantissa
+//              bits.
 //   re-rank    exact distances of the candidates, reference tie rules, certificate
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "k2_filter.h"
@@ -29,25 +40,41 @@ namespace bmu {
 
 constexpr int K2_TM = 128;   // rows per sample tile (UMMA M)
 constexpr int K2_TN = 256;   // codes per code tile (UMMA N)
-constexpr int K2_KS = 64;    // K elements per pipeline stage (4 MMAs)
+constexpr int K2_KS = 64;    // K elements per pipeline stage (4 MMAs), streaming kernel
 constexpr int K2_NSTAGE = 4;
 constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
-constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp
-constexpr int K2_GROUP_MAX_KP = 0;    // group-minimum epilogue (k == 1) up to this Kp; 0 = off: its
-                                      // re-rank gathers 64 code rows per sample and costs more than it saves
+constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp (streaming kernel)
 
-struct CbStats {     // maxima over the codebook (centred), device side
-  float nm;          // max ||m'||
-  float nmlo;        // max ||m'_lo||
-  float nrm;         // max ||m' - m'_hi - m'_lo||
-  float nm2;         // max ||m'||^2
+constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel
+constexpr int K2R_BST = 3;        // staged code tiles
+constexpr int K2R_THREADS = 320;  // warps 0-7 epilogue (two groups of 4), warp 8 producer, warp 9 MMA
+constexpr int K2R_TG = 4;         // candidates kept per row
+constexpr int K2R_MAX_KP = 96;    // code tile (256 x Kp fp16) <= 48 KB
+
+struct CbStats {     // maxima over the codebook (centred, scaled), device side
+  float nm2_raw;     // max ||m'||^2 before scaling (rounded up)
+  float scale;       // s (a power of two)
+  float inv_s2;      // 1 / s^2
+  float nm;          // max ||s m'||
+  float nrm;         // max ||s m' - fp16(s m')||
+  float nm2;         // max ||s m'||^2
 };
 
 __host__ __device__ inline int k2_dp(int D) { return (D + 7) & ~7; }
-__host__ __device__ inline int k2_kp(int D) { return (3 * k2_dp(D) + 3 + 15) & ~15; }
+__host__ __device__ inline int k2_kp(int D) { return (k2_dp(D) + 3 + 15) & ~15; }
 
 __device__ __forceinline__ void atomic_max_pos(float *addr, float v) {
   atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));   // non-negative floats order as ints
+}
+
+// s = 2^e such that s^2 * nm2_raw lies in [2^11, 2^13); 1 for degenerate codebooks
+__device__ __forceinline__ float k2_scale_from(float nm2_raw) {
+  if (!(nm2_raw > 0.0f) || !(nm2_raw < INFINITY)) return 1.0f;
+  int ex;
+  frexpf(nm2_raw, &ex);                         // nm2_raw = f * 2^ex, f in [0.5, 1)
+  int se = (13 - ex) >> 1;                      // floor((13 - ex) / 2)
+  se = max(-60, min(60, se));
+  return ldexpf(1.0f, se);
 }
 
 // ---------------------------------------------------------------- codebook side
@@ -60,59 +87,72 @@ __global__ void k2_mean_kernel(const float *__restrict__ codes, long M, int D, f
   mean[i] = (float)(s / (double)M);
 }
 
-// one warp per code: centre, split, write the B image, accumulate the maxima
+// one warp per code: max ||m'||^2 (fixes the scale)
+__global__ void __launch_bounds__(256)
+k2_cb_norm_kernel(const float *__restrict__ codes, long M, int D, const float *__restrict__ mean,
+                  CbStats *__restrict__ st) {
+  const int lane = threadIdx.x & 31;
+  const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  if (w >= M) return;
+  double n2 = 0.0;
+  for (int i = lane; i < D; i += 32) {
+    const float c = __fsub_rn(codes[w * D + i], mean[i]);
+    n2 += (double)c * c;
+  }
+  for (int off = 16; off >= 1; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  if (lane == 0) {
+    float v = (float)n2 * 1.0001f;
+    if (!(v < INFINITY)) v = INFINITY;          // NaN / overflow: degenerate, scale 1
+    atomic_max_pos(&st->nm2_raw, v);
+  }
+}
+
+// one warp per code: centre, scale, round to fp16, write the B image, accumulate the maxima
 __global__ void __launch_bounds__(256)
 k2_cb_prep_kernel(const float *__restrict__ codes, long M, int D, const float *__restrict__ mean,
-                  __nv_bfloat16 *__restrict__ Bimg, CbStats *__restrict__ st) {
+                  __half *__restrict__ Bimg, CbStats *__restrict__ st) {
   const int lane = threadIdx.x & 31;
   const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const long nct = (M + K2_TN - 1) / K2_TN;
   if (w >= nct * K2_TN) return;
   const int Dp = k2_dp(D), Kp = k2_kp(D);
+  const float sc = k2_scale_from(st->nm2_raw);
+  if (w == 0 && lane == 0) { st->scale = sc; st->inv_s2 = 1.0f / (sc * sc); }   // powers of two: exact
   const long ct = w / K2_TN;
   const int r = (int)(w % K2_TN);
-  __nv_bfloat16 *img = Bimg + ct * (long)K2_TN * Kp;           // [kc][TN][8]
-  auto put = [&](int k, float v) { img[((long)(k >> 3) * K2_TN + r) * 8 + (k & 7)] = __float2bfloat16(v); };
+  __half *img = Bimg + ct * (long)K2_TN * Kp;           // [kc][TN][8]
+  auto put = [&](int k, float v) { img[((long)(k >> 3) * K2_TN + r) * 8 + (k & 7)] = __float2half_rn(v); };
   // zero everything this row owns first (pads included)
   for (int k = lane; k < Kp; k += 32) put(k, 0.0f);
   __syncwarp();
-  if (w >= M) {            // padding code: a huge score so it never becomes a candidate
-    if (lane == 0) put(3 * Dp, 1e30f);
+  if (w >= M) {            // padding code: a large score (never a candidate: column >= M is masked / range-checked)
+    if (lane == 0) { put(Dp, 65504.0f); put(Dp + 1, 65504.0f); put(Dp + 2, 65504.0f); }
     return;
   }
-  double n2 = 0.0, nlo2 = 0.0, nr2 = 0.0;
+  double n2 = 0.0, nr2 = 0.0;
   for (int i = lane; i < D; i += 32) {
-    float c = __fsub_rn(codes[w * D + i], mean[i]);
-    __nv_bfloat16 h = __float2bfloat16(c);
-    float lo_f = __fsub_rn(c, __bfloat162float(h));
-    __nv_bfloat16 l = __float2bfloat16(lo_f);
-    float res = __fsub_rn(lo_f, __bfloat162float(l));
-    // the factor -2 is exact in bf16
-    put(i, -2.0f * __bfloat162float(h));            // pairs with x_hi
-    put(Dp + i, -2.0f * __bfloat162float(l));       // pairs with x_hi
-    put(2 * Dp + i, -2.0f * __bfloat162float(h));   // pairs with x_lo
+    const float c = __fmul_rn(__fsub_rn(codes[w * D + i], mean[i]), sc);
+    const float h = __half2float(__float2half_rn(c));
+    const float res = __fsub_rn(c, h);           // exact (Sterbenz / fp16 grid is a subset of fp32)
+    put(i, -2.0f * h);                           // |h| <= 2^6.5: the factor -2 is exact in fp16
     n2 += (double)c * c;
-    nlo2 += (double)__bfloat162float(l) * __bfloat162float(l);
     nr2 += (double)res * res;
   }
   for (int off = 16; off >= 1; off >>= 1) {
     n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-    nlo2 += __shfl_xor_sync(0xffffffffu, nlo2, off);
     nr2 += __shfl_xor_sync(0xffffffffu, nr2, off);
   }
   if (lane == 0) {
-    float nf = (float)n2;
-    __nv_bfloat16 a = __float2bfloat16(nf);
-    float r1 = nf - __bfloat162float(a);
-    __nv_bfloat16 b = __float2bfloat16(r1);
-    float r2 = r1 - __bfloat162float(b);
-    __nv_bfloat16 c3 = __float2bfloat16(r2);
-    put(3 * Dp, __bfloat162float(a));
-    put(3 * Dp + 1, __bfloat162float(b));
-    put(3 * Dp + 2, __bfloat162float(c3));
+    const float nf = (float)n2;                  // < 2^13 * 1.0001 by the choice of the scale
+    const float a = __half2float(__float2half_rn(nf));
+    const float r1 = nf - a;
+    const float b = __half2float(__float2half_rn(r1));
+    const float r2 = r1 - b;
+    put(Dp, a);
+    put(Dp + 1, b);
+    put(Dp + 2, r2);
     const float up = 1.0001f;
     atomic_max_pos(&st->nm, (float)sqrt(n2) * up);
-    atomic_max_pos(&st->nmlo, (float)sqrt(nlo2) * up);
     atomic_max_pos(&st->nrm, (float)sqrt(nr2) * up);
     atomic_max_pos(&st->nm2, (float)n2 * up);
   }
@@ -120,14 +160,16 @@ k2_cb_prep_kernel(const float *__restrict__ codes, long M, int D, const float *_
 
 // ---------------------------------------------------------------- row side
 // One CTA per tile of 128 rows: classification + work lists (same rules as K1's
-// data_prep_kernel), centred bf16 split written as the A image [kc][128][8], row bounds.
+// data_prep_kernel), centred+scaled fp16 image [kc][128][8], and the per-row error bound.
 struct RowStats {
-  double nx2;     // ||x'||^2
-  float nx;       // ||x'||      (rounded up)
-  float nxlo;     // ||x'_lo||
-  float nrx;      // ||x' - x'_hi - x'_lo||
+  double nx2;     // ||s x'||^2 (fp32 centred values, before the fp16 rounding)
+  float nx;       // ||s x'||   (rounded up)
+  float E;        // bound on |score - (||s x' - s m'||^2 - nx2)| over all codes (scaled units)
+  float delta;    // candidate window of the record epilogue: > 2E + rounding slack
   float pad;
 };
+
+#define ROW_RANGE 16u       // a scaled component overflows fp16: row answered by K1
 
 __device__ __forceinline__ unsigned k2_classify(float v) {
   unsigned b = __float_as_uint(v) & 0x7fffffffu;
@@ -137,26 +179,27 @@ __device__ __forceinline__ unsigned k2_classify(float v) {
   return f;
 }
 
-__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);      // .x = lo (low 16 bits), .y = hi
+__device__ __forceinline__ uint32_t half2_bits(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);      // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
 constexpr int K2_PS = 32;     // components per row-prep slab
 
+// pack_bits: low mantissa bits the GEMM epilogue overwrites with the column index (0 or 8)
 __global__ void __launch_bounds__(256)
 k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restrict__ mask, long N,
-                   int D, int k, const float *__restrict__ mean, __nv_bfloat16 *__restrict__ Aimg,
+                   int D, int k, int pack_bits, const float *__restrict__ mean,
+                   const CbStats *__restrict__ cst, __half *__restrict__ Aimg,
                    RowStats *__restrict__ rs, unsigned char *__restrict__ flags,
                    int *__restrict__ listW, int *__restrict__ listS, int *__restrict__ counters,
                    int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
   // staged through shared memory so that both the row reads and the image writes are coalesced
-  __shared__ float xs[K2_TM][K2_PS + 1];                      // centred inputs of the slab
+  __shared__ float xs[K2_TM][K2_PS + 1];                      // inputs of the slab
   __shared__ unsigned char ms[K2_TM][K2_PS];                  // mask bytes of the slab
-  __shared__ __align__(16) uint4 img_s[3][K2_PS / 8][K2_TM];  // three image regions of the slab
-  // row-combine scratch aliases the image staging buffer (used only after the slab loop)
-  double (*red)[3] = reinterpret_cast<double (*)[3]>(&img_s[0][0][0]);
-  int (*redi)[2] = reinterpret_cast<int (*)[2]>(&img_s[1][0][0]);
+  __shared__ __align__(16) uint4 img_s[K2_PS / 8][K2_TM];     // image chunks of the slab
+  __shared__ double red[K2_TM][2];
+  __shared__ int redi[K2_TM][2];
   const int Dp = k2_dp(D), Kp = k2_kp(D);
   const long tile = blockIdx.x;
   const long n0 = tile * K2_TM;
@@ -164,13 +207,14 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
   const int row = tid & (K2_TM - 1), half = tid >> 7;           // thread = (row, 16-component half)
   uint4 *img = reinterpret_cast<uint4 *>(Aimg + tile * (long)K2_TM * Kp);   // [kc][128] uint4
   const long nrow = n0 + row;
-  double n2 = 0.0, nlo2 = 0.0, nr2 = 0.0;
+  const float sc = cst->scale;
+  double n2 = 0.0, nr2 = 0.0;
   unsigned f = 0;
   int nmasked = 0;
 
   for (int d0 = 0; d0 < Dp; d0 += K2_PS) {
     __syncthreads();
-    // phase 1: coalesced load of 128 rows x 32 components, centred
+    // phase 1: coalesced load of 128 rows x 32 components
     for (int r = warp; r < K2_TM; r += 8) {
       const long n = n0 + r;
       const int i = d0 + lane;
@@ -184,79 +228,85 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
       ms[r][lane] = mk;
     }
     __syncthreads();
-    // phase 2: split; each thread packs 2 x 8 components of one row
+    // phase 2: centre, scale, round; each thread packs 2 x 8 components of one row
 #pragma unroll
     for (int grp = 0; grp < 2; grp++) {
-      uint32_t hi_w[4], lo_w[4];
+      uint32_t hw[4];
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        float hv[2], lv[2];
+        float hv[2];
 #pragma unroll
         for (int q = 0; q < 2; q++) {
           const int il = half * 16 + grp * 8 + p * 2 + q;
           const int i = d0 + il;
-          hv[q] = 0.0f; lv[q] = 0.0f;
+          hv[q] = 0.0f;
           if (i < D && nrow < N) {
             if (ms[row][il]) { nmasked++; }
             else {
               const float v = xs[row][il];
               f |= k2_classify(v);
-              const float c = __fsub_rn(v, mean[i]);
-              const __nv_bfloat16 h = __float2bfloat16(c);
-              const float lo_f = __fsub_rn(c, __bfloat162float(h));
-              const __nv_bfloat16 l = __float2bfloat16(lo_f);
-              const float res = __fsub_rn(lo_f, __bfloat162float(l));
-              hv[q] = __bfloat162float(h);
-              lv[q] = __bfloat162float(l);
+              const float c = __fmul_rn(__fsub_rn(v, mean[i]), sc);
+              const float h = __half2float(__float2half_rn(c));
+              if (!(fabsf(h) < INFINITY)) f |= ROW_RANGE;
+              const float res = __fsub_rn(c, h);
+              hv[q] = h;
               n2 += (double)c * c;
-              nlo2 += (double)lv[q] * lv[q];
               nr2 += (double)res * res;
             }
           }
         }
-        hi_w[p] = bf16x2_bits(hv[0], hv[1]);
-        lo_w[p] = bf16x2_bits(lv[0], lv[1]);
+        hw[p] = half2_bits(hv[0], hv[1]);
       }
-      const int ch = half * 2 + grp;                            // chunk of 8 inside the slab
-      const uint4 hq = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-      const uint4 lq = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-      img_s[0][ch][row] = hq;       // x_hi against -2 m_hi
-      img_s[1][ch][row] = hq;       // x_hi against -2 m_lo
-      img_s[2][ch][row] = lq;       // x_lo against -2 m_hi
+      img_s[half * 2 + grp][row] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }
     __syncthreads();
-    // phase 3: the three regions are contiguous runs of (chunks x 128) uint4 in the image
+    // phase 3: (chunks x 128) uint4 form one contiguous run of the image
     const int nch = min(K2_PS, Dp - d0) / 8;
-    for (int t = tid; t < 3 * nch * K2_TM; t += 256) {
-      const int reg = t / (nch * K2_TM), rem = t % (nch * K2_TM);
-      const int ch = rem / K2_TM, r = rem % K2_TM;
-      img[((long)(reg * Dp + d0) / 8 + ch) * K2_TM + r] = img_s[reg][ch][r];
+    for (int t = tid; t < nch * K2_TM; t += 256) {
+      const int ch = t / K2_TM, r = t % K2_TM;
+      img[((long)d0 / 8 + ch) * K2_TM + r] = img_s[ch][r];
     }
   }
-  // tail: the column(s) of ones that pick up ||m'||^2, then zero padding up to Kp
-  for (int t = tid; t < (Kp - 3 * Dp) / 8 * K2_TM; t += 256) {
+  // tail: the columns of ones that pick up ||m'||^2, then zero padding up to Kp
+  for (int t = tid; t < (Kp - Dp) / 8 * K2_TM; t += 256) {
     const int ch = t / K2_TM, r = t % K2_TM;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (ch == 0 && n0 + r < N) { v.x = bf16x2_bits(1.0f, 1.0f); v.y = bf16x2_bits(1.0f, 0.0f); }
-    img[((long)(3 * Dp) / 8 + ch) * K2_TM + r] = v;
+    if (ch == 0 && n0 + r < N) { v.x = half2_bits(1.0f, 1.0f); v.y = half2_bits(1.0f, 0.0f); }
+    img[((long)Dp / 8 + ch) * K2_TM + r] = v;
   }
   // combine the two halves of every row
   __syncthreads();
-  if (half == 1) { red[row][0] = n2; red[row][1] = nlo2; red[row][2] = nr2; redi[row][0] = (int)f; redi[row][1] = nmasked; }
+  if (half == 1) { red[row][0] = n2; red[row][1] = nr2; redi[row][0] = (int)f; redi[row][1] = nmasked; }
   __syncthreads();
   if (half == 0 && nrow < N) {
-    n2 += red[row][0]; nlo2 += red[row][1]; nr2 += red[row][2];
+    n2 += red[row][0]; nr2 += red[row][1];
     f |= (unsigned)redi[row][0]; nmasked += redi[row][1];
     if (nmasked > 0) f |= ROW_MASKED;
     if (nmasked == D) f |= ROW_ALLMASKED;
     const long n = nrow;
     flags[n] = (unsigned char)f;
+    // ---- error bound of the tensor-core score for this row (double; scaled units)
+    const CbStats cs = *cst;
+    const double up = 1.0001;
+    const double nx = sqrt(n2) * up, nrx = sqrt(nr2) * up;
+    const double NM = cs.nm, nrm = cs.nrm, nm2 = cs.nm2;
+    const double nxh = nx + nrx, NMh = NM + nrm;
+    const double amag = 2.0 * nxh * NMh + nm2;                         // bound on |partial sums|, |score|
+    const double e_dot = 2.0 * (nrx * NM + nxh * nrm);                 // fp16 rounding of both operands
+    const double e_norm = ldexp(nm2, -23) + ldexp(1.0, -22);           // ||m'||^2 as three fp16 terms
+    const double e_acc = 2.0 * (double)(Kp / 16) * 17.0 * ldexp(amag, -23);   // FP32 accumulation in the tensor core
+    const double e_pack = pack_bits ? ldexp(amag, pack_bits - 22) : 0.0;      // index bits in the mantissa
+    const double E = (e_dot + e_norm + e_acc + e_pack) * up;
+    // slack of the certificate's other roundings: centring (eta), the reference's own sum (gamma)
+    const double dmax = (nx + NM) * (nx + NM);
+    const double eta = ldexp(nx + NM, -23);
+    const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01 + 1e-6;
+    const double slack = 4.0 * (2.0 * eta * (nx + NM) + gamma * dmax);
     RowStats s;
-    const float up = 1.0001f;
     s.nx2 = n2;
-    s.nx = (float)sqrt(n2) * up;
-    s.nxlo = (float)sqrt(nlo2) * up;
-    s.nrx = (float)sqrt(nr2) * up;
+    s.nx = (float)nx * 1.0001f;
+    s.E = (float)E * 1.0001f;
+    s.delta = (float)(2.02 * E + slack) * 1.0001f;
     s.pad = 0.0f;
     rs[n] = s;
     if (f & ROW_ALLMASKED) {
@@ -264,12 +314,11 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
       for (int t = 0; t < k; t++) { idx[n * k + t] = -1; diff[n * k + t] = (k == 1) ? -1.0f : FLT_MAX; }
     } else if (f & ROW_NONFINITE) {
       listS[atomicAdd(&counters[1], 1)] = (int)n;
-    } else if (f & (ROW_TINY | ROW_MASKED)) {
+    } else if (f & (ROW_TINY | ROW_MASKED | ROW_RANGE)) {
       listW[atomicAdd(&counters[0], 1)] = (int)n;
     }
   }
 }
-
 // ---------------------------------------------------------------- GEMM + fused top-k
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   // no-swizzle K-major canonical layout: core matrix = 8 rows x 16 B, contiguous 128 B;
@@ -283,7 +332,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
@@ -333,26 +382,16 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
 }
 
-__device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
-  // 3-input minima (FMNMX3): 32 -> 11 -> 4 -> 2 -> 1
-  float a[11];
-#pragma unroll
-  for (int t = 0; t < 10; t++)
-    a[t] = fminf(fminf(__uint_as_float(v[3 * t]), __uint_as_float(v[3 * t + 1])), __uint_as_float(v[3 * t + 2]));
-  a[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-  float b0 = fminf(fminf(a[0], a[1]), a[2]), b1 = fminf(fminf(a[3], a[4]), a[5]);
-  float b2 = fminf(fminf(a[6], a[7]), a[8]), b3 = fminf(a[9], a[10]);
-  return fminf(fminf(b0, b1), fminf(b2, b3));
+// instruction descriptor: D=F32, A=B=F16 (format 0), both K-major, N=256, M=128
+__device__ __forceinline__ uint32_t k2_idesc() {
+  return (1u << 4) | ((uint32_t)(K2_TN >> 3) << 17) | ((uint32_t)(K2_TM >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- streaming kernel (k >= 2 / long K)
 // TG: candidates kept per row, TT: smallest keys tracked per code tile.
-// GROUP mode (k == 1): the epilogue only tracks the minimum of every group of 32 columns
-// (~0.8 ALU op per score instead of 4) and keeps the TG best GROUPS per row; all 32 codes of
-// those groups are re-ranked exactly, and every code outside them has a score >= the
-// (TG+1)-th smallest group minimum, which is what the certificate needs.
-template <int TG, int TT, bool GROUP>
+template <int TG, int TT>
 __global__ void __launch_bounds__(K2_THREADS, 1)
-k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__restrict__ Bimg, long N,
+k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg, long N,
                long M, int Kp, int a_res, int32_t *__restrict__ cand, float *__restrict__ thr) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const size_t a_res_bytes = a_res ? (size_t)K2_TM * Kp * 2 : 0;
@@ -396,7 +435,6 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
         const unsigned char *gA = reinterpret_cast<const unsigned char *>(Aimg) + (size_t)tile * K2_TM * Kp * 2;
         if (a_res) {
           mbar_wait(aempty, (tcount & 1) ^ 1);           // previous tile's MMAs have consumed A
-          // a bulk copy moves < 1 MiB; the resident image is at most 80 KB: one transaction
           mbar_arrive_expect_tx(afull, (uint32_t)a_res_bytes);
           bulk_g2s(sAres, gA, (uint32_t)a_res_bytes, afull);
         }
@@ -418,9 +456,7 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
   } else if (warp == 5) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K2_TN >> 3) << 17) |
-                             ((uint32_t)(K2_TM >> 4) << 24);
+      const uint32_t idesc = k2_idesc();
       unsigned seq = 0, acc_seq = 0, tcount = 0;
       for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
         if (a_res) { mbar_wait(afull, tcount & 1); tc_fence_after(); }
@@ -441,7 +477,7 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
               // one MMA consumes K=16 = two 8-element chunks, K2_T? * 16 bytes apart
               const uint64_t da = umma_desc(aBase + kk * 2 * (K2_TM * 16), K2_TM * 16, 128);
               const uint64_t db = umma_desc(bBase + kk * 2 * (K2_TN * 16), K2_TN * 16, 128);
-              umma_bf16(d_tmem, da, db, idesc, (sl | kk) ? 1u : 0u);
+              umma_f16(d_tmem, da, db, idesc, (sl | kk) ? 1u : 0u);
             }
             umma_commit(&empty[st]);                // smem slot reusable once these MMAs retire
           }
@@ -451,72 +487,6 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
       }
     }
   } else {
-    if constexpr (GROUP) {
-    // ===================== epilogue, group mode: one row per thread =====================
-    unsigned acc_seq = 0;
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      float gk[TG + 1];
-      int gi[TG + 1];
-#pragma unroll
-      for (int t = 0; t <= TG; t++) { gk[t] = INFINITY; gi[t] = -1; }
-      for (int ct = 0; ct < nct; ct++, acc_seq++) {
-        const int buf = acc_seq & 1;
-        mbar_wait(&tfull[buf], (acc_seq >> 1) & 1);
-        tc_fence_after();
-        // tile-level top-(TG+1) group minima; the 3 low mantissa bits carry the group number
-        float tk[TG + 1];
-#pragma unroll
-        for (int t = 0; t <= TG; t++) tk[t] = INFINITY;
-        uint32_t va[32], vb[32];
-        tmem_ld32_nowait(lane_base + buf * K2_TN, va);
-#pragma unroll
-        for (int g = 0; g < K2_TN / 32; g += 2) {
-          tmem_ld_wait32(va);
-          tmem_ld32_nowait(lane_base + buf * K2_TN + (g + 1) * 32, vb);     // overlap with the min tree
-          {
-            float key = __uint_as_float((__float_as_uint(min32(va)) & 0xFFFFFFF8u) | (uint32_t)g);
-#pragma unroll
-            for (int t = 0; t <= TG; t++) { float lo = fminf(tk[t], key); key = fmaxf(tk[t], key); tk[t] = lo; }
-          }
-          tmem_ld_wait32(vb);
-          if (g + 2 < K2_TN / 32) tmem_ld32_nowait(lane_base + buf * K2_TN + (g + 2) * 32, va);
-          {
-            float key = __uint_as_float((__float_as_uint(min32(vb)) & 0xFFFFFFF8u) | (uint32_t)(g + 1));
-#pragma unroll
-            for (int t = 0; t <= TG; t++) { float lo = fminf(tk[t], key); key = fmaxf(tk[t], key); tk[t] = lo; }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-#pragma unroll
-        for (int t = 0; t <= TG; t++) {
-          float key = tk[t];
-          int j = ct * (K2_TN / 32) + (int)(__float_as_uint(key) & 7u);      // global group index
-          if (key < gk[TG]) {
-            bool ins = false;
-#pragma unroll
-            for (int p = 0; p <= TG; p++) {
-              if (ins || key < gk[p]) {
-                float t2 = gk[p]; int i2 = gi[p];
-                gk[p] = key; gi[p] = j;
-                key = t2; j = i2;
-                ins = true;
-              }
-            }
-          }
-        }
-      }
-      const long n = tile * K2_TM + row;
-      if (n < N) {
-#pragma unroll
-        for (int t = 0; t < TG; t++) cand[n * TG + t] = gi[t];
-        thr[n] = gk[TG];           // every group that was not kept has a minimum >= this key
-      }
-    }
-    } else {
     // ===================== epilogue: one row per thread =====================
     unsigned acc_seq = 0;
     const int row = warp * 32 + lane;
@@ -607,10 +577,234 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
       }
     }
   }
-    }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+// ---------------------------------------------------------------- record kernel (k == 1, short K)
+// Per 32 scores of a row: a min tree (15 FMNMX3/FMNMX); only if the minimum is below the row's
+// running threshold thr = best + delta does the thread look at individual columns and append
+// the ones below thr to a small ring in shared memory.  Invariant: a column that is never
+// appended had score >= thr at that time >= final best + delta; an entry pushed out of the
+// ring lowers `lost`.  The slow path is kept SMALL (one out-of-line append, no sorted lists):
+// the SM's instruction caches are 6 KB / 32 KB and a divergent, unrolled slow path of tens of
+// KB was measured to cost ~7000 cycles per trigger in instruction fetches alone.
+constexpr int K2R_PACK = 5;       // low mantissa bits that carry the column inside a 32-column chunk
+
+// per-row state of the record epilogue: running best key, threshold best + delta, the two
+// smallest keys seen so far with their code indices, and `lost` = lower bound of every key
+// that was looked at but is not (or no longer) one of the two
+struct K2RRow {
+  float best, thr, lost, k0, k1;
+  int i0, i1;
+};
+
+// fold 8 columns (chunk-relative columns base .. base+7) into the two smallest packed keys
+__device__ __forceinline__ void k2r_fold8(const uint32_t *w, unsigned base, float &b0, float &b1) {
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    const float k0 = __uint_as_float((w[c] & ~31u) | (base + c));
+    const float k1 = __uint_as_float((w[c + 1] & ~31u) | (base + c + 1));
+    const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+    const float t = fmaxf(b0, lo);
+    b0 = fminf(b0, lo);
+    b1 = fminf(fminf(b1, hi), t);
+  }
+}
+
+// one 32-column chunk of one row (code columns col0 .. col0+31)
+template <int DBG>
+__device__ __forceinline__ void k2r_chunk(const uint32_t (&v)[32], int col0, float delta, bool warm, K2RRow &r) {
+  if (DBG == 2) { r.best = fminf(r.best, __uint_as_float(v[0] ^ v[31])); return; }
+  // minima of the four 8-column groups (3-input FMNMX3), then of the chunk: 0.56 ALU op per score
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float a0 = fminf(fminf(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])), __uint_as_float(v[8 * q + 2]));
+    const float a1 = fminf(fminf(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4])), __uint_as_float(v[8 * q + 5]));
+    g[q] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+  }
+  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+  if (DBG == 1 || warm) { r.best = fminf(r.best, m); return; }
+  if (__any_sync(0xffffffffu, m < r.thr)) {
+    // ---- slow path (warp-uniform entry, straight-line, predicated): two smallest keys of the
+    // 8-column groups that some lane needs, column packed into the low mantissa bits
+    if (DBG == 3) return;
+    float b0 = INFINITY, b1 = INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (__any_sync(0xffffffffu, g[q] < r.thr)) k2r_fold8(&v[8 * q], 8u * q, b0, b1);
+    if (DBG == 4) { r.lost = fminf(r.lost, b0 + b1); return; }
+    // lanes that did not trigger have b0 >= thr (no column of theirs is below it)
+    const bool ins = b0 < r.thr;
+    const int i = col0 + (int)(__float_as_uint(b0) & 31u);
+    const bool first = ins && b0 < r.k0, second = ins && !first && b0 < r.k1;
+    // the key that leaves the pair (or b0 itself when it does not enter) bounds what is dropped
+    r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? b0 : INFINITY));
+    r.k1 = first ? r.k0 : (second ? b0 : r.k1);
+    r.i1 = first ? r.i0 : (second ? i : r.i1);
+    r.k0 = first ? b0 : r.k0;
+    r.i0 = first ? i : r.i0;
+    r.best = ins ? fminf(r.best, b0) : r.best;
+    r.thr = ins ? __fadd_ru(r.best, delta) : r.thr;
+    // only b0 is kept from this chunk; everything else of it is >= b1
+    r.lost = (ins && b1 < r.thr) ? fminf(r.lost, b1) : r.lost;
+  }
+}
+
+template <int R, int DBG>
+__global__ void __launch_bounds__(K2R_THREADS, 1)
+k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
+              const RowStats *__restrict__ rs, long N, long M, int Kp,
+              int32_t *__restrict__ cand, float *__restrict__ thr) {
+  static_assert(R % 2 == 0, "row tiles alternate between the two accumulators");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t a_tile_bytes = (uint32_t)K2_TM * Kp * 2, b_tile_bytes = (uint32_t)K2_TN * Kp * 2;
+  unsigned char *sA = smem;                                   // R row tiles
+  unsigned char *sB = smem + (size_t)R * a_tile_bytes;        // K2R_BST code tiles
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)K2R_BST * b_tile_bytes);
+  uint64_t *full = bars, *empty = bars + K2R_BST;
+  uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + 2;
+  uint64_t *afull = tempty + 2, *aempty = afull + 1;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(aempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long ntiles = (N + K2_TM - 1) / K2_TM;
+  const long nsuper = (ntiles + R - 1) / R;
+  const int nct = (int)((M + K2_TN - 1) / K2_TN);
+  // warm-up: the first code tile is visited twice, first only for its minimum.  Most of a row's
+  // running-minimum records fall into the first columns it sees (harmonic series); with the
+  // threshold already tight the real pass triggers the slow path ~3x less often.
+  const int nwarm = nct >= 4 ? 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < K2R_BST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    mbar_init(afull, 1);
+    mbar_init(aempty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      unsigned bseq = 0, tcount = 0;
+      for (long st = blockIdx.x; st < nsuper; st += gridDim.x, tcount++) {
+        // the image is allocated for nsuper*R tiles; tiles past the last row hold don't-care bits
+        const unsigned char *gA = reinterpret_cast<const unsigned char *>(Aimg) + (size_t)st * R * a_tile_bytes;
+        mbar_wait(aempty, (tcount & 1) ^ 1);             // previous pass's MMAs have consumed A
+        mbar_arrive_expect_tx(afull, (uint32_t)R * a_tile_bytes);
+#pragma unroll
+        for (int r = 0; r < R; r++) bulk_g2s(sA + (size_t)r * a_tile_bytes, gA + (size_t)r * a_tile_bytes, a_tile_bytes, afull);
+        for (int qt = 0; qt < nct + nwarm; qt++, bseq++) {
+          const int ct = qt < nwarm ? qt : qt - nwarm;
+          const int s = bseq % K2R_BST;
+          mbar_wait(&empty[s], ((bseq / K2R_BST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], b_tile_bytes);
+          bulk_g2s(sB + (size_t)s * b_tile_bytes,
+                   reinterpret_cast<const unsigned char *>(Bimg) + (size_t)ct * b_tile_bytes, b_tile_bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = k2_idesc();
+      const int nk = Kp / 16;
+      unsigned bseq = 0, tcount = 0, use[2] = {0u, 0u};
+      for (long st = blockIdx.x; st < nsuper; st += gridDim.x, tcount++) {
+        mbar_wait(afull, tcount & 1);
+        tc_fence_after();
+        for (int qt = 0; qt < nct + nwarm; qt++, bseq++) {
+          const int s = bseq % K2R_BST;
+          mbar_wait(&full[s], (bseq / K2R_BST) & 1);
+          tc_fence_after();
+          const uint32_t bBase = smem_u32(sB + (size_t)s * b_tile_bytes);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int buf = r & 1;
+            mbar_wait(&tempty[buf], (use[buf] & 1) ^ 1);       // epilogue group `buf` drained it
+            use[buf]++;
+            tc_fence_after();
+            const uint32_t aBase = smem_u32(sA) + (uint32_t)r * a_tile_bytes;
+            const uint32_t d_tmem = tmem_base + buf * K2_TN;
+            for (int kk = 0; kk < nk; kk++) {
+              const uint64_t da = umma_desc(aBase + kk * 2 * (K2_TM * 16), K2_TM * 16, 128);
+              const uint64_t db = umma_desc(bBase + kk * 2 * (K2_TN * 16), K2_TN * 16, 128);
+              umma_f16(d_tmem, da, db, idesc, kk ? 1u : 0u);
+            }
+            umma_commit(&tfull[buf]);
+          }
+          umma_commit(&empty[s]);                   // code tile slot reusable once all R products retire
+        }
+        umma_commit(aempty);
+      }
+    }
+  } else {
+    // ===================== epilogue: group g = warp / 4 owns accumulator g and row tiles g, g+2 =====
+    // One code instance serves both rows of a thread: the per-row state is selected at the
+    // start of every accumulation (keeps the loop body inside the instruction cache).
+    static_assert(R == 4, "two rows per epilogue thread");
+    const int g = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + g * K2_TN;
+    unsigned use = 0;
+    for (long st = blockIdx.x; st < nsuper; st += gridDim.x) {
+      const long n0 = (st * R + g) * K2_TM + row, n1 = n0 + 2 * K2_TM;
+      const float delta0 = n0 < N ? rs[n0].delta : 0.0f, delta1 = n1 < N ? rs[n1].delta : 0.0f;
+      K2RRow r0 = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1}, r1 = r0;
+      for (int q = 0; q < 2 * (nct + nwarm); q++) {
+        const int j = q & 1, qt = q >> 1;
+        const bool warm = qt < nwarm;
+        const int ct = warm ? qt : qt - nwarm;
+        K2RRow r = j ? r1 : r0;
+        const float delta = j ? delta1 : delta0;
+        mbar_wait(&tfull[g], use & 1);
+        use++;
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(tbase, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < K2_TN; c0 += 64) {
+          tmem_ld_wait32(va);
+          tmem_ld32_nowait(tbase + c0 + 32, vb);
+          k2r_chunk<DBG>(va, ct * K2_TN + c0, delta, warm, r);
+          tmem_ld_wait32(vb);
+          if (c0 + 64 < K2_TN) tmem_ld32_nowait(tbase + c0 + 64, va);
+          k2r_chunk<DBG>(vb, ct * K2_TN + c0 + 32, delta, warm, r);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[g]);
+        if (warm && qt == nwarm - 1) r.thr = __fadd_ru(r.best, delta);     // threshold from the warm-up tiles
+        if (j) r1 = r; else r0 = r;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const long n = j ? n1 : n0;
+        if (n < N) {
+          const K2RRow r = j ? r1 : r0;
+          const float bound = r.thr;                      // final best + delta (rounded up)
+          const int c0 = (r.k0 < bound && r.i0 < M) ? r.i0 : -1, c1 = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
+          *reinterpret_cast<int4 *>(cand + n * K2R_TG) = make_int4(c0, c1, -1, -1);
+          // never looked at: >= best + delta; looked at and dropped: >= lost
+          thr[n] = fminf(bound, r.lost);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 // ---------------------------------------------------------------- exact re-rank + certificate
@@ -620,7 +814,7 @@ k2_gemm_kernel(const __nv_bfloat16 *__restrict__ Aimg, const __nv_bfloat16 *__re
 template <int TG, int LPR>
 __global__ void __launch_bounds__(256)
 k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M, int D,
-                 int k, int Kp, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
+                 int k, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
                  const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
                  const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
                  int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
@@ -679,25 +873,18 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
       else sw = cd[b] < cd[a] || (cd[b] == cd[a] && (knn_rule ? ci[b] > ci[a] : ci[b] < ci[a]));
       if (sw) { float td = cd[a]; cd[a] = cd[b]; cd[b] = td; int ti = ci[a]; ci[a] = ci[b]; ci[b] = ti; }
     }
-  // ---- certificate (double arithmetic; any NaN makes it fail)
+  // ---- certificate (double arithmetic; any NaN makes it fail).  In scaled units every code
+  // that is not a candidate has  ||s x' - s m'||^2 >= nx2 + thr - E =: Lc.
   const RowStats s = rs[n];
   const CbStats cs = *cst;
-  const double nx = s.nx, NM = cs.nm;
-  const double amag = 2.0 * nx * NM + (double)cs.nm2;                  // bound on |partial sums|, |score|
-  const double e_dot = 2.0 * ((double)s.nxlo * cs.nmlo + (double)s.nrx * NM + nx * (double)cs.nrm);
-  const double e_norm = ldexp((double)cs.nm2, -25);
-  const double e_acc = 2.0 * (double)(Kp / 16) * 17.0 * ldexp(amag, -23);
-  const double e_pack = ldexp(amag, -14);
-  const double E = (e_dot + e_norm + e_acc + e_pack) * 1.0001;
-  const double Lc = s.nx2 + (double)thr[n] - E;                         // lower bound, centred exact distance
-  const double eta = ldexp(nx + NM, -23);                               // centring rounding, both vectors
+  const double Lc = s.nx2 + (double)thr[n] - (double)s.E;
+  const double eta = ldexp((double)s.nx + (double)cs.nm, -23);         // centring rounding, both vectors
   bool ok = false;
-  double L = 0.0;
   if (Lc > 0.0) {
     const double r = sqrt(Lc) - eta;
     if (r > 0.0) {
       const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;     // reference's own rounding
-      L = r * r * (1.0 - gamma) * (1.0 - 1e-6);
+      const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6) * (double)cs.inv_s2;
       // the k-th winner must be strictly below every non-candidate; all real candidates needed
       const int need = k < (int)M ? k : (int)M;
       ok = nc >= need && need >= 1 && (double)cd[need - 1] < L && cd[need - 1] < FLT_MAX;
@@ -719,99 +906,9 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
   nfound[n] = k;
 }
 
-// ---------------------------------------------------------------- group re-rank (k == 1)
-// One warp per row: lane l computes the exact distance to code 32*g + l of each candidate
-// group g, the warp takes the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and
-// lane 0 evaluates the certificate against the (NG+1)-th smallest group minimum.
-template <int NG>
-__global__ void __launch_bounds__(256)
-k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M,
-                       int D, int Kp, const unsigned char *__restrict__ flags,
-                       const RowStats *__restrict__ rs, const CbStats *__restrict__ cst,
-                       const int32_t *__restrict__ cand, const float *__restrict__ thr,
-                       int *__restrict__ listW, int *__restrict__ counters, int32_t *__restrict__ idx,
-                       float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  const int lane = threadIdx.x & 31;
-  const long n = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  if (n >= N || flags[n] != 0) return;                 // warp-uniform
-  const float *x = data + n * (long)D;
-  u64 best = ~0ull;
-  int ncodes = 0;
-#pragma unroll
-  for (int gsel = 0; gsel < NG; gsel++) {
-    const int gid = cand[n * NG + gsel];
-    if (gid < 0) continue;
-    const long j = (long)gid * 32 + lane;
-    ncodes += (int)min(32L, max(0L, M - (long)gid * 32));
-    if (j >= M) continue;
-    const float *c = codes + j * D;
-    float acc = 0.0f;
-    if ((D & 3) == 0) {
-      const float4 *x4 = reinterpret_cast<const float4 *>(x);
-      const float4 *c4 = reinterpret_cast<const float4 *>(c);
-#pragma unroll 4
-      for (int i = 0; i < D / 4; i++) {
-        const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i);
-        acc = sq_acc(acc, cv.x, xv.x);
-        acc = sq_acc(acc, cv.y, xv.y);
-        acc = sq_acc(acc, cv.z, xv.z);
-        acc = sq_acc(acc, cv.w, xv.w);
-      }
-    } else {
-      for (int i = 0; i < D; i++) acc = sq_acc(acc, __ldg(c + i), __ldg(x + i));
-    }
-    // only d < FLT_MAX can win; non-negative floats order like their bit patterns
-    if (acc < FLT_MAX) {
-      const u64 key = ((u64)__float_as_uint(acc) << 32) | (unsigned)j;
-      best = key < best ? key : best;
-    }
-  }
-  {
-    const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
-    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-    best = ((u64)mh << 32) | ml;
-  }
-  if (lane != 0) return;
-  const float dbest = __uint_as_float((unsigned)(best >> 32));
-  const int jbest = (int)(unsigned)best;
-  bool ok = false;
-  if (best != ~0ull) {
-    const RowStats s = rs[n];
-    const CbStats cs = *cst;
-    const double nx = s.nx, NM = cs.nm;
-    const double amag = 2.0 * nx * NM + (double)cs.nm2;
-    const double e_dot = 2.0 * ((double)s.nxlo * cs.nmlo + (double)s.nrx * NM + nx * (double)cs.nrm);
-    const double e_norm = ldexp((double)cs.nm2, -25);
-    const double e_acc = 2.0 * (double)(Kp / 16) * 17.0 * ldexp(amag, -23);
-    const double e_pack = ldexp(amag, -19);                 // 3 low mantissa bits carry the group number
-    const double E = (e_dot + e_norm + e_acc + e_pack) * 1.0001;
-    const double Lc = s.nx2 + (double)thr[n] - E;
-    const double eta = ldexp(nx + NM, -23);
-    if (Lc > 0.0) {
-      const double r = sqrt(Lc) - eta;
-      if (r > 0.0) {
-        const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;
-        const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6);
-        ok = (double)dbest < L;
-      }
-    }
-    if (ncodes >= M) ok = true;                             // every code was re-ranked
-  }
-  if (!ok) {
-    listW[atomicAdd(&counters[0], 1)] = (int)n;
-    atomicAdd(&counters[3], 1);
-    return;
-  }
-  atomicAdd(&counters[2], 1);
-  idx[n] = jbest;
-  diff[n] = dbest;
-  nfound[n] = 1;
-}
-
 // ---------------------------------------------------------------- host side
 struct K2Scratch {      // carved out of one grow-only device buffer
-  __nv_bfloat16 *Aimg;
+  __half *Aimg;
   RowStats *rs;
   int32_t *cand;
   float *thr;
@@ -850,16 +947,18 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
     c->ops_bytes = need;
   }
   if (!c->d_norm) {
-    // [CbStats (16 B)] [mean: D floats]
+    // [CbStats (64 B reserved)] [mean: D floats]
     if ((e = cudaMalloc((void **)&c->d_norm, 64 + sizeof(float) * 8192)) != cudaSuccess) return e;
   }
   if ((e = cudaMemsetAsync(c->d_norm, 0, 64, st)) != cudaSuccess) return e;
   float *mean = c->d_norm + 16;
+  CbStats *cst = (CbStats *)c->d_norm;
   k2_mean_kernel<<<(a.D + 127) / 128, 128, 0, st>>>(a.codes, a.M, a.D, mean);
+  k2_cb_norm_kernel<<<(unsigned)((a.M * 32 + 255) / 256), 256, 0, st>>>(a.codes, a.M, a.D, mean, cst);
   const long warps = nct * K2_TN;
   k2_cb_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-      a.codes, a.M, a.D, mean, (__nv_bfloat16 *)c->d_ops, (CbStats *)c->d_norm);
-  k1_count_launch(2);
+      a.codes, a.M, a.D, mean, (__half *)c->d_ops, cst);
+  k1_count_launch(3);
   c->Kp = Kp;
   c->valid = 1;
   return cudaGetLastError();
@@ -868,33 +967,54 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
 static cudaEvent_t g_k2ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 static bool g_k2ev_valid = false;
 
-template <int TG, int TT, bool GROUP>
-static cudaError_t k2_run(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+template <int TG>
+static cudaError_t k2_run_rerank(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+  constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
+  const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
+  k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
+      a.data, a.codes, a.N, a.M, a.D, a.k, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
+      a.listW, a.counters, a.idx, a.diff, a.nfound);
+  k1_count_launch(1);
+  return cudaGetLastError();
+}
+
+template <int TG, int TT>
+static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   const int Kp = c->Kp;
   const bool a_res = Kp <= K2_ARES_MAX_KP;
   const size_t smem = K2Smem::bytes(Kp, a_res);
-  cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long ntiles = (a.N + K2_TM - 1) / K2_TM;
   const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
-  k2_gemm_kernel<TG, TT, GROUP><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __nv_bfloat16 *)c->d_ops, a.N, a.M, Kp,
+  k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, a.N, a.M, Kp,
                                                         a_res ? 1 : 0, s.cand, s.thr);
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
-  if constexpr (GROUP) {
-    k2_rerank_group_kernel<TG><<<(unsigned)((a.N + 7) / 8), 256, 0, st>>>(
-        a.data, a.codes, a.N, a.M, a.D, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
-        a.listW, a.counters, a.idx, a.diff, a.nfound);
-  } else {
-    constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
-    const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
-    k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
-        a.data, a.codes, a.N, a.M, a.D, a.k, Kp, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
-        a.listW, a.counters, a.idx, a.diff, a.nfound);
-  }
+  return k2_run_rerank<TG>(c, a, s, st);
+}
+
+static size_t k2r_smem_bytes(int Kp) {
+  return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)K2R_BST * K2_TN * Kp * 2 + 256;
+}
+
+static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+  const int Kp = c->Kp;
+  const size_t smem = k2r_smem_bytes(Kp);
+  static int dbg = getenv("BMU_K2_DEBUG") ? atoi(getenv("BMU_K2_DEBUG")) : 0;
+  auto kern = dbg == 1 ? k2_rec_kernel<K2R_R, 1> : dbg == 2 ? k2_rec_kernel<K2R_R, 2> : dbg == 3 ? k2_rec_kernel<K2R_R, 3> : dbg == 4 ? k2_rec_kernel<K2R_R, 4> : k2_rec_kernel<K2R_R, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long ntiles = (a.N + K2_TM - 1) / K2_TM;
+  const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
+  const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
+  kern<<<grid, K2R_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
+                                                       s.cand, s.thr);
   k1_count_launch(1);
-  return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  cudaEventRecord(g_k2ev[2], st);
+  return k2_run_rerank<K2R_TG>(c, a, s, st);
 }
 
 cudaError_t k2_last_kernel_ms(float out[4]) {
@@ -914,11 +1034,14 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
       if ((e = cudaEventCreate(&g_k2ev[i])) != cudaSuccess) return e;
   if (!c->valid && (e = k2_build_codebook(c, a, st)) != cudaSuccess) return e;
   const int Kp = c->Kp;
+  // k == 1 and a code tile that fits a shared-memory stage: record kernel; else K streamed in slabs
+  const bool record = a.k == 1 && Kp <= K2R_MAX_KP;
   const int TG = a.k == 1 ? 4 : (a.k <= 5 ? 10 : 20);
   const long ntiles = (a.N + K2_TM - 1) / K2_TM;
+  const long ntiles_alloc = (ntiles + K2R_R - 1) / K2R_R * K2R_R;   // the record kernel loads whole groups of tiles
   // scratch layout
   size_t off = 0;
-  const size_t oA = off; off = align_up(off + (size_t)ntiles * K2_TM * Kp * 2, 256);
+  const size_t oA = off; off = align_up(off + (size_t)ntiles_alloc * K2_TM * Kp * 2, 256);
   const size_t oR = off; off = align_up(off + (size_t)a.N * sizeof(RowStats), 256);
   const size_t oC = off; off = align_up(off + (size_t)a.N * TG * 4, 256);
   const size_t oT = off; off = align_up(off + (size_t)a.N * 4, 256);
@@ -931,25 +1054,24 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   }
   K2Scratch s;
   unsigned char *base = (unsigned char *)*scratch;
-  s.Aimg = (__nv_bfloat16 *)(base + oA);
+  s.Aimg = (__half *)(base + oA);
   s.rs = (RowStats *)(base + oR);
   s.cand = (int32_t *)(base + oC);
   s.thr = (float *)(base + oT);
 
   if ((e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[0], st);
-  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, c->d_norm + 16, s.Aimg,
+  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, record ? K2R_PACK : 8,
+                                                      c->d_norm + 16, (const CbStats *)c->d_norm, s.Aimg,
                                                       s.rs, a.flags, a.listW, a.listS, a.counters, a.idx,
                                                       a.diff, a.nfound);
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[1], st);
-  // k == 1: group mode for short contractions (the 4-op/score epilogue would outlast the MMAs);
-  // long contractions keep the element mode, whose re-rank touches 4 instead of 64 code rows
-  if (a.k == 1 && Kp <= K2_GROUP_MAX_KP) e = k2_run<2, 2, true>(c, a, s, st);
-  else if (a.k == 1) e = k2_run<4, 2, false>(c, a, s, st);
-  else if (a.k <= 5) e = k2_run<10, 4, false>(c, a, s, st);
-  else e = k2_run<20, 4, false>(c, a, s, st);
+  if (record) e = k2_run_record(c, a, s, st);
+  else if (a.k == 1) e = k2_run_stream<4, 2>(c, a, s, st);
+  else if (a.k <= 5) e = k2_run_stream<10, 4>(c, a, s, st);
+  else e = k2_run_stream<20, 4>(c, a, s, st);
   if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[3], st);
   // rows that failed the certificate + masked / tiny rows, then the non-finite rows
