@@ -45,10 +45,12 @@ constexpr int K2_NSTAGE = 4;
 constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp (streaming kernel)
 
-constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel
+constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel = epilogue groups = accumulators
 constexpr int K2R_BST = 3;        // staged code tiles
-constexpr int K2R_THREADS = 320;  // warps 0-7 epilogue (two groups of 4), warp 8 producer, warp 9 MMA
-constexpr int K2R_TG = 4;         // candidates kept per row
+constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM)
+constexpr int K2R_THREADS = 576;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA
+constexpr int K2R_GW = 8;         // candidate granularity: groups of 8 consecutive codes
+constexpr int K2R_NG = 2;         // candidate groups kept per row
 constexpr int K2R_MAX_KP = 96;    // code tile (256 x Kp fp16) <= 48 KB
 
 struct CbStats {     // maxima over the codebook (centred, scaled), device side
@@ -155,6 +157,22 @@ k2_cb_prep_kernel(const float *__restrict__ codes, long M, int D, const float *_
     atomic_max_pos(&st->nm, (float)sqrt(n2) * up);
     atomic_max_pos(&st->nrm, (float)sqrt(nr2) * up);
     atomic_max_pos(&st->nm2, (float)n2 * up);
+  }
+}
+
+// FP32 codebook regrouped for k2_rerank_group_kernel: [group of 8 codes][4-component chunk]
+// [code in group][4 comps], so that the 8 lanes of a group read 128 contiguous bytes per float4
+__global__ void k2_cb_regroup_kernel(const float *__restrict__ codes, long M, int D, float *__restrict__ grp) {
+  const int Dq = (D + 3) / 4;
+  const long total = ((M + 7) / 8) * (long)Dq * 32;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int e = (int)(t & 3), l = (int)((t >> 2) & 7);
+    const long rest = t >> 5;
+    const int c4 = (int)(rest % Dq);
+    const long gidx = rest / Dq;
+    const long j = gidx * 8 + l;
+    const int i = c4 * 4 + e;
+    grp[t] = (j < M && i < D) ? codes[j * D + i] : 0.0f;
   }
 }
 
@@ -583,109 +601,64 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 }
 
 // ---------------------------------------------------------------- record kernel (k == 1, short K)
-// Per 32 scores of a row: a min tree (15 FMNMX3/FMNMX); only if the minimum is below the row's
-// running threshold thr = best + delta does the thread look at individual columns and append
-// the ones below thr to a small ring in shared memory.  Invariant: a column that is never
-// appended had score >= thr at that time >= final best + delta; an entry pushed out of the
-// ring lowers `lost`.  The slow path is kept SMALL (one out-of-line append, no sorted lists):
-// the SM's instruction caches are 6 KB / 32 KB and a divergent, unrolled slow path of tens of
-// KB was measured to cost ~7000 cycles per trigger in instruction fetches alone.
-constexpr int K2R_PACK = 5;       // low mantissa bits that carry the column inside a 32-column chunk
-
-// per-row state of the record epilogue: running best key, threshold best + delta, the two
-// smallest keys seen so far with their code indices, and `lost` = lower bound of every key
-// that was looked at but is not (or no longer) one of the two
+// per-row state of the record epilogue: running best score, threshold best + delta, the two
+// smallest group minima seen so far with the first code of their group, and `lost` = lower
+// bound of every group minimum that was looked at but is not (or no longer) one of the two
 struct K2RRow {
   float best, thr, lost, k0, k1;
   int i0, i1;
 };
 
-// fold 8 columns (chunk-relative columns base .. base+7) into the two smallest packed keys
-__device__ __forceinline__ void k2r_fold8(const uint32_t *w, unsigned base, float &b0, float &b1) {
-#pragma unroll
-  for (int c = 0; c < 8; c += 2) {
-    const float k0 = __uint_as_float((w[c] & ~31u) | (base + c));
-    const float k1 = __uint_as_float((w[c + 1] & ~31u) | (base + c + 1));
-    const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
-    const float t = fmaxf(b0, lo);
-    b0 = fminf(b0, lo);
-    b1 = fminf(fminf(b1, hi), t);
-  }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
 }
 
-// one 32-column chunk of one row (code columns col0 .. col0+31)
-template <int DBG>
-__device__ __forceinline__ void k2r_chunk(const uint32_t (&v)[32], int col0, float delta, bool warm, K2RRow &r) {
-  if (DBG == 2) { r.best = fminf(r.best, __uint_as_float(v[0] ^ v[31])); return; }
-  // minima of the four 8-column groups (3-input FMNMX3), then of the chunk: 0.56 ALU op per score
-  float g[4];
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const float a0 = fminf(fminf(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])), __uint_as_float(v[8 * q + 2]));
-    const float a1 = fminf(fminf(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4])), __uint_as_float(v[8 * q + 5]));
-    g[q] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
-  }
-  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-  if (DBG == 1 || warm) { r.best = fminf(r.best, m); return; }
-  if (__any_sync(0xffffffffu, m < r.thr)) {
-    // ---- slow path (warp-uniform entry, straight-line, predicated): two smallest keys of the
-    // 8-column groups that some lane needs, column packed into the low mantissa bits
-    if (DBG == 3) return;
-    float b0 = INFINITY, b1 = INFINITY;
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      if (__any_sync(0xffffffffu, g[q] < r.thr)) k2r_fold8(&v[8 * q], 8u * q, b0, b1);
-    if (DBG == 4) { r.lost = fminf(r.lost, b0 + b1); return; }
-    // lanes that did not trigger have b0 >= thr (no column of theirs is below it)
-    const bool ins = b0 < r.thr;
-    const int i = col0 + (int)(__float_as_uint(b0) & 31u);
-    const bool first = ins && b0 < r.k0, second = ins && !first && b0 < r.k1;
-    // the key that leaves the pair (or b0 itself when it does not enter) bounds what is dropped
-    r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? b0 : INFINITY));
-    r.k1 = first ? r.k0 : (second ? b0 : r.k1);
-    r.i1 = first ? r.i0 : (second ? i : r.i1);
-    r.k0 = first ? b0 : r.k0;
-    r.i0 = first ? i : r.i0;
-    r.best = ins ? fminf(r.best, b0) : r.best;
-    r.thr = ins ? __fadd_ru(r.best, delta) : r.thr;
-    // only b0 is kept from this chunk; everything else of it is >= b1
-    r.lost = (ins && b1 < r.thr) ? fminf(r.lost, b1) : r.lost;
-  }
+// N = 128 variant of the instruction descriptor
+__device__ __forceinline__ uint32_t k2r_idesc() {
+  return (1u << 4) | ((uint32_t)(K2R_TNH >> 3) << 17) | ((uint32_t)(K2_TM >> 4) << 24);
 }
 
-template <int R, int DBG>
+// Record kernel.  CTA = 4 row tiles (A resident) x all code tiles (staged whole, 3-deep ring).
+// MMA order per code tile: (half h, row tile r) -> accumulator r (128 TMEM columns each), so an
+// accumulator is rewritten every 4th MMA group and its epilogue group has 3 MMA groups of time.
+// Epilogue per 32 columns of a row: minima of the four 8-column groups and of the chunk
+// (18 FMNMX3/FMNMX, 0.56 ALU op per score).  Only if some lane's chunk minimum is below its
+// running threshold thr = best + delta (vote) does the warp run the short predicated update that
+// records the GROUP holding the minimum; the exact distances of the <= 2 x 8 codes of the
+// recorded groups are computed by k2_rerank_group_kernel.  Invariant for the certificate: a
+// group that is not recorded has a minimum >= min(final best + delta, lost).
+template <int R, int NK>
 __global__ void __launch_bounds__(K2R_THREADS, 1)
 k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
               const RowStats *__restrict__ rs, long N, long M, int Kp,
               int32_t *__restrict__ cand, float *__restrict__ thr) {
-  static_assert(R % 2 == 0, "row tiles alternate between the two accumulators");
+  static_assert(R == 4, "one epilogue group and one 128-column accumulator per row tile");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t a_tile_bytes = (uint32_t)K2_TM * Kp * 2, b_tile_bytes = (uint32_t)K2_TN * Kp * 2;
   unsigned char *sA = smem;                                   // R row tiles
   unsigned char *sB = smem + (size_t)R * a_tile_bytes;        // K2R_BST code tiles
   uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)K2R_BST * b_tile_bytes);
   uint64_t *full = bars, *empty = bars + K2R_BST;
-  uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + 2;
-  uint64_t *afull = tempty + 2, *aempty = afull + 1;
+  uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + R;
+  uint64_t *afull = tempty + R, *aempty = afull + 1;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(aempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long ntiles = (N + K2_TM - 1) / K2_TM;
   const long nsuper = (ntiles + R - 1) / R;
   const int nct = (int)((M + K2_TN - 1) / K2_TN);
-  // warm-up: the first code tile is visited twice, first only for its minimum.  Most of a row's
-  // running-minimum records fall into the first columns it sees (harmonic series); with the
-  // threshold already tight the real pass triggers the slow path ~3x less often.
-  const int nwarm = nct >= 4 ? 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K2R_BST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < R; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     mbar_init(afull, 1);
     mbar_init(aempty, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -694,7 +667,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       unsigned bseq = 0, tcount = 0;
@@ -705,8 +678,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         mbar_arrive_expect_tx(afull, (uint32_t)R * a_tile_bytes);
 #pragma unroll
         for (int r = 0; r < R; r++) bulk_g2s(sA + (size_t)r * a_tile_bytes, gA + (size_t)r * a_tile_bytes, a_tile_bytes, afull);
-        for (int qt = 0; qt < nct + nwarm; qt++, bseq++) {
-          const int ct = qt < nwarm ? qt : qt - nwarm;
+        for (int ct = 0; ct < nct; ct++, bseq++) {
           const int s = bseq % K2R_BST;
           mbar_wait(&empty[s], ((bseq / K2R_BST) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], b_tile_bytes);
@@ -715,96 +687,117 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = k2_idesc();
-      const int nk = Kp / 16;
-      unsigned bseq = 0, tcount = 0, use[2] = {0u, 0u};
-      for (long st = blockIdx.x; st < nsuper; st += gridDim.x, tcount++) {
-        mbar_wait(afull, tcount & 1);
+  } else if (warp == 17) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the loop (uniform control flow, barrier waits by every lane); one
+    // elected lane issues.  Descriptors are built once and advanced by constant offsets: the
+    // issue loop has to stay well under the 64 cycles that one 128x128x16 MMA takes.
+    const uint32_t idesc = k2r_idesc();
+    const bool leader = elect_one();
+    const uint64_t da0 = umma_desc(smem_u32(sA), K2_TM * 16, 128);
+    const uint64_t db0 = umma_desc(smem_u32(sB), K2_TN * 16, 128);
+    const uint64_t a_tile_step = (uint64_t)(a_tile_bytes >> 4), b_tile_step = (uint64_t)(b_tile_bytes >> 4);
+    unsigned bseq = 0, tcount = 0, use = 0;              // `use`: accumulations issued per accumulator so far
+    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, tcount++) {
+      mbar_wait(afull, tcount & 1);
+      tc_fence_after();
+      for (int ct = 0; ct < nct; ct++, bseq++) {
+        const int s = bseq % K2R_BST;
+        mbar_wait(&full[s], (bseq / K2R_BST) & 1);
         tc_fence_after();
-        for (int qt = 0; qt < nct + nwarm; qt++, bseq++) {
-          const int s = bseq % K2R_BST;
-          mbar_wait(&full[s], (bseq / K2R_BST) & 1);
-          tc_fence_after();
-          const uint32_t bBase = smem_u32(sB + (size_t)s * b_tile_bytes);
+        const uint64_t dbs = db0 + (uint64_t)s * b_tile_step;
+#pragma unroll
+        for (int h = 0; h < 2; h++, use++) {
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            const int buf = r & 1;
-            mbar_wait(&tempty[buf], (use[buf] & 1) ^ 1);       // epilogue group `buf` drained it
-            use[buf]++;
+            mbar_wait(&tempty[r], (use & 1) ^ 1);          // epilogue group r drained its accumulator
             tc_fence_after();
-            const uint32_t aBase = smem_u32(sA) + (uint32_t)r * a_tile_bytes;
-            const uint32_t d_tmem = tmem_base + buf * K2_TN;
-            for (int kk = 0; kk < nk; kk++) {
-              const uint64_t da = umma_desc(aBase + kk * 2 * (K2_TM * 16), K2_TM * 16, 128);
-              const uint64_t db = umma_desc(bBase + kk * 2 * (K2_TN * 16), K2_TN * 16, 128);
-              umma_f16(d_tmem, da, db, idesc, kk ? 1u : 0u);
+            if (leader) {
+              const uint64_t da = da0 + (uint64_t)r * a_tile_step;
+              const uint64_t db = dbs + (uint64_t)(h * ((K2R_TNH * 16) >> 4));     // codes 128h.. of every K chunk
+              const uint32_t d_tmem = tmem_base + r * K2R_TNH;
+#pragma unroll
+              for (int kk = 0; kk < NK; kk++)
+                umma_f16(d_tmem, da + (uint64_t)(kk * ((2 * K2_TM * 16) >> 4)),
+                         db + (uint64_t)(kk * ((2 * K2_TN * 16) >> 4)), idesc, kk ? 1u : 0u);
+              umma_commit(&tfull[r]);
             }
-            umma_commit(&tfull[buf]);
+            __syncwarp();
           }
-          umma_commit(&empty[s]);                   // code tile slot reusable once all R products retire
         }
-        umma_commit(aempty);
+        if (leader) umma_commit(&empty[s]);               // code tile slot reusable once all products retire
+        __syncwarp();
       }
+      if (leader) umma_commit(aempty);
+      __syncwarp();
     }
   } else {
-    // ===================== epilogue: group g = warp / 4 owns accumulator g and row tiles g, g+2 =====
-    // One code instance serves both rows of a thread: the per-row state is selected at the
-    // start of every accumulation (keeps the loop body inside the instruction cache).
-    static_assert(R == 4, "two rows per epilogue thread");
+    // ===================== epilogue: group g = warp / 4 owns row tile g and accumulator g =====
     const int g = warp >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + g * K2_TN;
+    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + g * K2R_TNH;
     unsigned use = 0;
     for (long st = blockIdx.x; st < nsuper; st += gridDim.x) {
-      const long n0 = (st * R + g) * K2_TM + row, n1 = n0 + 2 * K2_TM;
-      const float delta0 = n0 < N ? rs[n0].delta : 0.0f, delta1 = n1 < N ? rs[n1].delta : 0.0f;
-      K2RRow r0 = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1}, r1 = r0;
-      for (int q = 0; q < 2 * (nct + nwarm); q++) {
-        const int j = q & 1, qt = q >> 1;
-        const bool warm = qt < nwarm;
-        const int ct = warm ? qt : qt - nwarm;
-        K2RRow r = j ? r1 : r0;
-        const float delta = j ? delta1 : delta0;
+      const long n = (st * R + g) * K2_TM + row;
+      const float delta = n < N ? rs[n].delta : 0.0f;
+      K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
+      for (int q = 0; q < 2 * nct; q++, use++) {            // q = 2 * code tile + half
         mbar_wait(&tfull[g], use & 1);
-        use++;
         tc_fence_after();
-        uint32_t va[32], vb[32];
-        tmem_ld32_nowait(tbase, va);
+        uint32_t v[32];
+        tmem_ld32_nowait(tbase, v);
 #pragma unroll 1
-        for (int c0 = 0; c0 < K2_TN; c0 += 64) {
-          tmem_ld_wait32(va);
-          tmem_ld32_nowait(tbase + c0 + 32, vb);
-          k2r_chunk<DBG>(va, ct * K2_TN + c0, delta, warm, r);
-          tmem_ld_wait32(vb);
-          if (c0 + 64 < K2_TN) tmem_ld32_nowait(tbase + c0 + 64, va);
-          k2r_chunk<DBG>(vb, ct * K2_TN + c0 + 32, delta, warm, r);
+        for (int c0 = 0; c0 < K2R_TNH; c0 += 32) {
+          tmem_ld_wait32(v);
+          // minima of the four 8-column groups (3-input FMNMX3), then of the chunk
+          float gm[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const float a0 = fminf(fminf(__uint_as_float(v[8 * t]), __uint_as_float(v[8 * t + 1])), __uint_as_float(v[8 * t + 2]));
+            const float a1 = fminf(fminf(__uint_as_float(v[8 * t + 3]), __uint_as_float(v[8 * t + 4])), __uint_as_float(v[8 * t + 5]));
+            gm[t] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * t + 6]), __uint_as_float(v[8 * t + 7])));
+          }
+          // the scores are dead now: the next chunk streams into the same registers
+          if (c0 + 32 < K2R_TNH) tmem_ld32_nowait(tbase + c0 + 32, v);
+          const float m = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+          const bool ins = m < r.thr;
+          if (__any_sync(0xffffffffu, ins)) {
+            // ---- slow path: warp-uniform entry, straight-line predicated code
+            // group holding the minimum, and the smallest minimum of the other three
+            const int qs = gm[0] == m ? 0 : (gm[1] == m ? 1 : (gm[2] == m ? 2 : 3));
+            const float o0 = qs == 0 ? INFINITY : gm[0], o1 = qs == 1 ? INFINITY : gm[1];
+            const float o2 = qs == 2 ? INFINITY : gm[2], o3 = qs == 3 ? INFINITY : gm[3];
+            const float s2 = fminf(fminf(o0, o1), fminf(o2, o3));
+            const int gi = q * K2R_TNH + c0 + 8 * qs;          // first code of that group
+            const bool first = ins && m < r.k0, second = ins && !first && m < r.k1;
+            // the minimum that leaves the pair (or m itself when it does not enter) bounds what is dropped
+            r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? m : INFINITY));
+            r.k1 = first ? r.k0 : (second ? m : r.k1);
+            r.i1 = first ? r.i0 : (second ? gi : r.i1);
+            r.k0 = first ? m : r.k0;
+            r.i0 = first ? gi : r.i0;
+            r.best = ins ? fminf(r.best, m) : r.best;
+            r.thr = ins ? __fadd_ru(r.best, delta) : r.thr;
+            // only one group of this chunk is recorded; the others are >= s2
+            r.lost = (ins && s2 < r.thr) ? fminf(r.lost, s2) : r.lost;
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[g]);
-        if (warm && qt == nwarm - 1) r.thr = __fadd_ru(r.best, delta);     // threshold from the warm-up tiles
-        if (j) r1 = r; else r0 = r;
       }
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const long n = j ? n1 : n0;
-        if (n < N) {
-          const K2RRow r = j ? r1 : r0;
-          const float bound = r.thr;                      // final best + delta (rounded up)
-          const int c0 = (r.k0 < bound && r.i0 < M) ? r.i0 : -1, c1 = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
-          *reinterpret_cast<int4 *>(cand + n * K2R_TG) = make_int4(c0, c1, -1, -1);
-          // never looked at: >= best + delta; looked at and dropped: >= lost
-          thr[n] = fminf(bound, r.lost);
-        }
+      if (n < N) {
+        const float bound = r.thr;                      // final best + delta (rounded up)
+        cand[n * K2R_NG] = (r.k0 < bound && r.i0 < M) ? r.i0 : -1;
+        cand[n * K2R_NG + 1] = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
+        // groups never recorded: minimum >= best + delta; recorded and dropped: >= lost
+        thr[n] = fminf(bound, r.lost);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  if (warp == 17) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 // ---------------------------------------------------------------- exact re-rank + certificate
@@ -906,6 +899,88 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
   nfound[n] = k;
 }
 
+// ---------------------------------------------------------------- group re-rank (record kernel, k == 1)
+// 16 lanes per row: lane l computes the exact distance to code l % 8 of candidate group l / 8;
+// the 16 lanes take the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and the
+// leader evaluates the certificate against thr (lower bound of every code outside the groups).
+__global__ void __launch_bounds__(256)
+k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ grp, long N, long M,
+                       int D, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
+                       const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
+                       const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
+                       int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
+  constexpr int LPR = K2R_NG * K2R_GW;                  // 16 lanes per row
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const long warp_id = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long n = warp_id * (32 / LPR) + lane / LPR;
+  const bool row_ok = n < N && flags[n] == 0;           // other rows are answered by K1
+  u64 key = ~0ull;
+  if (row_ok) {
+    const int g0 = cand[n * K2R_NG + sub / K2R_GW];          // first code of the group (multiple of 8)
+    const int l = sub % K2R_GW;
+    const long j = (long)g0 + l;
+    if (g0 >= 0 && j < M) {
+      const float *x = data + n * (long)D;
+      const int Dq = (D + 3) / 4;
+      const float4 *c4 = reinterpret_cast<const float4 *>(grp) + ((long)(g0 >> 3) * Dq) * 8 + l;
+      float acc = 0.0f;
+      if ((D & 3) == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+#pragma unroll 4
+        for (int i = 0; i < Dq; i++) {
+          const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i * 8);
+          acc = sq_acc(acc, cv.x, xv.x);               // the reference's sum, component order
+          acc = sq_acc(acc, cv.y, xv.y);
+          acc = sq_acc(acc, cv.z, xv.z);
+          acc = sq_acc(acc, cv.w, xv.w);
+        }
+      } else {
+        for (int i = 0; i < Dq; i++) {
+          const float4 cv = __ldg(c4 + i * 8);
+          const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (4 * i + e < D) acc = sq_acc(acc, cc[e], __ldg(x + 4 * i + e));
+        }
+      }
+      // only d < FLT_MAX can win; non-negative floats order like their bit patterns
+      if (acc < FLT_MAX) key = ((u64)__float_as_uint(acc) << 32) | (unsigned)j;
+    }
+  }
+#pragma unroll
+  for (int off = LPR / 2; off >= 1; off >>= 1) {
+    const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
+    key = o < key ? o : key;
+  }
+  if (!row_ok || sub != 0) return;
+  bool ok = false;
+  const float dbest = __uint_as_float((unsigned)(key >> 32));
+  if (key != ~0ull) {
+    // in scaled units every code outside the candidate groups has ||s x' - s m'||^2 >= nx2 + thr - E
+    const RowStats s = rs[n];
+    const CbStats cs = *cst;
+    const double Lc = s.nx2 + (double)thr[n] - (double)s.E;
+    const double eta = ldexp((double)s.nx + (double)cs.nm, -23);
+    if (Lc > 0.0) {
+      const double r = sqrt(Lc) - eta;
+      if (r > 0.0) {
+        const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;
+        const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6) * (double)cs.inv_s2;
+        ok = (double)dbest < L;
+      }
+    }
+  }
+  if (!ok) {
+    listW[atomicAdd(&counters[0], 1)] = (int)n;
+    atomicAdd(&counters[3], 1);
+    return;
+  }
+  atomicAdd(&counters[2], 1);
+  idx[n] = (int)(unsigned)key;
+  diff[n] = dbest;
+  nfound[n] = 1;
+}
+
 // ---------------------------------------------------------------- host side
 struct K2Scratch {      // carved out of one grow-only device buffer
   __half *Aimg;
@@ -930,8 +1005,11 @@ void k2_codebook_invalidate(K2Codebook *c) { c->valid = 0; }
 void k2_codebook_free(K2Codebook *c) {
   if (c->d_ops) cudaFree(c->d_ops);
   if (c->d_norm) cudaFree(c->d_norm);
+  if (c->d_grp) cudaFree(c->d_grp);
   c->d_ops = nullptr;
   c->d_norm = nullptr;
+  c->d_grp = nullptr;
+  c->ops_bytes = c->grp_bytes = 0;
   c->valid = 0;
 }
 
@@ -958,7 +1036,15 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
   const long warps = nct * K2_TN;
   k2_cb_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
       a.codes, a.M, a.D, mean, (__half *)c->d_ops, cst);
-  k1_count_launch(3);
+  const size_t gneed = (size_t)((a.M + 7) / 8) * ((a.D + 3) / 4) * 32 * sizeof(float);
+  if (gneed > c->grp_bytes) {
+    if (c->d_grp) cudaFree(c->d_grp);
+    c->d_grp = nullptr;
+    if ((e = cudaMalloc((void **)&c->d_grp, gneed)) != cudaSuccess) return e;
+    c->grp_bytes = gneed;
+  }
+  k2_cb_regroup_kernel<<<1024, 256, 0, st>>>(a.codes, a.M, a.D, c->d_grp);
+  k1_count_launch(4);
   c->Kp = Kp;
   c->valid = 1;
   return cudaGetLastError();
@@ -999,22 +1085,39 @@ static size_t k2r_smem_bytes(int Kp) {
   return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)K2R_BST * K2_TN * Kp * 2 + 256;
 }
 
-static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+template <int NK>
+static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   const int Kp = c->Kp;
   const size_t smem = k2r_smem_bytes(Kp);
-  static int dbg = getenv("BMU_K2_DEBUG") ? atoi(getenv("BMU_K2_DEBUG")) : 0;
-  auto kern = dbg == 1 ? k2_rec_kernel<K2R_R, 1> : dbg == 2 ? k2_rec_kernel<K2R_R, 2> : dbg == 3 ? k2_rec_kernel<K2R_R, 3> : dbg == 4 ? k2_rec_kernel<K2R_R, 4> : k2_rec_kernel<K2R_R, 0>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k2_rec_kernel<K2R_R, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long ntiles = (a.N + K2_TM - 1) / K2_TM;
   const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
   const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
-  kern<<<grid, K2R_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
-                                                       s.cand, s.thr);
+  k2_rec_kernel<K2R_R, NK><<<grid, K2R_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
+                                                           s.cand, s.thr);
+  return cudaGetLastError();
+}
+
+static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+  cudaError_t e;
+  switch (c->Kp / 16) {                                 // K2R_MAX_KP / 16 = 6 unrolled issue loops
+    case 1: e = k2_launch_record<1>(c, a, s, st); break;
+    case 2: e = k2_launch_record<2>(c, a, s, st); break;
+    case 3: e = k2_launch_record<3>(c, a, s, st); break;
+    case 4: e = k2_launch_record<4>(c, a, s, st); break;
+    case 5: e = k2_launch_record<5>(c, a, s, st); break;
+    default: e = k2_launch_record<6>(c, a, s, st); break;
+  }
   k1_count_launch(1);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
-  return k2_run_rerank<K2R_TG>(c, a, s, st);
+  const long rr_warps = (a.N + 1) / 2;                  // two rows per warp
+  k2_rerank_group_kernel<<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
+      a.data, c->d_grp, a.N, a.M, a.D, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr, a.listW,
+      a.counters, a.idx, a.diff, a.nfound);
+  k1_count_launch(1);
+  return cudaGetLastError();
 }
 
 cudaError_t k2_last_kernel_ms(float out[4]) {
@@ -1061,7 +1164,7 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
 
   if ((e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[0], st);
-  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, record ? K2R_PACK : 8,
+  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, record ? 0 : 8,
                                                       c->d_norm + 16, (const CbStats *)c->d_norm, s.Aimg,
                                                       s.rs, a.flags, a.listW, a.listS, a.counters, a.idx,
                                                       a.diff, a.nfound);
