@@ -38,6 +38,10 @@ WORKLOADS = {
 
 MASK64 = (1 << 64) - 1
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
+# committed ncu --set full capture of exactly this shape (profiles/): (kernel, rows, D, M) -> bytes
+NCU_TRAFFIC = {}
+
 
 # ------------------------------------------------------------------ synthetic data
 def _s64(v):
@@ -321,19 +325,25 @@ def main_gpu(args, w):
         step_ms = {n: v for n, v in zip(names, kernel_ms) if (n.startswith("k2") == used_k2)}
         hbm_bytes = rows * (4.0 * D + 12.0 * k)
         if used_k2:
-            k_ms, kname = kernel_ms[5], "k2_gemm_kernel"
+            kp = ((D + 7) // 8 * 8 + 3 + 15) // 16 * 16                   # fp16 operand K: D + 3 norm columns
+            k_ms = kernel_ms[5]
+            kname = "k2_rec_kernel" if (k == 1 and kp <= 96) else "k2_gemm_kernel"
             flop = 2.0 * M * D * rows                                      # 2*M*D per search
             achieved = flop / (k_ms * 1e-3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            kp = (3 * ((D + 7) // 8 * 8) + 3 + 15) // 16 * 16
+            m_pad = (M + 255) // 256 * 256
+            issued = achieved * (kp / D) * (m_pad / M)
             roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "step_kernels_ms": step_ms,
-                    "note": "algorithmic 2*M*D flop per search vs the measured sustained bf16 peak (%s); the "
-                            "kernel issues %.2fx that many MMA flops (3-term bf16 split + norm columns, K %d -> %d), "
-                            "so the tensor pipe itself runs at %.3f of peak"
-                            % ("measured" if "bf16_tflops_sustained" in peaks else "fallback", kp / D, D, kp,
-                               achieved * kp / D / peak),
-                    "mma_issued_tflops": achieved * kp / D,
+                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((kname, rows, D, M)),
+                    "kernel_ms": k_ms, "step_kernels_ms": step_ms,
+                    "note": "algorithmic 2*M*D flop per search over the live CUDA-event duration of %s vs the "
+                            "sustained fp16/bf16 cuBLAS peak (%s); the kernel issues %.2fx that many MMA flops "
+                            "(K %d -> %d: 3 norm columns + padding to 16; M %d -> %d), so the tensor pipe itself "
+                            "runs at %.3f of that peak.  traffic = ncu dram bytes of one launch (profiles/), "
+                            "null when no capture exists for this shape"
+                            % (kname, "measured" if "bf16_tflops_sustained" in peaks else "fallback",
+                               (kp / D) * (m_pad / M), D, kp, M, m_pad, issued / peak),
+                    "mma_issued_tflops": issued,
                     "rows_certified": bd["k2_certified"], "rows_redone_exactly": bd["k2_failed"]}
             search_path = "filter (K2 tcgen05 GEMM + exact re-rank, K1 for uncertified rows)"
         else:

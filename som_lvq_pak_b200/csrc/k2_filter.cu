@@ -49,7 +49,7 @@ constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel
 constexpr int K2R_BST = 3;        // staged code tiles
 constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM)
 constexpr int K2R_THREADS = 576;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA
-constexpr int K2R_GW = 8;         // candidate granularity: groups of 8 consecutive codes
+constexpr int K2R_GW = 4;         // candidate granularity: groups of 4 consecutive codes
 constexpr int K2R_NG = 2;         // candidate groups kept per row
 constexpr int K2R_MAX_KP = 96;    // code tile (256 x Kp fp16) <= 48 KB
 
@@ -160,17 +160,17 @@ k2_cb_prep_kernel(const float *__restrict__ codes, long M, int D, const float *_
   }
 }
 
-// FP32 codebook regrouped for k2_rerank_group_kernel: [group of 8 codes][4-component chunk]
-// [code in group][4 comps], so that the 8 lanes of a group read 128 contiguous bytes per float4
+// FP32 codebook regrouped for k2_rerank_group_kernel: [group of K2R_GW codes][4-component chunk]
+// [code in group][4 comps], so that the lanes of a group read contiguous bytes per float4
 __global__ void k2_cb_regroup_kernel(const float *__restrict__ codes, long M, int D, float *__restrict__ grp) {
   const int Dq = (D + 3) / 4;
-  const long total = ((M + 7) / 8) * (long)Dq * 32;
+  const long total = ((M + K2R_GW - 1) / K2R_GW) * (long)Dq * K2R_GW * 4;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int e = (int)(t & 3), l = (int)((t >> 2) & 7);
-    const long rest = t >> 5;
+    const int e = (int)(t & 3), l = (int)((t >> 2) % K2R_GW);
+    const long rest = t / (4 * K2R_GW);
     const int c4 = (int)(rest % Dq);
     const long gidx = rest / Dq;
-    const long j = gidx * 8 + l;
+    const long j = gidx * K2R_GW + l;
     const int i = c4 * 4 + e;
     grp[t] = (j < M && i < D) ? codes[j * D + i] : 0.0f;
   }
@@ -749,26 +749,26 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 #pragma unroll 1
         for (int c0 = 0; c0 < K2R_TNH; c0 += 32) {
           tmem_ld_wait32(v);
-          // minima of the four 8-column groups (3-input FMNMX3), then of the chunk
-          float gm[4];
+          // minima of the eight 4-column groups (FMNMX3 + FMNMX), then of the chunk: 20 ALU ops
+          float gm[8];
 #pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const float a0 = fminf(fminf(__uint_as_float(v[8 * t]), __uint_as_float(v[8 * t + 1])), __uint_as_float(v[8 * t + 2]));
-            const float a1 = fminf(fminf(__uint_as_float(v[8 * t + 3]), __uint_as_float(v[8 * t + 4])), __uint_as_float(v[8 * t + 5]));
-            gm[t] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * t + 6]), __uint_as_float(v[8 * t + 7])));
-          }
+          for (int t = 0; t < 8; t++)
+            gm[t] = fminf(fminf(fminf(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), __uint_as_float(v[4 * t + 2])),
+                          __uint_as_float(v[4 * t + 3]));
           // the scores are dead now: the next chunk streams into the same registers
           if (c0 + 32 < K2R_TNH) tmem_ld32_nowait(tbase + c0 + 32, v);
-          const float m = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+          const float m = fminf(fminf(fminf(fminf(gm[0], gm[1]), gm[2]), fminf(fminf(gm[3], gm[4]), gm[5])), fminf(gm[6], gm[7]));
           const bool ins = m < r.thr;
           if (__any_sync(0xffffffffu, ins)) {
             // ---- slow path: warp-uniform entry, straight-line predicated code
-            // group holding the minimum, and the smallest minimum of the other three
-            const int qs = gm[0] == m ? 0 : (gm[1] == m ? 1 : (gm[2] == m ? 2 : 3));
-            const float o0 = qs == 0 ? INFINITY : gm[0], o1 = qs == 1 ? INFINITY : gm[1];
-            const float o2 = qs == 2 ? INFINITY : gm[2], o3 = qs == 3 ? INFINITY : gm[3];
-            const float s2 = fminf(fminf(o0, o1), fminf(o2, o3));
-            const int gi = q * K2R_TNH + c0 + 8 * qs;          // first code of that group
+            // group holding the minimum, and the smallest minimum of the other seven
+            int qs = 7;
+            float s2 = INFINITY;
+#pragma unroll
+            for (int t = 6; t >= 0; t--) qs = gm[t] == m ? t : qs;
+#pragma unroll
+            for (int t = 0; t < 8; t++) s2 = fminf(s2, qs == t ? INFINITY : gm[t]);
+            const int gi = q * K2R_TNH + c0 + K2R_GW * qs;     // first code of that group
             const bool first = ins && m < r.k0, second = ins && !first && m < r.k1;
             // the minimum that leaves the pair (or m itself when it does not enter) bounds what is dropped
             r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? m : INFINITY));
@@ -900,8 +900,8 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
 }
 
 // ---------------------------------------------------------------- group re-rank (record kernel, k == 1)
-// 16 lanes per row: lane l computes the exact distance to code l % 8 of candidate group l / 8;
-// the 16 lanes take the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and the
+// K2R_NG * K2R_GW lanes per row: lane l computes the exact distance to code l % GW of candidate
+// group l / GW; those lanes take the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and the
 // leader evaluates the certificate against thr (lower bound of every code outside the groups).
 __global__ void __launch_bounds__(256)
 k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ grp, long N, long M,
@@ -909,26 +909,26 @@ k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__
                        const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
                        const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
                        int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  constexpr int LPR = K2R_NG * K2R_GW;                  // 16 lanes per row
+  constexpr int LPR = K2R_NG * K2R_GW;                  // lanes per row
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const long warp_id = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const long n = warp_id * (32 / LPR) + lane / LPR;
   const bool row_ok = n < N && flags[n] == 0;           // other rows are answered by K1
   u64 key = ~0ull;
   if (row_ok) {
-    const int g0 = cand[n * K2R_NG + sub / K2R_GW];          // first code of the group (multiple of 8)
+    const int g0 = cand[n * K2R_NG + sub / K2R_GW];          // first code of the group (multiple of GW)
     const int l = sub % K2R_GW;
     const long j = (long)g0 + l;
     if (g0 >= 0 && j < M) {
       const float *x = data + n * (long)D;
       const int Dq = (D + 3) / 4;
-      const float4 *c4 = reinterpret_cast<const float4 *>(grp) + ((long)(g0 >> 3) * Dq) * 8 + l;
+      const float4 *c4 = reinterpret_cast<const float4 *>(grp) + ((long)(g0 / K2R_GW) * Dq) * K2R_GW + l;
       float acc = 0.0f;
       if ((D & 3) == 0) {
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
 #pragma unroll 4
         for (int i = 0; i < Dq; i++) {
-          const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i * 8);
+          const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i * K2R_GW);
           acc = sq_acc(acc, cv.x, xv.x);               // the reference's sum, component order
           acc = sq_acc(acc, cv.y, xv.y);
           acc = sq_acc(acc, cv.z, xv.z);
@@ -936,7 +936,7 @@ k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__
         }
       } else {
         for (int i = 0; i < Dq; i++) {
-          const float4 cv = __ldg(c4 + i * 8);
+          const float4 cv = __ldg(c4 + i * K2R_GW);
           const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
           for (int e = 0; e < 4; e++)
@@ -1036,7 +1036,7 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
   const long warps = nct * K2_TN;
   k2_cb_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
       a.codes, a.M, a.D, mean, (__half *)c->d_ops, cst);
-  const size_t gneed = (size_t)((a.M + 7) / 8) * ((a.D + 3) / 4) * 32 * sizeof(float);
+  const size_t gneed = (size_t)((a.M + K2R_GW - 1) / K2R_GW) * ((a.D + 3) / 4) * K2R_GW * 4 * sizeof(float);
   if (gneed > c->grp_bytes) {
     if (c->d_grp) cudaFree(c->d_grp);
     c->d_grp = nullptr;
@@ -1112,7 +1112,8 @@ static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch
   k1_count_launch(1);
   if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
-  const long rr_warps = (a.N + 1) / 2;                  // two rows per warp
+  constexpr int RPW = 32 / (K2R_NG * K2R_GW);           // rows per warp of the group re-rank
+  const long rr_warps = (a.N + RPW - 1) / RPW;
   k2_rerank_group_kernel<<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
       a.data, c->d_grp, a.N, a.M, a.D, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr, a.listW,
       a.counters, a.idx, a.diff, a.nfound);

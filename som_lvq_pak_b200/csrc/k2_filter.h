@@ -9,7 +9,7 @@ namespace bmu {
 struct K2Codebook {
   void *d_ops = nullptr;        // fp16 operand image of the codebook, UMMA tile layout
   float *d_norm = nullptr;      // codebook statistics (scale, maxima) and the mean vector
-  float *d_grp = nullptr;       // FP32 codebook regrouped [M/8][D/4][8 codes][4 comps] for the group re-rank
+  float *d_grp = nullptr;       // FP32 codebook regrouped [M/GW][D/4][GW codes][4 comps] for the group re-rank
   size_t grp_bytes = 0;
   size_t ops_bytes = 0;
   int valid = 0;
