@@ -41,4 +41,5 @@ struct bmu_codebook {
   unsigned *d_flags;   // ROW_* bits of the codebook
   unsigned h_flags;
   bmu::K2Codebook k2;  // operands of the tcgen05 filter (built lazily)
+  float *d_cq;         // component-major copy for K4 (qerror2), built lazily; nullptr = stale
 };

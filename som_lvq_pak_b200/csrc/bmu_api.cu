@@ -13,6 +13,7 @@
 #include "k1_search.h"
 #include "k2_filter.h"
 #include "k3_train.h"
+#include "k4_qerror2.h"
 #include "api_internal.h"
 
 using namespace bmu;
@@ -72,6 +73,7 @@ struct SearchScratch {
 };
 SearchScratch g_ss[2];          // two sets so that chunked host searches can overlap
 Scratch g_stage_in[2], g_stage_mask[2], g_stage_idx[2], g_stage_diff[2], g_stage_nf[2];
+Scratch g_q2_out;                // per-sample values of bmu_qerror2
 
 }  // namespace
 
@@ -112,6 +114,7 @@ void bmu_shutdown(void) {
     g_stage_in[i].release(); g_stage_mask[i].release(); g_stage_idx[i].release();
     g_stage_diff[i].release(); g_stage_nf[i].release();
   }
+  g_q2_out.release();
   if (g_compute) cudaStreamDestroy(g_compute);
   if (g_copy) cudaStreamDestroy(g_copy);
   if (g_out) cudaStreamDestroy(g_out);
@@ -214,6 +217,7 @@ int bmu_codebook_update(bmu_codebook *cb, const float *codes) {
   CK(cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute));
   CK(cudaStreamSynchronize(g_compute));
   k2_codebook_invalidate(&cb->k2);
+  if (cb->d_cq) { cudaFree(cb->d_cq); cb->d_cq = nullptr; }
   return BMU_OK;
 }
 
@@ -222,6 +226,7 @@ void bmu_codebook_destroy(bmu_codebook *cb) {
   if (cb->d_codes) cudaFree(cb->d_codes);
   if (cb->d_cT) cudaFree(cb->d_cT);
   if (cb->d_flags) cudaFree(cb->d_flags);
+  if (cb->d_cq) cudaFree(cb->d_cq);
   k2_codebook_free(&cb->k2);
   free(cb);
 }
@@ -338,6 +343,56 @@ int bmu_search(bmu_codebook *cb, const float *data, const unsigned char *mask, l
   if (status) return status;
   if (e1 != cudaSuccess) return fail(BMU_ERR_CUDA, "search failed: %s", cudaGetErrorString(e1));
   if (e2 != cudaSuccess) return fail(BMU_ERR_CUDA, "search copy failed: %s", cudaGetErrorString(e2));
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ qerror -qetype 1
+// find_qerror2 (som_rout.c:823-891): winner search (k = 1) followed by the neighbourhood-weighted
+// pass K4 over the same resident chunk; the host adds out[] in data order (one float, som_rout.c:872).
+int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, float radius,
+                const float *data, const unsigned char *mask, long N, float *out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!cb || !data || !out) return fail(BMU_ERR_ARG, "NULL argument");
+  if (xdim < 1 || ydim < 1 || (long)xdim * ydim != cb->M)
+    return fail(BMU_ERR_ARG, "map %d x %d does not match the codebook (%ld units)", xdim, ydim, cb->M);
+  if (topol != BMU_TOPOL_HEXA && topol != BMU_TOPOL_RECT) return fail(BMU_ERR_ARG, "bad topology %d", topol);
+  if (neigh != BMU_NEIGH_BUBBLE && neigh != BMU_NEIGH_GAUSSIAN) return fail(BMU_ERR_ARG, "bad neighbourhood %d", neigh);
+  if (N <= 0) return N == 0 ? BMU_OK : fail(BMU_ERR_ARG, "bad N");
+  const int D = cb->D;
+  if (!cb->d_cq) {
+    if (cudaMalloc((void **)&cb->d_cq, (size_t)k4_mp(cb->M) * D * sizeof(float)) != cudaSuccess) {
+      cb->d_cq = nullptr;
+      return fail(BMU_ERR_NOMEM, "cudaMalloc of the component-major codebook failed");
+    }
+    CK(k4_transpose_codebook(cb->d_codes, cb->M, D, cb->d_cq, g_compute));
+    k1_count_launch(1);
+  }
+  long chunk = (256L << 20) / ((long)D * 4);
+  if (chunk < 1) chunk = 1;
+  if (chunk > N) chunk = N;
+  if ((rc = g_stage_in[0].ensure((size_t)chunk * D * 4))) return rc;
+  if (mask && (rc = g_stage_mask[0].ensure((size_t)chunk * D))) return rc;
+  if ((rc = g_stage_idx[0].ensure((size_t)chunk * 4))) return rc;
+  if ((rc = g_stage_diff[0].ensure((size_t)chunk * 4))) return rc;
+  if ((rc = g_stage_nf[0].ensure((size_t)chunk * 4))) return rc;
+  if ((rc = g_q2_out.ensure((size_t)chunk * 4))) return rc;
+  for (long n0 = 0; n0 < N; n0 += chunk) {
+    const long n = (N - n0 < chunk) ? N - n0 : chunk;
+    CK(cudaMemcpyAsync(g_stage_in[0].p, data + n0 * (long)D, (size_t)n * D * 4, cudaMemcpyHostToDevice, g_compute));
+    if (mask)
+      CK(cudaMemcpyAsync(g_stage_mask[0].p, mask + n0 * (long)D, (size_t)n * D, cudaMemcpyHostToDevice, g_compute));
+    const unsigned char *d_mask = mask ? (const unsigned char *)g_stage_mask[0].p : nullptr;
+    if ((rc = search_dev_impl(cb, (const float *)g_stage_in[0].p, d_mask, n, 1, (int32_t *)g_stage_idx[0].p,
+                              (float *)g_stage_diff[0].p, (int32_t *)g_stage_nf[0].p, g_compute, g_ss[0])))
+      return rc;
+    CK(k4_qerror2(cb->d_cq, cb->M, D, xdim, topol, neigh, radius, (const float *)g_stage_in[0].p, d_mask, n,
+                  (const int32_t *)g_stage_idx[0].p, (const int32_t *)g_stage_nf[0].p, (float *)g_q2_out.p,
+                  g_sms, g_compute));
+    k1_count_launch(1);
+    CK(cudaMemcpyAsync(out + n0, g_q2_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_compute));
+    CK(cudaStreamSynchronize(g_compute));
+  }
   return BMU_OK;
 }
 

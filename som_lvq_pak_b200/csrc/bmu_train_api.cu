@@ -1,5 +1,5 @@
 // bmu_train_api.cu -- C ABI for online training (bmu_trainer_*, bmu_som_train,
-// bmu_lvq_train) on top of the persistent kernel K3, and bmu_qerror2.
+// bmu_lvq_train) on top of the persistent kernel K3.
 #include <stdlib.h>
 #include <string.h>
 
@@ -226,11 +226,6 @@ int bmu_lvq_train(int algo, float *codes, const int32_t *code_label, long M, int
   if (!rc && algo == BMU_OLVQ1) rc = bmu_trainer_get_unit_alpha(t, unit_alpha);
   bmu_trainer_destroy(t);
   return rc;
-}
-
-int bmu_qerror2(bmu_codebook *, int, int, int, int, float, const float *, const unsigned char *,
-                long, float *) {
-  return fail(BMU_ERR_ARG, "bmu_qerror2 is not implemented yet");
 }
 
 }  // extern "C"

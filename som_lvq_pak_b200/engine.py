@@ -129,6 +129,35 @@ def find_winner_knn(codes, data, knn, mask=None):
         cb.close()
 
 
+def find_qerror(codes, data, mask=None):
+    """find_qerror (som_rout.c:678-731): sum over the samples of sqrt(diff), accumulated in one
+    float in data order (bmu_replay_qerror); samples without a winner are skipped."""
+    idx, diff, nf = find_winner_knn(codes, data, 1, mask)
+    lib = _lib.load()
+    lib.bmu_replay_qerror.restype = C.c_float
+    return np.float32(lib.bmu_replay_qerror(_ptr(diff), _ptr(nf), C.c_long(diff.shape[0]), 1))
+
+
+def find_qerror2(codes, data, xdim, ydim, topol, neigh, radius, mask=None):
+    """find_qerror2 (som_rout.c:823-891, `qerror -qetype 1`): neighbourhood-weighted error around
+    each sample's winner.  The per-sample values come from the GPU (bmu_qerror2); they are added
+    here in data order in one float, as som_rout.c:872 does."""
+    codes, data = _f32(codes), _f32(data)
+    mask = _opt(mask, np.uint8)
+    N = data.shape[0]
+    out = np.empty(N, np.float32)
+    cb = Codebook(codes)
+    try:
+        _lib.check(_lib.load().bmu_qerror2(cb._h, xdim, ydim, topol, neigh, C.c_float(radius), _ptr(data),
+                                           _ptr(mask), N, _ptr(out)))
+    finally:
+        cb.close()
+    q = np.float32(0.0)
+    if N:
+        q = np.cumsum(out, dtype=np.float32)[-1]      # cumsum is strictly sequential: float q += e
+    return np.float32(q), out
+
+
 # ---------------------------------------------------------------------------- host helpers
 def rand_order(n, seed):
     """list order after `-rand seed` (datafile.c:1152-1188 driven by lvq_pak.c:459-473)"""
