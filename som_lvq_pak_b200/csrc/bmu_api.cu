@@ -254,6 +254,7 @@ static int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned
   a.cb_flags = cb->d_flags; a.N = N; a.M = cb->M; a.D = D; a.k = k;
   a.skip_fast = need_tiles ? 0 : 1;
   a.num_sms = g_sms;
+  a.short_list = use_k2 ? 1 : 0;
   a.xT = (float *)ss.xT.p; a.flags = (unsigned char *)ss.flags.p;
   a.listW = (int *)ss.listW.p; a.listS = (int *)ss.listS.p; a.counters = (int *)ss.counters.p;
   a.idx = d_idx; a.diff = d_diff; a.nfound = d_nfound;

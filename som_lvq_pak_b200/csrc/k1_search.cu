@@ -294,12 +294,13 @@ k1_fast_kernel(const float *__restrict__ xT, const float *__restrict__ cT, long 
 __global__ void __launch_bounds__(256)
 k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__ mask,
                const float *__restrict__ cT, long M, int D, int k, const int *__restrict__ list,
-               const int *__restrict__ count, int32_t *__restrict__ idx,
+               const int *__restrict__ count, int max_cnt, int32_t *__restrict__ idx,
                float *__restrict__ diff, int32_t *__restrict__ nfound) {
   __shared__ float sl_d[8][BMU_KMAX_];
   __shared__ int sl_i[8][BMU_KMAX_];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cnt = *count;
+  if (cnt >= max_cnt) return;                            // long list: k1_warp8_kernel answers it
   const int nct = (int)((M + K1_TC - 1) / K1_TC);
   const bool knn_rule = k > 1;
   // short lists (K2 certificate failures, a few masked rows): S warps of a CTA share one row
@@ -409,6 +410,99 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
         }
       }
       nfound[n] = k;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- K1-warp8 (k == 1, no masks)
+// Short lists -- the K2 certificate failures -- are bound by L2 bandwidth when every row streams
+// the whole codebook by itself.  Here a warp takes EIGHT listed rows against each 128-code tile
+// (8 rows x 4 codes per lane in registers), which divides the codebook traffic by eight.
+__global__ void __launch_bounds__(256)
+k1_warp8_kernel(const float *__restrict__ data, const float *__restrict__ cT, long M, int D,
+                const int *__restrict__ list, const int *__restrict__ count, int min_cnt,
+                int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
+  __shared__ u64 skey[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = *count;
+  if (cnt < min_cnt) return;                             // very short list: one row per warp is faster
+  const long groups = (cnt + 7) / 8;
+  const int nct = (int)((M + K1_TC - 1) / K1_TC);
+  int S = 1;                                             // warps of a CTA sharing one group of rows
+  const long total_warps = (long)gridDim.x * 8;
+  while (S < 8 && S * 2 <= nct && groups * S * 2 <= total_warps) S *= 2;
+  const int groups_per_cta = 8 / S;
+  const int gloc = warp / S, sub = warp % S;
+  for (long base = (long)blockIdx.x * groups_per_cta; base < groups; base += (long)gridDim.x * groups_per_cta) {
+    const long gidx = base + gloc;
+    const bool valid = gidx < groups;
+    const float *xp[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      long w = gidx * 8 + r;
+      if (!valid || w >= cnt) w = valid ? gidx * 8 : 0;     // harmless duplicate, never written
+      xp[r] = data + (long)list[cnt > 0 ? w : 0] * D;
+    }
+    u64 best[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) best[r] = ~0ull;
+    if (valid)
+      for (int ct = sub; ct < nct; ct += S) {
+        const float *cbase = cT + (long)ct * D * K1_TC + lane;
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+        for (int i = 0; i < D; i++) {
+          const float *cr = cbase + (long)i * K1_TC;
+          const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const float xi = __ldg(xp[r] + i);
+            acc[r][0] = sq_acc(acc[r][0], c0, xi);
+            acc[r][1] = sq_acc(acc[r][1], c1, xi);
+            acc[r][2] = sq_acc(acc[r][2], c2, xi);
+            acc[r][3] = sq_acc(acc[r][3], c3, xi);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int j = ct * K1_TC + tile_code(lane + 32 * q);
+          if (j >= M) continue;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            // strict < against the FLT_MAX start value (lvq_pak.c:60,79); NaN never wins; the
+            // 64-bit key orders by distance, then by the lower index
+            if (acc[r][q] < FLT_MAX) {
+              const u64 key = ((u64)__float_as_uint(acc[r][q]) << 32) | (unsigned)j;
+              best[r] = key < best[r] ? key : best[r];
+            }
+          }
+        }
+      }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      u64 b = best[r];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, b, off);
+        b = o < b ? o : b;
+      }
+      if (lane == 0) skey[warp][r] = b;
+    }
+    __syncthreads();
+    if (valid && sub == 0 && lane < 8) {
+      const long w = gidx * 8 + lane;
+      if (w < cnt) {
+        u64 b = ~0ull;
+        for (int q = 0; q < S; q++) { const u64 o = skey[warp + q][lane]; b = o < b ? o : b; }
+        const long n = list[w];
+        idx[n] = b == ~0ull ? -1 : (int)(unsigned)b;
+        diff[n] = b == ~0ull ? -1.0f : __uint_as_float((unsigned)(b >> 32));
+        nfound[n] = 1;
+      }
     }
     __syncthreads();
   }
@@ -541,8 +635,19 @@ cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
   long warps = a.N < 8L * a.num_sms * 8 ? a.N : 8L * a.num_sms * 8;   // persistent over the list
   if (warps < 8) warps = 8;
   int grid = (int)((warps + 7) / 8);
+  // The list length is only known on the device.  With k == 1 and no masks, lists long enough to
+  // give every SM two warps of eight rows go to k1_warp8_kernel (codebook traffic / 8); shorter
+  // ones (and k >= 2, masks) to k1_warp_kernel, whose warps share a row.  Each kernel returns
+  // at once when the count is outside its range.
+  int split = 0x7fffffff;
+  if (a.k == 1 && a.mask == nullptr && a.short_list) {
+    split = 16 * a.num_sms;
+    k1_warp8_kernel<<<grid, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, split, a.idx, a.diff,
+                                          a.nfound);
+    g_launches++;
+  }
   k1_warp_kernel<<<grid, 256, 0, st>>>(a.data, a.mask, a.cT, a.M, a.D, a.k, a.listW,
-                                       a.counters + 0, a.idx, a.diff, a.nfound);
+                                       a.counters + 0, split, a.idx, a.diff, a.nfound);
   g_launches++;
   return cudaGetLastError();
 }

@@ -20,6 +20,7 @@ struct K1Args {
   int D, k;
   int skip_fast;                // host copy of (*cb_flags != 0)
   int num_sms;
+  int short_list;               // listW is expected to be short (K2 certificate failures): 8 rows per warp
   // scratch
   float *xT;                    // k1_xT_floats(N, D) floats (only touched when k == 1)
   unsigned char *flags;         // N

@@ -409,8 +409,9 @@ __device__ __forceinline__ uint32_t k2_idesc() {
 // TG: candidates kept per row, TT: smallest keys tracked per code tile.
 template <int TG, int TT>
 __global__ void __launch_bounds__(K2_THREADS, 1)
-k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg, long N,
-               long M, int Kp, int a_res, int32_t *__restrict__ cand, float *__restrict__ thr) {
+k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
+               const RowStats *__restrict__ rs, long N, long M, int Kp, int a_res, int k,
+               int32_t *__restrict__ cand, float *__restrict__ thr) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const size_t a_res_bytes = a_res ? (size_t)K2_TM * Kp * 2 : 0;
   const size_t b_stage_bytes = (size_t)K2_TN * K2_KS * 2;
@@ -588,10 +589,17 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
       }
       const long n = tile * K2_TM + row;
       if (n < N) {
+        // only keys within delta (> 2E) of the k-th smallest can still win or tie: the others
+        // become non-candidates bounded by `bound`, which spares the re-rank their code rows
+        const int kk = k < TG ? k : TG;
+        float kth = gk[0];
 #pragma unroll
-        for (int t = 0; t < TG; t++) cand[n * TG + t] = gi[t];
+        for (int t = 1; t < TG; t++) kth = (t < kk) ? gk[t] : kth;
+        const float bound = __fadd_ru(kth, rs[n].delta);
+#pragma unroll
+        for (int t = 0; t < TG; t++) cand[n * TG + t] = (gk[t] < bound) ? gi[t] : -1;
         // candidates dropped from the list are >= its last key; kept ones are re-ranked exactly
-        thr[n] = fminf(tmin, gk[TG - 1]);
+        thr[n] = fminf(fminf(tmin, gk[TG - 1]), bound);
       }
     }
   }
@@ -1073,8 +1081,8 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
   if (e != cudaSuccess) return e;
   const long ntiles = (a.N + K2_TM - 1) / K2_TM;
   const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
-  k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, a.N, a.M, Kp,
-                                                        a_res ? 1 : 0, s.cand, s.thr);
+  k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
+                                                        a_res ? 1 : 0, a.k, s.cand, s.thr);
   k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[2], st);
@@ -1173,7 +1181,7 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[1], st);
   if (record) e = k2_run_record(c, a, s, st);
-  else if (a.k == 1) e = k2_run_stream<4, 2>(c, a, s, st);
+  else if (a.k == 1) e = k2_run_stream<4, 3>(c, a, s, st);
   else if (a.k <= 5) e = k2_run_stream<10, 4>(c, a, s, st);
   else e = k2_run_stream<20, 4>(c, a, s, st);
   if (e != cudaSuccess) return e;
