@@ -1,0 +1,543 @@
+/* programs.c -- the SOM_PAK / LVQ_PAK programs whose loops sit on the BMU hot path, re-hosted on
+ * libbmu_b200 (include/bmu.h): same options, same stdout, same output files.
+ *
+ *   reference per-sample loop                         here
+ *   find_qerror / find_qerror2  som_rout.c:678-891    bmu_search + bmu_replay_qerror / bmu_qerror2
+ *   compute_visual_data         visual.c:48-155       bmu_search, rows written in data order
+ *   find_labels                 vcal.c:45-167         bmu_search, per-unit hitlists replayed in data order
+ *   compute_accuracy            accuracy.c:39-137     bmu_search, hitlists replayed in data order
+ *   compute_classifications     classify.c:41-95      bmu_search
+ *   compute_knnaccuracy         knntest.c:41-157      bmu_search (k), majority vote = head of the hitlist
+ *   som_training                som_rout.c:556-671    bmu_som_schedule + bmu_som_train
+ *   lvq1/olvq1/lvq2/lvq3        lvq_rout.c:498-916    bmu_lvq_schedule + bmu_lvq_train
+ *
+ * Not carried over (outside SURVEY.md section 8): -buffer (files are loaded whole), -selfuncs,
+ * snapshots, compressed / piped file names.
+ */
+#include "somhost.h"
+
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/bmu.h"
+
+/* ------------------------------------------------------------------ options */
+static const char *opt(int argc, char **argv, const char *name) {       /* lvq_pak.c:583-612, OPTION */
+  int i;
+  for (i = 0; i < argc - 1; i++)
+    if (strcmp(argv[i], name) == 0) return argv[i + 1];
+  return NULL;
+}
+static const char *need(int argc, char **argv, const char *name) {      /* ALWAYS */
+  const char *v = opt(argc, argv, name);
+  if (!v) { fprintf(stderr, "Can't find asked option %s\n", name); exit(-1); }
+  return v;
+}
+static int flag(int argc, char **argv, const char *name) {              /* OPTION2 */
+  int i;
+  for (i = 0; i < argc; i++)
+    if (strcmp(argv[i], name) == 0) return 1;
+  return 0;
+}
+static int verbose_level = 1;
+static void global_options(int argc, char **argv) {                     /* lvq_pak.c:618-661 */
+  const char *s = getenv("LVQSOM_MASK_STR");
+  if (s) pak_mask_string = s;
+  s = opt(argc, argv, "-mask_str");
+  if (s) pak_mask_string = s;
+  s = opt(argc, argv, "-v");
+  verbose_level = s ? atoi(s) : 1;
+  if (opt(argc, argv, "-buffer") || opt(argc, argv, "-selfuncs") || opt(argc, argv, "-snapinterval"))
+    fprintf(stderr, "note: -buffer, -selfuncs and snapshots are not supported by the B200 host; ignored\n");
+}
+
+static int engine_failed(const char *what) {
+  fprintf(stderr, "%s: %s\n", what, bmu_last_error());
+  return 1;
+}
+
+/* winners of every data vector: idx, squared diff, return value of the reference's winner function */
+struct winners {
+  int32_t *idx, *nfound;
+  float *diff;
+};
+static void winners_free(struct winners *w) { free(w->idx); free(w->nfound); free(w->diff); }
+static int find_winners(const struct pak_entries *codes, const struct pak_entries *data, int knn, struct winners *w) {
+  bmu_codebook *cb;
+  int rc;
+  size_t n = (size_t)(data->n > 0 ? data->n : 1);
+  w->idx = (int32_t *)malloc(sizeof(int32_t) * n * knn);
+  w->diff = (float *)malloc(sizeof(float) * n * knn);
+  w->nfound = (int32_t *)malloc(sizeof(int32_t) * n);
+  if (!w->idx || !w->diff || !w->nfound) { fprintf(stderr, "out of memory\n"); return 1; }
+  if (data->n == 0) return 0;
+  cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
+  if (!cb) return engine_failed("bmu_codebook_create");
+  rc = bmu_search(cb, data->points, data->mask, data->n, knn, w->idx, w->diff, w->nfound);
+  bmu_codebook_destroy(cb);
+  return rc ? engine_failed("bmu_search") : 0;
+}
+
+static int open_pair(int argc, char **argv, int data_labels_needed, int code_labels_needed, int skip_empty,
+                     int want_map, struct pak_entries **data, struct pak_entries **codes) {
+  const char *din = need(argc, argv, "-din"), *cin = need(argc, argv, "-cin");
+  *data = pak_load(din, data_labels_needed, skip_empty);
+  if (!*data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  *codes = pak_load(cin, code_labels_needed, 1);
+  if (!*codes) { fprintf(stderr, "Can't open code file '%s'\n", cin); return 1; }
+  if (want_map && (*codes)->topol < TOPOL_HEXA) { fprintf(stderr, "File %s is not a map file\n", cin); return 1; }
+  if ((*data)->dim != (*codes)->dim) {
+    fprintf(stderr, "Data and codebook vectors have different dimensions (%d != %d)", (*data)->dim, (*codes)->dim);
+    return 1;
+  }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+  return 0;
+}
+
+/* ------------------------------------------------------------------ qerror */
+int qerror_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  const char *s;
+  float radius, qerror = 0.0f;
+  int qmode;
+  global_options(argc, argv);
+  s = opt(argc, argv, "-radius");
+  radius = s ? (float)atof(s) : 1.0f;
+  s = opt(argc, argv, "-qetype");
+  qmode = s ? atoi(s) : 0;
+  if (open_pair(argc, argv, 0, 0, 1, 1, &data, &codes)) return 1;
+  if (qmode > 0) {
+    /* find_qerror2: per-sample neighbourhood-weighted error on the GPU, added in data order */
+    float *per = (float *)malloc(sizeof(float) * (size_t)(data->n > 0 ? data->n : 1));
+    bmu_codebook *cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
+    long i;
+    if (!per || !cb) return engine_failed("bmu_codebook_create");
+    if (bmu_qerror2(cb, codes->xdim, codes->ydim, codes->topol, codes->neigh, radius, data->points, data->mask,
+                    data->n, per))
+      return engine_failed("bmu_qerror2");
+    for (i = 0; i < data->n; i++) qerror += per[i];                 /* som_rout.c:872 */
+    bmu_codebook_destroy(cb);
+    free(per);
+  } else {
+    struct winners w;
+    if (find_winners(codes, data, 1, &w)) return 1;
+    qerror = bmu_replay_qerror(w.diff, w.nfound, data->n, 1);      /* som_rout.c:715 */
+    winners_free(&w);
+  }
+  if (verbose_level >= 1)                                          /* qerror.c:114-118 */
+    fprintf(stdout, "Quantization error of %s with map %s is %f per sample (%ld samples)\n",
+            need(argc, argv, "-din"), need(argc, argv, "-cin"), qerror / (float)data->n, data->n);
+  else
+    fprintf(stdout, "%f\n", qerror / (float)data->n);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ visual */
+int visual_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL, head;
+  struct winners w;
+  const char *dout;
+  FILE *fp;
+  long i, l;
+  int emptylab;
+  global_options(argc, argv);
+  dout = need(argc, argv, "-dout");
+  if (open_pair(argc, argv, 0, 0, !flag(argc, argv, "-noskip"), 1, &data, &codes)) return 1;
+  emptylab = label_index("EMPTY_LINE");                            /* visual.c:67 */
+  if (find_winners(codes, data, 1, &w)) return 1;
+  fp = fopen(dout, "w");
+  if (!fp) { fprintf(stderr, "can't open file for output: '%s'\n", dout); return 1; }
+  head = *codes;
+  head.dim = 3;
+  pak_write_header(fp, &head);                                     /* visual.c:74-100 */
+  for (i = 0; i < data->n; i++) {
+    if (w.nfound[i] == 0) {                                        /* visual.c:113-122 */
+      fprintf(fp, "%g %g %g %s \n", -1.0f, -1.0f, -1.0f, label_string(emptylab));
+      continue;
+    }
+    {
+      const long b = w.idx[i];
+      const float x = (float)(b % codes->xdim), y = (float)(b / codes->xdim);
+      const float qe = (float)sqrt((double)w.diff[i]);             /* visual.c:132 */
+      fprintf(fp, "%g %g %g ", x, y, qe);
+      for (l = codes->lab_off[b]; l < codes->lab_off[b + 1]; l++) fprintf(fp, "%s ", label_string(codes->lab_pool[l]));
+      fprintf(fp, "\n");
+    }
+  }
+  fclose(fp);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ vcal */
+int vcal_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  struct pak_hitlist *hits;
+  const char *s, *cout_name;
+  int numlabs, *nlab, *labs;
+  long i, tot = 0, pos = 0;
+  global_options(argc, argv);
+  cout_name = need(argc, argv, "-cout");
+  s = opt(argc, argv, "-numlabs");
+  numlabs = s ? atoi(s) : 1;
+  if (numlabs < 0) numlabs = 0;
+  /* vcal.c:196-205: the data file is opened while labels are still required */
+  if (open_pair(argc, argv, 1, 0, 1, 1, &data, &codes)) return 1;
+  if (find_winners(codes, data, 1, &w)) return 1;
+  hits = (struct pak_hitlist *)malloc(sizeof(*hits) * (size_t)codes->n);
+  nlab = (int *)malloc(sizeof(int) * (size_t)codes->n);
+  if (!hits || !nlab) return 1;
+  for (i = 0; i < codes->n; i++) hit_init(&hits[i]);
+  for (i = 0; i < data->n; i++) {                                  /* vcal.c:104-118: data order */
+    const int lab = pak_label(data, i);
+    if (w.nfound[i] == 0 || lab == LABEL_EMPTY) continue;
+    hit_add(&hits[w.idx[i]], lab);
+  }
+  for (i = 0; i < codes->n; i++) {                                 /* vcal.c:140-160 */
+    nlab[i] = (int)(numlabs == 0 ? hits[i].n : (hits[i].n < numlabs ? hits[i].n : numlabs));
+    tot += nlab[i];
+  }
+  labs = (int *)malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+  if (!labs) return 1;
+  for (i = 0; i < codes->n; i++) {
+    int t;
+    for (t = 0; t < nlab[i]; t++) labs[pos++] = (int)hits[i].label[t];
+    hit_free(&hits[i]);
+  }
+  if (pak_set_labels(codes, nlab, labs)) return 1;
+  pak_save(codes, cout_name);
+  free(hits); free(nlab); free(labs);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ accuracy / knntest */
+static void print_accuracy(const struct pak_hitlist *totals, const struct pak_hitlist *correct, long total,
+                           long stotal, int knn_style) {
+  long i;
+  fprintf(stdout, "\nRecognition accuracy:\n\n");
+  for (i = 0; i < totals->n; i++) {
+    const long tot = totals->freq[i], res = hit_freq(correct, totals->label[i]);
+    if (knn_style) {                                               /* knntest.c:133-142 */
+      fprintf(stdout, "%14s: ", label_string((int)totals->label[i]));
+      fprintf(stdout, "%6.2f %%\n", 100.0 * (float)res / tot);
+    } else {                                                       /* accuracy.c:118-127 */
+      fprintf(stdout, "%9s: %4ld entries ", label_string((int)totals->label[i]), tot);
+      fprintf(stdout, "%6.2f %%\n", 100.0 * (float)res / tot);
+    }
+  }
+  if (knn_style) fprintf(stdout, "\nTotal accuracy: %6.2f %%\n\n", 100.0 * (float)stotal / total);
+  else fprintf(stdout, "\nTotal accuracy: %5ld entries %6.2f %%\n\n", total, 100.0 * (float)stotal / total);
+}
+
+int accuracy_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  struct pak_hitlist correct, totals;
+  const char *cfout;
+  FILE *ocf = NULL;
+  long i, total = 0, stotal = 0;
+  global_options(argc, argv);
+  cfout = opt(argc, argv, "-cfout");
+  if (open_pair(argc, argv, 1, 1, 1, 0, &data, &codes)) return 1;
+  if (cfout && !(ocf = fopen(cfout, "w"))) { fprintf(stderr, "Cannot open '%s' for output\n", cfout); return 1; }
+  if (find_winners(codes, data, 1, &w)) return 1;
+  hit_init(&correct);
+  hit_init(&totals);
+  for (i = 0; i < data->n; i++) {                                  /* accuracy.c:80-105 */
+    const int datalabel = pak_label(data, i);
+    const int winlabel = w.idx[i] >= 0 ? pak_label(codes, w.idx[i]) : -1;
+    if (winlabel == datalabel) {
+      stotal++;
+      hit_add(&correct, datalabel);
+      if (ocf) fprintf(ocf, "1\n");
+    } else if (ocf) {
+      fprintf(ocf, "0\n");
+    }
+    hit_add(&totals, datalabel);
+    total++;
+  }
+  print_accuracy(&totals, &correct, total, stotal, 0);
+  if (ocf) fclose(ocf);
+  hit_free(&correct); hit_free(&totals);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+int knntest_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  struct pak_hitlist hits, correct, totals;
+  const char *s;
+  long i, total = 0, stotal = 0;
+  int knn, t;
+  global_options(argc, argv);
+  s = opt(argc, argv, "-knn");
+  knn = s ? atoi(s) : 5;                                           /* knntest.c:177 */
+  if (knn < 1) knn = 1;
+  if (knn > BMU_KMAX) { fprintf(stderr, "-knn %d is larger than the engine's limit %d\n", knn, BMU_KMAX); return 1; }
+  if (open_pair(argc, argv, 1, 1, 1, 0, &data, &codes)) return 1;
+  if (find_winners(codes, data, knn, &w)) return 1;
+  hit_init(&hits); hit_init(&correct); hit_init(&totals);
+  for (i = 0; i < data->n; i++) {                                  /* knntest.c:96-122 */
+    const int datalabel = pak_label(data, i);
+    hit_clear(&hits);
+    for (t = 0; t < knn; t++) {
+      const int j = w.idx[i * knn + t];
+      if (j >= 0) hit_add(&hits, pak_label(codes, j));
+    }
+    if (hits.n > 0 && hits.label[0] == datalabel) {
+      stotal++;
+      hit_add(&correct, datalabel);
+    }
+    hit_add(&totals, datalabel);
+    total++;
+  }
+  print_accuracy(&totals, &correct, total, stotal, 1);
+  hit_free(&hits); hit_free(&correct); hit_free(&totals);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ classify */
+int classify_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  const char *cfout, *dout;
+  FILE *ocf = NULL;
+  int *nlab, *labs;
+  long i;
+  global_options(argc, argv);
+  cfout = opt(argc, argv, "-cfout");
+  dout = need(argc, argv, "-dout");
+  if (open_pair(argc, argv, 0, 1, 1, 0, &data, &codes)) return 1;  /* classify.c:117-129 */
+  if (cfout && !(ocf = fopen(cfout, "w"))) { fprintf(stderr, "Cannot write to %s\n", cfout); return 1; }
+  if (find_winners(codes, data, 1, &w)) return 1;
+  nlab = (int *)malloc(sizeof(int) * (size_t)(data->n > 0 ? data->n : 1));
+  labs = (int *)malloc(sizeof(int) * (size_t)(data->n > 0 ? data->n : 1));
+  if (!nlab || !labs) return 1;
+  {
+    long pos = 0, keep = 0;
+    /* entries without a winner keep their labels (classify.c:63-67); count them first */
+    for (i = 0; i < data->n; i++) if (w.nfound[i] == 0) keep += data->lab_off[i + 1] - data->lab_off[i];
+    if (keep > 0) {
+      int *t = (int *)realloc(labs, sizeof(int) * (size_t)(data->n + keep));
+      if (!t) return 1;
+      labs = t;
+    }
+    for (i = 0; i < data->n; i++) {                                /* classify.c:62-80 */
+      int label;
+      if (w.nfound[i] == 0) {
+        long l;
+        label = label_index("# empty datavector");
+        nlab[i] = (int)(data->lab_off[i + 1] - data->lab_off[i]);
+        for (l = data->lab_off[i]; l < data->lab_off[i + 1]; l++) labs[pos++] = data->lab_pool[l];
+      } else {
+        label = pak_label(codes, w.idx[i]);                        /* only the first label */
+        nlab[i] = label != LABEL_EMPTY ? 1 : 0;
+        if (label != LABEL_EMPTY) labs[pos++] = label;
+      }
+      if (ocf) fprintf(ocf, "%s\n", label_string(label) ? label_string(label) : "(null)");
+    }
+  }
+  if (pak_set_labels(data, nlab, labs)) return 1;
+  if (ocf) fclose(ocf);
+  pak_save(data, dout);
+  free(nlab); free(labs);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ training */
+static int alpha_type_of(int argc, char **argv, int *type) {
+  const char *s = opt(argc, argv, "-alpha_type");
+  *type = BMU_ALPHA_LINEAR;
+  if (!s) return 0;
+  if (strcasecmp(s, "linear") == 0) return 0;
+  if (strcasecmp(s, "inverse_t") == 0) { *type = BMU_ALPHA_INVERSE_T; return 0; }
+  fprintf(stderr, "Unknown alpha type %s\n", s);
+  return 1;
+}
+
+/* list order of the data: identity, or the reference's shuffle when -rand is given
+ * (datafile.c:1152-1188; seed 0 means "seed from the clock", lvq_pak.c:476-484) */
+static int32_t *sample_order(int argc, char **argv, long n) {
+  const char *s = opt(argc, argv, "-rand");
+  int32_t *order;
+  int seed;
+  if (!s) return NULL;
+  seed = atoi(s);
+  if (seed == 0) seed = (int)time(NULL);
+  order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+  if (order) bmu_rand_order(n, seed, order);
+  return order;
+}
+
+int vsom_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  const char *cout_name;
+  long length;
+  float alpha, radius;
+  int alpha_type, use_fixed, use_weights, rc;
+  int32_t *order, *sample;
+  float *talp, *trad;
+  global_options(argc, argv);
+  cout_name = need(argc, argv, "-cout");
+  length = atol(need(argc, argv, "-rlen"));
+  alpha = (float)atof(need(argc, argv, "-alpha"));
+  radius = (float)atof(need(argc, argv, "-radius"));
+  use_fixed = flag(argc, argv, "-fixed");
+  use_weights = flag(argc, argv, "-weights");
+  if (alpha_type_of(argc, argv, &alpha_type)) return 1;
+  if (open_pair(argc, argv, 0, 0, 1, 1, &data, &codes)) return 1;
+  if (length > 0 && data->n > 0) {
+    order = sample_order(argc, argv, data->n);
+    sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)length);
+    talp = (float *)malloc(sizeof(float) * (size_t)length);
+    trad = (float *)malloc(sizeof(float) * (size_t)length);
+    if (!sample || !talp || !trad) { fprintf(stderr, "out of memory\n"); return 1; }
+    bmu_som_schedule(0, length, length, alpha, radius, alpha_type, data->n, order,
+                     use_weights ? data->weight : NULL, sample, talp, trad);
+    rc = bmu_som_train(codes->points, codes->n, codes->dim, codes->xdim, codes->ydim, codes->topol, codes->neigh,
+                       data->points, data->mask, data->n, use_fixed ? data->fixed_xy : NULL, sample, talp, trad,
+                       length);
+    if (rc) return engine_failed("bmu_som_train");
+    free(order); free(sample); free(talp); free(trad);
+  }
+  pak_save(codes, cout_name);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* datafile.c:1030-1046: strtok(basename, ".") -- leading dots are skipped, the name ends at the next one */
+static void lra_name(const char *codefile, char *out, size_t outsz) {
+  size_t i = 0;
+  while (codefile[i] == '.' && i + 5 < outsz) { out[i] = codefile[i]; i++; }
+  while (codefile[i] && codefile[i] != '.' && i + 5 < outsz) { out[i] = codefile[i]; i++; }
+  strcpy(out + i, ".lra");
+}
+
+int lvqtrain_main(int argc, char **argv, const char *progname) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  const char *cin_name, *cout_name, *s;
+  long length, i;
+  float alpha = 0.0f, winlen = 0.0f, epsilon = 0.0f, win_thr = 0.0f, *talp, *unit_alpha = NULL;
+  int algo, alpha_type, rc;
+  int32_t *order, *sample, *code_label, *data_label;
+  char lra[2048];
+  global_options(argc, argv);
+  s = opt(argc, argv, "-type");
+  if (s) progname = s;
+  if (strcasecmp(progname, "lvq1") == 0) algo = BMU_LVQ1;
+  else if (strcasecmp(progname, "lvq2") == 0) algo = BMU_LVQ2;
+  else if (strcasecmp(progname, "lvq3") == 0) algo = BMU_LVQ3;
+  else if (strcasecmp(progname, "olvq1") == 0) algo = BMU_OLVQ1;
+  else { fprintf(stderr, "Unknown LVQ type %s\n", progname); return 1; }
+  cin_name = need(argc, argv, "-cin");
+  cout_name = need(argc, argv, "-cout");
+  length = atol(need(argc, argv, "-rlen"));
+  if (algo == BMU_OLVQ1) { s = opt(argc, argv, "-alpha"); alpha = s ? (float)atof(s) : 0.0f; }   /* lvqtrain.c:151-166 */
+  else alpha = (float)atof(need(argc, argv, "-alpha"));
+  if (algo == BMU_LVQ2 || algo == BMU_LVQ3) winlen = (float)atof(need(argc, argv, "-win"));
+  if (algo == BMU_LVQ3) epsilon = (float)atof(need(argc, argv, "-epsilon"));
+  if (alpha_type_of(argc, argv, &alpha_type)) return 1;
+  if (open_pair(argc, argv, 1, 1, 1, 0, &data, &codes)) return 1;
+
+  code_label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(codes->n > 0 ? codes->n : 1));
+  data_label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(data->n > 0 ? data->n : 1));
+  if (!code_label || !data_label) return 1;
+  for (i = 0; i < codes->n; i++) code_label[i] = pak_label(codes, i);
+  for (i = 0; i < data->n; i++) data_label[i] = pak_label(data, i);
+
+  if (algo == BMU_OLVQ1) {                                          /* lvq_rout.c:609-627 */
+    unit_alpha = (float *)malloc(sizeof(float) * (size_t)codes->n);
+    if (!unit_alpha) return 1;
+    rc = 0;
+    if (alpha == 0.0f) {
+      FILE *fp;
+      lra_name(cin_name, lra, sizeof lra);
+      fp = fopen(lra, "r");
+      if (fp) {
+        rc = 1;
+        for (i = 0; i < codes->n; i++)
+          if (fscanf(fp, "%g\n", &unit_alpha[i]) < 0) { rc = 0; break; }
+        fclose(fp);
+      } else if (verbose_level >= 1) {
+        fprintf(stderr, "Can't open alpha file %s", lra);
+      }
+      if (!rc) alpha = 0.3f;
+    }
+    if (!rc)
+      for (i = 0; i < codes->n; i++) unit_alpha[i] = alpha;
+  }
+  {
+    const float w = winlen;
+    win_thr = (1 - w) / (1 + w);                                     /* lvq_rout.c:770, float arithmetic */
+  }
+  if (length > 0 && data->n > 0) {
+    order = sample_order(argc, argv, data->n);
+    sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)length);
+    talp = (float *)malloc(sizeof(float) * (size_t)length);
+    if (!sample || !talp) { fprintf(stderr, "out of memory\n"); return 1; }
+    bmu_lvq_schedule(0, length, length, alpha, alpha_type, data->n, order, sample, talp);
+    rc = bmu_lvq_train(algo, codes->points, code_label, codes->n, codes->dim, data->points, data->mask, data_label,
+                       data->n, sample, talp, length, win_thr, epsilon, alpha, unit_alpha);
+    if (rc) return engine_failed("bmu_lvq_train");
+    free(order); free(sample); free(talp);
+  }
+  if (algo == BMU_OLVQ1) {                                          /* lvq_rout.c:694, datafile.c:1061-1086 */
+    FILE *fp;
+    lra_name(cout_name, lra, sizeof lra);
+    fp = fopen(lra, "w+");
+    if (fp) {
+      for (i = 0; i < codes->n; i++) fprintf(fp, "%g\n", unit_alpha[i]);
+      fclose(fp);
+    } else {
+      fprintf(stderr, "Can't open alpha file %s for writing", lra);
+    }
+  }
+  pak_save(codes, cout_name);
+  /* lvqtrain.c:248-249 invalidate_alphafile(): every lvq program, olvq1 included, removes the
+   * .lra that belongs to the output name again */
+  lra_name(cout_name, lra, sizeof lra);
+  {
+    FILE *fp = fopen(lra, "r");
+    if (fp) {                                                       /* datafile.c:1088-1108 */
+      if (verbose_level >= 1) fprintf(stdout, "Removing the learning rate file %s\n", lra);
+      fclose(fp);
+      if (remove(lra)) fprintf(stderr, "Can not remove %s", lra);
+    }
+  }
+  free(code_label); free(data_label); free(unit_alpha);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ pakcat */
+int pakcat_main(int argc, char **argv) {
+  struct pak_entries *e;
+  global_options(argc, argv);
+  e = pak_load(need(argc, argv, "-din"), 0, !flag(argc, argv, "-noskip"));
+  if (!e) return 1;
+  if (pak_save(e, need(argc, argv, "-dout"))) return 1;
+  pak_free(e);
+  return 0;
+}

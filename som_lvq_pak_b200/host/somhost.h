@@ -1,11 +1,13 @@
-/* somhost.h -- C host layer of the B200 BMU engine: the data model, file formats and loops of
- * SOM_PAK / LVQ_PAK that sit on either side of the hot path, calling libbmu_b200 (include/bmu.h).
+/* somhost.h -- C host layer of the B200 BMU engine: the data model, file formats and program
+ * loops of SOM_PAK / LVQ_PAK that sit on either side of the hot path, calling libbmu_b200
+ * (include/bmu.h) instead of the per-sample function pointers of struct teach_params.
  *
- * The struct and function names mirror the reference's interface (reference lvq_pak.h:73-124,
- * 186-204; datafile.h; labels.h; som_rout.h; lvq_rout.h) so that the reference's programs read
- * the same against this layer; the implementation is new: entries are loaded into flat arrays
- * once, the per-sample winner loop is one bmu_search() call, and the consumers replay the
- * results in data order (which is what makes stdout and the output files byte-identical).
+ * The reference keeps `struct entries` as a linked list of `struct data_entry`
+ * (reference lvq_pak.h:73-113) and reaches its winner function once per sample.  Here a file
+ * is loaded ONCE into flat arrays (what bmu_search / bmu_som_train / bmu_lvq_train take), the
+ * per-sample loop becomes one batch call, and the consumers replay the results in data order,
+ * which is what makes stdout and the output files byte-identical to the reference programs.
+ * File grammar: SURVEY.md appendix B (datafile.c:112-148, 552-748, 396-447).
  */
 #ifndef SOMHOST_H
 #define SOMHOST_H
@@ -20,91 +22,50 @@
 #define NEIGH_UNKNOWN 0
 #define NEIGH_BUBBLE 1
 #define NEIGH_GAUSSIAN 2
-#define ALPHA_LINEAR 1
-#define ALPHA_INVERSE_T 2
 #define LABEL_EMPTY 0
 
-struct fixpoint { short xfix, yfix; };
+/* ---- label table (reference labels.c:36-128): index 0 is the empty label ---------- */
+int label_index(const char *str);        /* adds the label when it is new */
+const char *label_string(int ind);       /* NULL for LABEL_EMPTY / unknown */
 
-struct data_entry {                 /* reference lvq_pak.h:73-87 */
-  float *points;
-  int *labels;                      /* label ids, num_labs of them */
-  short num_labs;
-  short weight;
-  struct data_entry *next;
-  char *mask;                       /* non-zero = component ignored */
-  struct fixpoint *fixed;
+/* ---- entries: one .dat / .cod file in flat arrays ------------------------------------- */
+struct pak_entries {
+  int dim, topol, neigh, xdim, ydim;
+  long n;                  /* number of entries kept (all-masked ones are dropped unless asked) */
+  float *points;           /* n x dim, masked components stored as 0 (datafile.c:623,659) */
+  unsigned char *mask;     /* n x dim, non-zero = component ignored; NULL when the file has none */
+  long *lab_off;           /* n + 1 offsets into lab_pool: entry i has labels lab_pool[lab_off[i] .. lab_off[i+1]) */
+  int *lab_pool;
+  short *weight;           /* n, `weight=N` terms (0 when absent) */
+  short *fixed_xy;         /* n x 2, `fixed=x,y` terms (-1,-1 when absent) */
 };
 
-struct entries {                    /* reference lvq_pak.h:89-113 */
-  short dimension, topol, neigh, xdim, ydim;
-  struct data_entry *entries;
-  long num_entries;
-  int skip_empty, labels_needed, random_order;
+/* labels_needed: a line without a label is an error (datafile.c:737-745);
+ * skip_empty: drop entries whose components are all masked (datafile.c:677-690) */
+struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty);
+struct pak_entries *pak_alloc(int dim, long n);
+void pak_free(struct pak_entries *e);
+int pak_save(const struct pak_entries *e, const char *name);
+void pak_write_header(FILE *fp, const struct pak_entries *e);
+/* first label of entry i (get_entry_label, labels.h:45) */
+int pak_label(const struct pak_entries *e, long i);
+/* replace the labels of every entry: nlab[i] labels taken from labs (concatenated) */
+int pak_set_labels(struct pak_entries *e, const int *nlab, const int *labs);
+extern const char *pak_mask_string;      /* "x" unless -mask_str / LVQSOM_MASK_STR */
+
+/* ---- hitlist (labels.c:286-444): (label, count) pairs, highest count first; a label that
+ * ties with the one in front of it stays behind it */
+struct pak_hitlist {
+  long n, cap;
+  long *label, *freq;
 };
+void hit_init(struct pak_hitlist *h);
+void hit_clear(struct pak_hitlist *h);
+void hit_free(struct pak_hitlist *h);
+long hit_add(struct pak_hitlist *h, long label);
+long hit_freq(const struct pak_hitlist *h, long label);
 
-struct winner_info {                /* reference lvq_pak.h:120-124 */
-  long index;
-  struct data_entry *winner;
-  float diff;
-};
-
-struct teach_params {               /* reference lvq_pak.h:186-204 (the fields the loops use) */
-  short topol, neigh, alpha_type;
-  float radius, alpha;
-  long length;
-  int knn;
-  struct entries *codes, *data;
-  long snap_interval;               /* 0 = no snapshots */
-  const char *snap_file;
-};
-
-struct hit_entry { struct hit_entry *next, *prev; long label, freq; };
-struct hitlist { struct hit_entry *head, *tail; long entries; };
-
-/* ---- global switches (reference datafile.c:1310-1319, lvq_pak.c:486-495) */
-int label_not_needed(int level);
-int use_weights(int level);
-int use_fixed(int level);
-extern int verbose_level;
-extern const char *masked_string;
-
-/* ---- labels (labels.c) */
-int find_conv_to_ind(const char *str);
-const char *find_conv_to_lab(int ind);
-int get_entry_label(const struct data_entry *e);
-void set_entry_label(struct data_entry *e, int label);
-void add_entry_label(struct data_entry *e, int label);
-void clear_entry_labels(struct data_entry *e);
-struct hitlist *new_hitlist(void);
-void clear_hitlist(struct hitlist *hl);
-void free_hitlist(struct hitlist *hl);
-long add_hit(struct hitlist *hl, long label);
-long hitlist_label_freq(struct hitlist *hl, long label);
-
-/* ---- entries (datafile.c) */
-struct entries *open_entries(const char *name);       /* loads the whole file */
-struct entries *alloc_entries(void);
-void close_entries(struct entries *e);
-int save_entries(struct entries *e, const char *name);
-int write_header(FILE *fp, const struct entries *e);
-int write_entry(FILE *fp, const struct entries *e, const struct data_entry *d);
-void init_random(int seed);
-void randomize_entry_order(struct entries *e);          /* datafile.c:1152-1188 */
-
-/* ---- the loops on the hot path, now batch calls into libbmu_b200 */
-float find_qerror(struct teach_params *teach);                       /* som_rout.c:678-731 */
-float find_qerror2(struct teach_params *teach);                      /* som_rout.c:823-891 */
-struct entries *som_training(struct teach_params *teach);            /* som_rout.c:556-671 */
-struct entries *lvq1_training(struct teach_params *teach);           /* lvq_rout.c:498-577 */
-struct entries *olvq1_training(struct teach_params *teach, const char *in, const char *out);
-struct entries *lvq2_training(struct teach_params *teach, float winlen);
-struct entries *lvq3_training(struct teach_params *teach, float epsilon, float winlen);
-/* batch WINNER_FUNCTION: win is N x knn, ret[n] = what find_winner_euc/knn would return */
-int find_winners_batch(struct entries *codes, struct entries *data, int knn,
-                       struct winner_info *win, int *ret);
-
-/* ---- programs (one main each in the reference) */
+/* ---- programs: same options, stdout and output files as the reference's ----------------- */
 int vsom_main(int argc, char **argv);
 int qerror_main(int argc, char **argv);
 int visual_main(int argc, char **argv);
@@ -113,5 +74,6 @@ int accuracy_main(int argc, char **argv);
 int classify_main(int argc, char **argv);
 int knntest_main(int argc, char **argv);
 int lvqtrain_main(int argc, char **argv, const char *progname);
+int pakcat_main(int argc, char **argv);   /* load + save: exercises the file layer alone */
 
 #endif
