@@ -414,6 +414,213 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
     for (int u = tid; u < ucount; u += K3_THREADS) p.unit_alpha[u0 + u] = ua_s[u];
 }
 
+// ---------------------------------------------------------------- fused SOM kernel
+// Specialisation for the large-map case (no masks, no fixed points, D >= 64, <= 512 units per
+// CTA): the generic kernel above makes three passes over its shared-memory slice per step
+// (search: read; update: read + write) and is bound by shared-memory bandwidth -- measured on
+// C5 (443 units x 128 dims per CTA): search 3350 + update 6139 of 12200 cycles per step.  Here
+//   * one thread owns one unit; its first K3F_DR components live in REGISTERS for the whole run,
+//     the rest in shared memory as component pairs [(D-DR)/2][512] (conflict-free 8-byte lanes);
+//   * the update of step t and the winner search of step t+1 are ONE pass: a component pair is
+//     adapted towards x_t and, while still in registers, its squared difference to x_{t+1} is
+//     accumulated (same operations and order as adapt_vector / find_winner_euc, lvq_pak.c:339-351,
+//     63-73: the search of step t+1 sees exactly the codebook the update of step t left).
+// The grid exchange is the generic kernel's (tagged slot per CTA, every CTA polls all slots).
+constexpr int K3F_THREADS = 512;
+constexpr int K3F_DR = 64;
+
+__device__ __forceinline__ void k3f_pair(u64 &c, float xt0, float xt1, float xn0, float xn1, bool upd, float a,
+                                         float &acc) {
+  float c0, c1;
+  unpack2(c, c0, c1);
+  if (upd) {                                            // c + a*(x - c), one rounding per operation
+    float p0, p1;
+    unpack2(mul2(pack2(a, a), sub2(pack2(xt0, xt1), c)), p0, p1);
+    c0 = __fadd_rn(c0, p0);
+    c1 = __fadd_rn(c1, p1);
+    c = pack2(c0, c1);
+  }
+  float s0, s1;
+  const u64 d = sub2(c, pack2(xn0, xn1));               // code - sample (lvq_pak.c:70)
+  unpack2(mul2(d, d), s0, s1);
+  acc = __fadd_rn(__fadd_rn(acc, s0), s1);              // component order
+}
+
+__global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = p.D, U = p.U;
+  const int Dp = (D + 3) & ~3;                                     // x rows padded with zeros
+  const int nsp = (Dp - K3F_DR) / 2;                               // component pairs kept in shared memory
+  float *xs = reinterpret_cast<float *>(smem_raw);                 // [3][Dp]
+  u64 *wred = reinterpret_cast<u64 *>(xs + 3 * Dp);                // [16] per-warp keys
+  u64 *gw = wred + 16;                                             // [2] global winner (+pad)
+  u64 *sl2 = gw + 2;                                               // [nsp][512] component pairs
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  const int u0 = blockIdx.x * U;
+  const int ucount = max(0, min(U, (int)p.M - u0));
+  const bool active = tid < ucount;
+  const int gidx = u0 + tid;
+  const bool gaussian = p.mode == K3_SOM_GAUSSIAN;
+  const bool small_map = p.xdim <= 1024 && p.ydim <= 1024 && p.xdim > 0;
+  const int tx = p.xdim > 0 ? gidx % p.xdim : 0, ty = p.xdim > 0 ? gidx / p.xdim : 0;   // som_rout.c:493-494
+
+  // ---- load this thread's unit (components beyond D are zero: they add +0 to every sum)
+  u64 cr[K3F_DR / 2];
+  {
+    const float *src = p.codes + (size_t)gidx * D;
+#pragma unroll
+    for (int j = 0; j < K3F_DR / 2; j++)
+      cr[j] = active ? pack2(src[2 * j], src[2 * j + 1]) : pack2(0.0f, 0.0f);
+    for (int j = 0; j < nsp; j++) {
+      const int i = K3F_DR + 2 * j;
+      const float v0 = (active && i < D) ? src[i] : 0.0f, v1 = (active && i + 1 < D) ? src[i + 1] : 0.0f;
+      sl2[(size_t)j * K3F_THREADS + tid] = pack2(v0, v1);
+    }
+  }
+  for (int i = tid; i < 3 * Dp; i += K3F_THREADS) xs[i] = 0.0f;    // pads stay zero: cp.async writes only D floats
+  __syncthreads();
+
+  auto stage = [&](int buf, long srow) {
+    const float *src = p.data + srow * D;
+    float *dst = xs + buf * Dp;
+    if ((D & 3) == 0) {
+      for (int i = tid * 4; i < D; i += K3F_THREADS * 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i)), "l"(src + i));
+    } else {
+      for (int i = tid; i < D; i += K3F_THREADS)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + i)), "l"(src + i));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // one pass over the unit: optional update towards xt, then the squared distance to xn
+  auto pass = [&](const float *xt, const float *xn, bool upd, float a) -> float {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < K3F_DR / 2; j += 2) {
+      const float4 t4 = *reinterpret_cast<const float4 *>(xt + 2 * j);
+      const float4 n4 = *reinterpret_cast<const float4 *>(xn + 2 * j);
+      k3f_pair(cr[j], t4.x, t4.y, n4.x, n4.y, upd, a, acc);
+      k3f_pair(cr[j + 1], t4.z, t4.w, n4.z, n4.w, upd, a, acc);
+    }
+#pragma unroll 2
+    for (int j = 0; j < nsp; j += 2) {
+      u64 *q0 = sl2 + (size_t)j * K3F_THREADS + tid, *q1 = q0 + K3F_THREADS;
+      u64 c0 = *q0, c1 = *q1;
+      const float4 t4 = *reinterpret_cast<const float4 *>(xt + K3F_DR + 2 * j);
+      const float4 n4 = *reinterpret_cast<const float4 *>(xn + K3F_DR + 2 * j);
+      k3f_pair(c0, t4.x, t4.y, n4.x, n4.y, upd, a, acc);
+      k3f_pair(c1, t4.z, t4.w, n4.z, n4.w, upd, a, acc);
+      if (upd) { *q0 = c0; *q1 = c1; }
+    }
+    return acc;
+  };
+
+  unsigned bstep = 0;
+  int b0 = 0;                                     // xs buffer of the current sample
+  float acc = 0.0f;
+  if (p.nsteps > 0) {
+    stage(0, p.sample[0]);
+    if (p.nsteps > 1) stage(1, p.sample[1]);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    acc = pass(xs, xs, false, 0.0f);              // distances to the first sample, no update
+  }
+  for (long t = 0; t < p.nsteps; t++) {
+    const float talp = p.talp[t], trad = p.trad[t];
+    const int b1 = b0 == 2 ? 0 : b0 + 1, b2 = b1 == 2 ? 0 : b1 + 1;
+    // ---- winner of step t: CTA minimum, then the grid exchange
+    u64 k1 = (active && acc < FLT_MAX) ? make_key(acc, gidx, false) : K3_NOKEY;   // lvq_pak.c:57,79
+    k1 = warp_min_u64(k1);
+    if (lane == 0) wred[warp] = k1;
+    __syncthreads();
+    if (warp == 0) {
+      u64 bk = lane < K3F_THREADS / 32 ? wred[lane] : K3_NOKEY;
+      bk = warp_min_u64(bk);
+      if (G > 1) {
+        const u64 tag = (u64)((bstep + 1) & 0xFFu);
+        u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
+        if (lane == 0) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, bk | tag);
+        constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
+        u64 v1[NQ];
+        unsigned pending = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          v1[q] = K3_NOKEY;
+          if (lane + 32 * q < G) pending |= 1u << q;
+        }
+        while (pending) {
+#pragma unroll
+          for (int q = 0; q < NQ; q++)
+            if (pending & (1u << q)) v1[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q));
+#pragma unroll
+          for (int q = 0; q < NQ; q++)
+            if ((pending & (1u << q)) && (v1[q] & 0xFFu) == tag) pending &= ~(1u << q);
+        }
+        u64 m1 = K3_NOKEY;
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+          if (lane + 32 * q < G) { const u64 a1 = v1[q] & ~0xFFull; m1 = a1 < m1 ? a1 : m1; }
+        bk = warp_min_u64(m1);
+      }
+      if (lane == 0) gw[0] = bk;
+    }
+    bstep++;
+    // sample t+1 (staged one step ago) must have landed before the fused pass reads it
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const u64 g1 = gw[0];
+    if (t + 2 < p.nsteps) stage(b2, p.sample[t + 2]);      // buffer b2 was last read two passes ago
+    // ---- update of step t fused with the search of step t+1
+    bool upd = false;
+    float a = talp;
+    if (g1 != K3_NOKEY) {                                  // no winner (all distances NaN/Inf): step skipped
+      const int w = key_idx(g1, false);
+      const int bx = w % p.xdim, by = w / p.xdim;          // som_rout.c:641-642
+      float dd;
+      if (small_map) dd = p.topol == 4 ? rect_dist_small(bx, by, tx, ty) : hexa_dist_small(bx, by, tx, ty);
+      else dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
+      if (gaussian) { a = gauss_alpha_dev(talp, dd, trad); upd = active; }
+      else upd = active && dd <= trad;                     // som_rout.c:496
+    }
+    const float *xt = xs + b0 * Dp;
+    const float *xn = (t + 1 < p.nsteps) ? xs + b1 * Dp : xt;
+    acc = pass(xt, xn, upd, a);
+    b0 = b1;
+  }
+
+  // ---- write the unit back
+  __syncthreads();
+  if (active) {
+    float *dst = p.codes + (size_t)gidx * D;
+#pragma unroll
+    for (int j = 0; j < K3F_DR / 2; j++) {
+      float c0, c1;
+      unpack2(cr[j], c0, c1);
+      dst[2 * j] = c0;
+      dst[2 * j + 1] = c1;
+    }
+    for (int j = 0; j < nsp; j++) {
+      float c0, c1;
+      unpack2(sl2[(size_t)j * K3F_THREADS + tid], c0, c1);
+      const int i = K3F_DR + 2 * j;
+      if (i < D) dst[i] = c0;
+      if (i + 1 < D) dst[i + 1] = c1;
+    }
+  }
+}
+
+static size_t k3f_smem_bytes(int D) {
+  const int Dp = (D + 3) & ~3;
+  return (size_t)3 * Dp * 4 + 18 * 8 + (size_t)((Dp - K3F_DR) / 2) * K3F_THREADS * 8;
+}
+
+bool k3_fused_eligible(const K3Params &p, const K3Plan &plan, bool has_mask, size_t smem_optin) {
+  return p.mode <= K3_SOM_GAUSSIAN && !has_mask && p.fixed_xy == nullptr && p.D >= K3F_DR && plan.U <= K3F_THREADS &&
+         plan.grid <= 160 && p.talp && p.trad && p.xdim > 0 && k3f_smem_bytes(p.D) <= smem_optin;
+}
+
 // ---------------------------------------------------------------- mask encoding
 __global__ void encode_mask_kernel(float *__restrict__ data, const unsigned char *__restrict__ mask,
                                    unsigned char *__restrict__ valid, long N, int D) {
@@ -469,6 +676,22 @@ K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
 cudaError_t k3_launch(const K3Params &p, const K3Plan &plan, bool has_mask, cudaStream_t st) {
   const bool top2 = p.mode == K3_LVQ2 || p.mode == K3_LVQ3;
   void *fn;
+  {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (k3_fused_eligible(p, plan, has_mask, (size_t)optin)) {
+      const size_t smem = k3f_smem_bytes(p.D);
+      cudaError_t e = cudaFuncSetAttribute((void *)k3_som_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaMemsetAsync(p.slots, 0, sizeof(u64) * 2 * K3_SLOT_STRIDE * plan.grid, st);
+      if (e != cudaSuccess) return e;
+      K3Params pp = p;
+      void *args[] = {&pp};
+      return cudaLaunchCooperativeKernel((void *)k3_som_fused_kernel, dim3(plan.grid), dim3(K3F_THREADS), args, smem, st);
+    }
+  }
   if (plan.slice_in_smem) {
     if (has_mask) fn = top2 ? (void *)k3_kernel<true, true, true> : (void *)k3_kernel<true, false, true>;
     else fn = top2 ? (void *)k3_kernel<false, true, true> : (void *)k3_kernel<false, false, true>;

@@ -102,3 +102,23 @@ def test_som_chunked_equals_whole(engine, golden):
                               snapshot_interval=400, snapshot_cb=lambda le, c: snaps.append(le))
     assert snaps == [400, 800, 1200]
     assert_bits_equal(out, g["t3_n1_a1_s-1"])
+
+
+@pytest.mark.parametrize("xdim,ydim,D,topol,neigh", [(20, 15, 70, 3, 1), (20, 15, 64, 4, 2), (64, 48, 64, 3, 2),
+                                                       (64, 48, 100, 4, 1), (37, 29, 128, 3, 2)])
+def test_som_large_dim_fused_kernel(engine, oracle, xdim, ydim, D, topol, neigh):
+    """D >= 64 without masks / fixed points takes the fused update+search kernel (one unit per
+    thread, half of it in registers); same bar as the generic kernel, -rand order and a radius
+    that shrinks through the run"""
+    rng = np.random.default_rng(xdim * 7 + D)
+    M, N, rlen = xdim * ydim, 500, 400
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    for at, seed in ((1, None), (2, 9)):
+        out = engine.som_training(codes, data, xdim, ydim, topol, neigh, rlen, 0.05, 6.0, at, rand_seed=seed)
+        order = None if seed is None else oracle.shuffle_order(N, seed)
+        exp = oracle.som_train(codes, data, xdim, ydim, topol, neigh, rlen, 0.05, 6.0, at, order=order)
+        close_or_equal(out, exp, neigh, "fused som %dx%d D=%d t%d n%d" % (xdim, ydim, D, topol, neigh))
+        if neigh == 2:
+            nbad = int((out.view(np.int32) != exp.view(np.int32)).sum())
+            assert nbad <= out.size // 100000 + 2, "%d of %d floats differ" % (nbad, out.size)
