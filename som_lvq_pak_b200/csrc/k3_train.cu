@@ -429,21 +429,40 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
 constexpr int K3F_THREADS = 512;
 constexpr int K3F_DR = 64;
 
-__device__ __forceinline__ void k3f_pair(u64 &c, float xt0, float xt1, float xn0, float xn1, bool upd, float a,
-                                         float &acc) {
-  float c0, c1;
-  unpack2(c, c0, c1);
+// Four component pairs of one unit: optional update towards xt, then the squared differences to
+// xn.  Written stage by stage over the four pairs so that the independent operations of different
+// pairs are adjacent in the instruction stream (a warp issues in order; one pair at a time left
+// the pass latency bound at ~80 cycles per pair).  Only the final accumulation is a chain.
+__device__ __forceinline__ void k3f_quad(u64 (&c)[4], const float4 &ta, const float4 &tb, const float4 &na,
+                                         const float4 &nb, bool upd, float a, float &acc) {
   if (upd) {                                            // c + a*(x - c), one rounding per operation
-    float p0, p1;
-    unpack2(mul2(pack2(a, a), sub2(pack2(xt0, xt1), c)), p0, p1);
-    c0 = __fadd_rn(c0, p0);
-    c1 = __fadd_rn(c1, p1);
-    c = pack2(c0, c1);
+    const u64 a2 = pack2(a, a);
+    const u64 xt[4] = {pack2(ta.x, ta.y), pack2(ta.z, ta.w), pack2(tb.x, tb.y), pack2(tb.z, tb.w)};
+    u64 d[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) d[k] = sub2(xt[k], c[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d[k] = mul2(a2, d[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float c0, c1, p0, p1;
+      unpack2(c[k], c0, c1);
+      unpack2(d[k], p0, p1);
+      c[k] = pack2(__fadd_rn(c0, p0), __fadd_rn(c1, p1));
+    }
   }
-  float s0, s1;
-  const u64 d = sub2(c, pack2(xn0, xn1));               // code - sample (lvq_pak.c:70)
-  unpack2(mul2(d, d), s0, s1);
-  acc = __fadd_rn(__fadd_rn(acc, s0), s1);              // component order
+  const u64 xn[4] = {pack2(na.x, na.y), pack2(na.z, na.w), pack2(nb.x, nb.y), pack2(nb.z, nb.w)};
+  u64 e[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) e[k] = sub2(c[k], xn[k]);  // code - sample (lvq_pak.c:70)
+#pragma unroll
+  for (int k = 0; k < 4; k++) e[k] = mul2(e[k], e[k]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {                          // component order
+    float s0, s1;
+    unpack2(e[k], s0, s1);
+    acc = __fadd_rn(__fadd_rn(acc, s0), s1);
+  }
 }
 
 __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Params p) {
@@ -498,21 +517,31 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
   auto pass = [&](const float *xt, const float *xn, bool upd, float a) -> float {
     float acc = 0.0f;
 #pragma unroll
-    for (int j = 0; j < K3F_DR / 2; j += 2) {
-      const float4 t4 = *reinterpret_cast<const float4 *>(xt + 2 * j);
-      const float4 n4 = *reinterpret_cast<const float4 *>(xn + 2 * j);
-      k3f_pair(cr[j], t4.x, t4.y, n4.x, n4.y, upd, a, acc);
-      k3f_pair(cr[j + 1], t4.z, t4.w, n4.z, n4.w, upd, a, acc);
+    for (int j = 0; j < K3F_DR / 2; j += 4) {
+      const float4 ta = *reinterpret_cast<const float4 *>(xt + 2 * j), tb = *reinterpret_cast<const float4 *>(xt + 2 * j + 4);
+      const float4 na = *reinterpret_cast<const float4 *>(xn + 2 * j), nb = *reinterpret_cast<const float4 *>(xn + 2 * j + 4);
+      u64 c[4] = {cr[j], cr[j + 1], cr[j + 2], cr[j + 3]};
+      k3f_quad(c, ta, tb, na, nb, upd, a, acc);
+      cr[j] = c[0]; cr[j + 1] = c[1]; cr[j + 2] = c[2]; cr[j + 3] = c[3];
     }
-#pragma unroll 2
-    for (int j = 0; j < nsp; j += 2) {
-      u64 *q0 = sl2 + (size_t)j * K3F_THREADS + tid, *q1 = q0 + K3F_THREADS;
-      u64 c0 = *q0, c1 = *q1;
-      const float4 t4 = *reinterpret_cast<const float4 *>(xt + K3F_DR + 2 * j);
-      const float4 n4 = *reinterpret_cast<const float4 *>(xn + K3F_DR + 2 * j);
-      k3f_pair(c0, t4.x, t4.y, n4.x, n4.y, upd, a, acc);
-      k3f_pair(c1, t4.z, t4.w, n4.z, n4.w, upd, a, acc);
-      if (upd) { *q0 = c0; *q1 = c1; }
+    for (int j = 0; j + 4 <= nsp; j += 4) {
+      u64 *q = sl2 + (size_t)j * K3F_THREADS + tid;
+      u64 c[4] = {q[0], q[K3F_THREADS], q[2 * K3F_THREADS], q[3 * K3F_THREADS]};
+      const float *xtj = xt + K3F_DR + 2 * j, *xnj = xn + K3F_DR + 2 * j;
+      const float4 ta = *reinterpret_cast<const float4 *>(xtj), tb = *reinterpret_cast<const float4 *>(xtj + 4);
+      const float4 na = *reinterpret_cast<const float4 *>(xnj), nb = *reinterpret_cast<const float4 *>(xnj + 4);
+      k3f_quad(c, ta, tb, na, nb, upd, a, acc);
+      if (upd) { q[0] = c[0]; q[K3F_THREADS] = c[1]; q[2 * K3F_THREADS] = c[2]; q[3 * K3F_THREADS] = c[3]; }
+    }
+    if (nsp & 2) {                                   // Dp - DR is a multiple of 4, so nsp is even: one pair of pairs left
+      const int j = nsp - 2;
+      u64 *q = sl2 + (size_t)j * K3F_THREADS + tid;
+      u64 c[4] = {q[0], q[K3F_THREADS], pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)};
+      const float *xtj = xt + K3F_DR + 2 * j, *xnj = xn + K3F_DR + 2 * j;
+      const float4 ta = *reinterpret_cast<const float4 *>(xtj), na = *reinterpret_cast<const float4 *>(xnj);
+      const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      k3f_quad(c, ta, z, na, z, upd, a, acc);          // zero pairs add +0 to the sum
+      if (upd) { q[0] = c[0]; q[K3F_THREADS] = c[1]; }
     }
     return acc;
   };
