@@ -1,0 +1,105 @@
+"""GPU: BASELINE.json's full-size configurations (C3 10 M x 64 vs 100x100, C4 1 M x 512 vs 4096
+units with k = 5, C5 256x256x128 map) checked through size-independent properties, plus direct
+oracle comparison on samples the CPU finishes in seconds:
+  * every row gets a winner, the BMU histogram sums to N;
+  * the tensor-core filter path (K2) and the exact FP32 path (K1) agree bit for bit on a sample;
+  * a sample agrees bit for bit with the oracle;
+  * searching the codebook against itself returns the identity with distance 0;
+  * k-NN lists are sorted by the reference's rule and hold distinct codes;
+  * a prefix of the C5 training schedule reproduces the oracle's codebook."""
+import numpy as np
+import pytest
+import torch
+
+from bench import synth_numpy, synth_rows_torch
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_search(engine, cb, data, k, path):
+    n = data.shape[0]
+    idx = torch.empty((n, k), dtype=torch.int32, device=data.device)
+    diff = torch.empty((n, k), dtype=torch.float32, device=data.device)
+    nf = torch.empty(n, dtype=torch.int32, device=data.device)
+    engine.set_search_path(path)
+    try:
+        cb.search_dev(data.data_ptr(), n, k, idx.data_ptr(), diff.data_ptr(), nf.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        engine.set_search_path(0)
+    return idx, diff, nf
+
+
+def test_c3_full_size(engine, oracle):
+    dev = torch.device("cuda:0")
+    N, D, M = 10_000_000, 64, 10_000
+    codes = synth_rows_torch(2, 0, M, D, dev)
+    data = synth_rows_torch(1, 0, N, D, dev)
+    cb = engine.Codebook(codes.cpu().numpy())
+    idx, diff, nf = dev_search(engine, cb, data, 1, 2)                      # K2 filter path
+    bd = engine.last_search_breakdown()
+    assert bd["k2_certified"] + bd["k2_failed"] == N and bd["k2_certified"] > 0.99 * N, bd
+    assert bool((nf == 1).all())
+    hist = torch.bincount(idx[:, 0].long(), minlength=M)
+    assert int(hist.sum()) == N and int(idx.min()) >= 0 and int(idx.max()) < M
+    # exact FP32 path on a random sample of rows: identical winners and distances
+    g = torch.Generator(device="cpu").manual_seed(5)
+    rows = torch.randperm(N, generator=g)[:200_000].to(dev)
+    sub = data[rows].contiguous()
+    eidx, ediff, _ = dev_search(engine, cb, sub, 1, 1)
+    assert bool((eidx == idx[rows]).all()) and bool((ediff.view(torch.int32) == diff[rows].view(torch.int32)).all())
+    # oracle on a smaller sample
+    h = rows[:1500]
+    o = oracle.search(codes.cpu().numpy(), data[h].cpu().numpy(), 1)
+    assert_bits_equal(idx[h].cpu().numpy(), o[0])
+    assert_bits_equal(diff[h].cpu().numpy(), o[1])
+    # the codebook against itself: identity, distance 0
+    sidx, sdiff, _ = dev_search(engine, cb, codes, 1, 2)
+    assert bool((sidx[:, 0] == torch.arange(M, device=dev, dtype=torch.int32)).all()) and float(sdiff.max()) == 0.0
+    cb.close()
+
+
+def test_c4_full_size_knn(engine, oracle):
+    dev = torch.device("cuda:0")
+    N, D, M, k = 1_000_000, 512, 4096, 5
+    codes = synth_rows_torch(2, 0, M, D, dev)
+    data = synth_rows_torch(3, 0, N, D, dev)
+    cb = engine.Codebook(codes.cpu().numpy())
+    idx, diff, nf = dev_search(engine, cb, data, k, 0)                      # AUTO: K2 streaming kernel
+    bd = engine.last_search_breakdown()
+    assert bd["k2_certified"] > 0.98 * N, bd
+    assert bool((nf == k).all())
+    # k-NN order (lvq_pak.c:197): distance ascending, ties by descending index; distinct codes
+    d0, d1 = diff[:, :-1], diff[:, 1:]
+    i0, i1 = idx[:, :-1], idx[:, 1:]
+    assert bool(((d0 < d1) | ((d0 == d1) & (i0 > i1))).all())
+    rows = torch.arange(0, N, 337, device=dev)[:3000]
+    sub = data[rows].contiguous()
+    eidx, ediff, _ = dev_search(engine, cb, sub, k, 1)                       # exact path
+    assert bool((eidx == idx[rows]).all()) and bool((ediff.view(torch.int32) == diff[rows].view(torch.int32)).all())
+    o = oracle.search(codes.cpu().numpy(), sub[:200].cpu().numpy(), k)
+    assert_bits_equal(idx[rows[:200]].cpu().numpy(), o[0])
+    assert_bits_equal(diff[rows[:200]].cpu().numpy(), o[1])
+    # k = 1 (accuracy / classify): first neighbour of the k-NN list unless a tie changes the rule
+    idx1, diff1, _ = dev_search(engine, cb, data, 1, 0)
+    assert bool((diff1[:, 0] == diff[:, 0]).all())
+    cb.close()
+
+
+def test_c5_schedule_prefix(engine, oracle):
+    """256x256 hexa gaussian map, 128-dim, the first steps of the rlen 1e6 schedule (fused K3 kernel)"""
+    N, D, xdim, ydim, length, steps = 100_000, 128, 256, 256, 1_000_000, 120
+    data = synth_numpy(4, 0, N * D).reshape(N, D)
+    codes = synth_numpy(5, 0, xdim * ydim * D).reshape(xdim * ydim, D)
+    order = engine.rand_order(N, 3)
+    s, ta, tr = engine.som_schedule(0, steps, length, 0.05, 100.0, engine.ALPHA_LINEAR, N, order)
+    t = engine.Trainer(codes, data)
+    t.set_som(xdim, ydim, engine.TOPOL_HEXA, engine.NEIGH_GAUSSIAN)
+    t.steps(s, ta, tr)
+    got = t.codes()
+    t.close()
+    exp = oracle.som_train_prefix(codes, data, xdim, ydim, 3, 2, length, steps, 0.05, 100.0, 1, order=order)
+    np.testing.assert_allclose(got, exp, rtol=1e-6, atol=0)
+    nbad = int((got.view(np.int32) != exp.view(np.int32)).sum())
+    assert nbad <= got.size // 1_000_000 + 4, "%d of %d floats differ" % (nbad, got.size)
