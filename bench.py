@@ -381,6 +381,10 @@ def main_gpu(args, w):
         }
         if world == 1 and not args.no_vsom:
             line["vsom"] = vsom_c5(bmu, args)
+        if world == 1 and not args.no_c4 and args.workload == "c3":
+            del data, idx, diff, nf, h_data, h_idx, h_diff, h_nf
+            torch.cuda.empty_cache()
+            line["c4"] = c4_extra(bmu, lib, _lib, dev, peaks)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rpc = args.ref_rows or max(64, int(10.0 * 1600 * (10_000 * 64) / (M * D)))
@@ -394,6 +398,49 @@ def main_gpu(args, w):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def c4_extra(bmu, lib, _lib, dev, peaks):
+    """BASELINE.json configs[3]: 1 M x 512-dim vs a 4096-unit codebook, k = 1 (accuracy / classify)
+    and k = 5 (knntest) -- the long-K streaming tcgen05 kernel.  Device-resident, CUDA events."""
+    import torch
+    rows, D, M = 1_000_000, 512, 4096
+    codes = synth_rows_torch(2, 0, M, D, dev)
+    data = synth_rows_torch(3, 0, rows, D, dev)
+    cb = lib.bmu_codebook_create_dev(codes.data_ptr(), M, D)
+    out = {"config": "synthetic high-dim: 1M x 512-dim vs 4096-unit codebook (BASELINE.json configs[3])"}
+    kms = (ctypes.c_float * 8)()
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    for k in (1, 5):
+        idx = torch.empty((rows, k), dtype=torch.int32, device=dev)
+        diff = torch.empty((rows, k), dtype=torch.float32, device=dev)
+        nf = torch.empty(rows, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            _lib.check(lib.bmu_search_dev(cb, data.data_ptr(), None, rows, k, idx.data_ptr(), diff.data_ptr(),
+                                          nf.data_ptr(), stream))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        steps = 5
+        for _ in range(steps):
+            _lib.check(lib.bmu_search_dev(cb, data.data_ptr(), None, rows, k, idx.data_ptr(), diff.data_ptr(),
+                                          nf.data_ptr(), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        lib.bmu_last_search_kernel_ms(kms)
+        bd = bmu.last_search_breakdown()
+        gemm_ms = float(kms[5])
+        out["k%d" % k] = {"value": rows / (ms * 1e-3), "unit": "searches/s", "ms_per_step": ms,
+                          "kernel_ms": {"k2_row_prep": float(kms[4]), "k2_gemm": gemm_ms, "k2_rerank": float(kms[6]),
+                                        "k2_lists": float(kms[7])},
+                          "gemm_tflops_algorithmic": 2.0 * M * D * rows / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                          "gemm_frac_of_sustained_peak": (2.0 * M * D * rows / (gemm_ms * 1e-3) / 1e12 / peak) if gemm_ms > 0 else None,
+                          "rows_certified": bd["k2_certified"], "rows_redone_exactly": bd["k2_failed"]}
+        del idx, diff, nf
+    lib.bmu_codebook_destroy(cb)
+    return out
 
 
 def vsom_c5(bmu, args):
@@ -459,6 +506,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=0, help="override CPU sample rows per core")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vsom", action="store_true", help="skip the vsom (configs[4]) extra metric")
+    ap.add_argument("--no-c4", action="store_true", help="skip the high-dim (configs[3]) extra metric")
     ap.add_argument("--vsom-steps", type=int, default=50000)
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "filter"],
                     help="search kernels: auto (default), exact = K1 only, filter = K2 forced")
