@@ -31,7 +31,6 @@ for it in range(4):
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
-print("rows %d M %d D %d k %d path %d dbg %s: %.3f ms  %.1f M searches/s" % (
-    rows, M, D, k, path, os.environ.get("BMU_K2_DEBUG", "0"), ms, rows / ms / 1e3))
+print("rows %d M %d D %d k %d path %d: %.3f ms  %.1f M searches/s" % (rows, M, D, k, path, ms, rows / ms / 1e3))
 print("  kernels:", {n: round(v, 3) for n, v in b.last_search_kernel_ms().items() if v})
 print("  breakdown:", b.last_search_breakdown())
