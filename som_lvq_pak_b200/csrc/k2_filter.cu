@@ -216,7 +216,7 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
   __shared__ float xs[K2_TM][K2_PS + 1];                      // inputs of the slab
   __shared__ unsigned char ms[K2_TM][K2_PS];                  // mask bytes of the slab
   __shared__ __align__(16) uint4 img_s[K2_PS / 8][K2_TM];     // image chunks of the slab
-  __shared__ double red[K2_TM][2];
+  __shared__ float red[K2_TM][2];
   __shared__ int redi[K2_TM][2];
   const int Dp = k2_dp(D), Kp = k2_kp(D);
   const long tile = blockIdx.x;
@@ -226,10 +226,52 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
   uint4 *img = reinterpret_cast<uint4 *>(Aimg + tile * (long)K2_TM * Kp);   // [kc][128] uint4
   const long nrow = n0 + row;
   const float sc = cst->scale;
-  double n2 = 0.0, nr2 = 0.0;
+  // ||x'||^2 and the squared fp16 residual, accumulated in FP32: the relative error (D+4) 2^-24 of
+  // these sums is charged to the bounds below, which is far cheaper than accumulating in double
+  float n2 = 0.0f, nr2 = 0.0f;
   unsigned f = 0;
   int nmasked = 0;
+  __shared__ float mean_s[K2_PS];
+  const bool fast = mask == nullptr && n0 + K2_TM <= N && (D % K2_PS) == 0;   // full tile: no per-element checks
 
+  if (fast) {
+    for (int d0 = 0; d0 < D; d0 += K2_PS) {
+      __syncthreads();
+      if (tid < K2_PS) mean_s[tid] = mean[d0 + tid];
+      // phase 1: coalesced load of 128 rows x 32 components
+#pragma unroll 4
+      for (int r = warp; r < K2_TM; r += 8) xs[r][lane] = data[(n0 + r) * (long)D + d0 + lane];
+      __syncthreads();
+      // phase 2: centre, scale, round; each thread packs 2 x 8 components of one row
+#pragma unroll
+      for (int grp = 0; grp < 2; grp++) {
+        uint32_t hw[4];
+#pragma unroll
+        for (int pq = 0; pq < 8; pq += 2) {
+          float hv[2];
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int il = half * 16 + grp * 8 + pq + q;
+            const float v = xs[row][il];
+            f |= k2_classify(v);
+            const float c = __fmul_rn(__fsub_rn(v, mean_s[il]), sc);
+            const float h = __half2float(__float2half_rn(c));
+            const float res = __fsub_rn(c, h);
+            hv[q] = h;
+            n2 = __fadd_rn(n2, __fmul_rn(c, c));
+            nr2 = __fadd_rn(nr2, __fmul_rn(res, res));
+          }
+          if (!(fabsf(hv[0]) < INFINITY) || !(fabsf(hv[1]) < INFINITY)) f |= ROW_RANGE;
+          hw[pq >> 1] = half2_bits(hv[0], hv[1]);
+        }
+        img_s[half * 2 + grp][row] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      }
+      __syncthreads();
+      // phase 3: (4 chunks x 128) uint4 form one contiguous run of the image
+      for (int t = tid; t < (K2_PS / 8) * K2_TM; t += 256)
+        img[((long)d0 / 8 + t / K2_TM) * K2_TM + (t % K2_TM)] = img_s[t / K2_TM][t % K2_TM];
+    }
+  } else
   for (int d0 = 0; d0 < Dp; d0 += K2_PS) {
     __syncthreads();
     // phase 1: coalesced load of 128 rows x 32 components
@@ -268,8 +310,8 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
               if (!(fabsf(h) < INFINITY)) f |= ROW_RANGE;
               const float res = __fsub_rn(c, h);
               hv[q] = h;
-              n2 += (double)c * c;
-              nr2 += (double)res * res;
+              n2 = __fadd_rn(n2, __fmul_rn(c, c));
+              nr2 = __fadd_rn(nr2, __fmul_rn(res, res));
             }
           }
         }
@@ -306,7 +348,8 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
     // ---- error bound of the tensor-core score for this row (double; scaled units)
     const CbStats cs = *cst;
     const double up = 1.0001;
-    const double nx = sqrt(n2) * up, nrx = sqrt(nr2) * up;
+    const double facc = (double)(D + 4) * ldexp(1.0, -23);               // FP32 accumulation of n2 / nr2 (x2 margin)
+    const double nx = sqrt((double)n2 * (1.0 + facc)) * up, nrx = sqrt((double)nr2 * (1.0 + facc)) * up;
     const double NM = cs.nm, nrm = cs.nrm, nm2 = cs.nm2;
     const double nxh = nx + nrx, NMh = NM + nrm;
     const double amag = 2.0 * nxh * NMh + nm2;                         // bound on |partial sums|, |score|
@@ -319,9 +362,11 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
     const double dmax = (nx + NM) * (nx + NM);
     const double eta = ldexp(nx + NM, -23);
     const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01 + 1e-6;
-    const double slack = 4.0 * (2.0 * eta * (nx + NM) + gamma * dmax);
+    // nx2 enters the certificate as a LOWER bound of ||x'||^2; what that gives away goes into the window
+    const double nx2_lo = (double)n2 * (1.0 - facc);
+    const double slack = 4.0 * (2.0 * eta * (nx + NM) + gamma * dmax) + 2.0 * facc * (double)n2;
     RowStats s;
-    s.nx2 = n2;
+    s.nx2 = nx2_lo;
     s.nx = (float)nx * 1.0001f;
     s.E = (float)E * 1.0001f;
     s.delta = (float)(2.02 * E + slack) * 1.0001f;
