@@ -1,6 +1,6 @@
 /* main.c -- multi-call front end of the B200 host programs: `bmu_pak <program> <options>` or a
- * link named after the program (vsom, qerror, visual, vcal, accuracy, classify, knntest, lvq1,
- * olvq1, lvq2, lvq3), as the reference installs one binary per program (reference Makefile). */
+ * link named after the program (vsom, qerror, visual, vcal, accuracy, classify, knntest, cmatr,
+ * setlabel, elimin, lvq1, olvq1, lvq2, lvq3), as the reference installs one binary per program (reference Makefile). */
 #include <stdio.h>
 #include <string.h>
 
@@ -14,6 +14,9 @@ static int dispatch(const char *prog, int argc, char **argv) {
   if (strcmp(prog, "accuracy") == 0) return accuracy_main(argc, argv);
   if (strcmp(prog, "classify") == 0) return classify_main(argc, argv);
   if (strcmp(prog, "knntest") == 0) return knntest_main(argc, argv);
+  if (strcmp(prog, "cmatr") == 0) return cmatr_main(argc, argv);
+  if (strcmp(prog, "setlabel") == 0) return setlabel_main(argc, argv);
+  if (strcmp(prog, "elimin") == 0) return elimin_main(argc, argv);
   if (strcmp(prog, "pakcat") == 0) return pakcat_main(argc, argv);
   if (strcmp(prog, "lvq1") == 0 || strcmp(prog, "lvq2") == 0 || strcmp(prog, "lvq3") == 0 ||
       strcmp(prog, "olvq1") == 0 || strcmp(prog, "lvqtrain") == 0)
@@ -28,7 +31,7 @@ int main(int argc, char **argv) {
   rc = dispatch(base, argc, argv);
   if (rc == -2 && argc > 1) rc = dispatch(argv[1], argc - 1, argv + 1);
   if (rc == -2) {
-    fprintf(stderr, "usage: bmu_pak <vsom|qerror|visual|vcal|accuracy|classify|knntest|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n");
+    fprintf(stderr, "usage: bmu_pak <vsom|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n");
     return 2;
   }
   return rc;

@@ -8,6 +8,9 @@
  *   compute_accuracy            accuracy.c:39-137     bmu_search, hitlists replayed in data order
  *   compute_classifications     classify.c:41-95      bmu_search
  *   compute_knnaccuracy         knntest.c:41-157      bmu_search (k), majority vote = head of the hitlist
+ *   compute_cmatr               cmatr.c:41-171        bmu_search, confusion counts replayed in data order
+ *   find_labels (setlabel)      setlabel.c:41-96      bmu_search (k) with the data set as the searched set
+ *   eliminate_codes             elimin.c:42-126       bmu_search (k) of the data set against itself
  *   som_training                som_rout.c:556-671    bmu_som_schedule + bmu_som_train
  *   lvq1/olvq1/lvq2/lvq3        lvq_rout.c:498-916    bmu_lvq_schedule + bmu_lvq_train
  *
@@ -53,6 +56,8 @@ static void global_options(int argc, char **argv) {                     /* lvq_p
   if (opt(argc, argv, "-buffer") || opt(argc, argv, "-selfuncs") || opt(argc, argv, "-snapinterval"))
     fprintf(stderr, "note: -buffer, -selfuncs and snapshots are not supported by the B200 host; ignored\n");
 }
+
+static void lra_name(const char *codefile, char *out, size_t outsz);
 
 static int engine_failed(const char *what) {
   fprintf(stderr, "%s: %s\n", what, bmu_last_error());
@@ -310,6 +315,157 @@ int knntest_main(int argc, char **argv) {
   winners_free(&w);
   pak_free(data);
   pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ cmatr */
+int cmatr_main(int argc, char **argv) {                              /* cmatr.c:41-171 */
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  struct pak_hitlist correct, totals, confusion;
+  const char *cfout;
+  FILE *ocf = NULL;
+  long i, j, total = 0, stotal = 0;
+  global_options(argc, argv);
+  cfout = opt(argc, argv, "-cfout");
+  if (open_pair(argc, argv, 1, 1, 1, 0, &data, &codes)) return 1;
+  if (cfout && !(ocf = fopen(cfout, "w"))) { fprintf(stderr, "Cannot open '%s' for output\n", cfout); return 1; }
+  if (find_winners(codes, data, 1, &w)) return 1;
+  hit_init(&correct); hit_init(&totals); hit_init(&confusion);
+  for (i = 0; i < data->n; i++) {
+    const int datalabel = pak_label(data, i);
+    int label;
+    if (w.nfound[i] == 0) continue;                                  /* invalid data vector */
+    label = pak_label(codes, w.idx[i]);
+    if (label == datalabel) {
+      stotal++;
+      hit_add(&correct, datalabel);
+      if (ocf) fprintf(ocf, "1\n");
+    } else if (ocf) {
+      fprintf(ocf, "0\n");
+    }
+    hit_add(&confusion, (long)datalabel * 65536 + label);
+    hit_add(&totals, datalabel);
+    total++;
+  }
+  print_accuracy(&totals, &correct, total, stotal, 0);
+  fprintf(stdout, "Confusion matrix:\n\n");
+  fprintf(stdout, "          ");
+  for (i = 0; i < totals.n; i++) fprintf(stdout, " %4s", label_string((int)totals.label[i]));
+  fprintf(stdout, "\n\n");
+  for (i = 0; i < totals.n; i++) {
+    fprintf(stdout, "%9s: ", label_string((int)totals.label[i]));
+    for (j = 0; j < totals.n; j++)
+      fprintf(stdout, "%4ld ", hit_freq(&confusion, totals.label[i] * 65536 + totals.label[j]));
+    fprintf(stdout, "\n");
+  }
+  fprintf(stdout, "\n");
+  if (ocf) fclose(ocf);
+  hit_free(&correct); hit_free(&totals); hit_free(&confusion);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ setlabel */
+/* labels every codebook vector by the majority among its knn nearest DATA vectors
+ * (setlabel.c:41-96): the roles are swapped, the data set is the searched "codebook" */
+int setlabel_main(int argc, char **argv) {
+  struct pak_entries *data = NULL, *codes = NULL;
+  struct winners w;
+  struct pak_hitlist hits;
+  const char *s, *cout_name;
+  int knn, t, *nlab, *labs;
+  long i, pos = 0;
+  global_options(argc, argv);
+  cout_name = need(argc, argv, "-cout");
+  s = opt(argc, argv, "-knn");
+  knn = s ? atoi(s) : 5;
+  if (knn < 1) knn = 1;
+  if (knn > BMU_KMAX) { fprintf(stderr, "-knn %d is larger than the engine's limit %d\n", knn, BMU_KMAX); return 1; }
+  if (open_pair(argc, argv, 1, 0, 1, 0, &data, &codes)) return 1;
+  if (find_winners(data, codes, knn, &w)) return 1;                  /* queries = code vectors */
+  nlab = (int *)malloc(sizeof(int) * (size_t)(codes->n > 0 ? codes->n : 1));
+  labs = (int *)malloc(sizeof(int) * (size_t)(codes->n > 0 ? codes->n : 1));
+  if (!nlab || !labs) return 1;
+  hit_init(&hits);
+  for (i = 0; i < codes->n; i++) {
+    hit_clear(&hits);
+    for (t = 0; t < knn; t++) {
+      const int j = w.idx[i * knn + t];
+      if (j >= 0) hit_add(&hits, pak_label(data, j));
+    }
+    nlab[i] = (hits.n > 0 && hits.label[0] != LABEL_EMPTY) ? 1 : 0;   /* set_entry_label, labels.c:146-155 */
+    if (nlab[i]) labs[pos++] = (int)hits.label[0];
+  }
+  if (pak_set_labels(codes, nlab, labs)) return 1;
+  pak_save(codes, cout_name);
+  hit_free(&hits);
+  free(nlab); free(labs);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ elimin */
+/* keeps the entries whose knn nearest neighbours in the SAME set (itself included) are mostly of
+ * its own class (elimin.c:42-126) */
+int elimin_main(int argc, char **argv) {
+  struct pak_entries *data, *out;
+  struct winners w;
+  const char *s, *din, *cout_name;
+  int knn, t;
+  long i, kept = 0, nl = 0;
+  char lra[2048];
+  global_options(argc, argv);
+  din = need(argc, argv, "-din");
+  cout_name = need(argc, argv, "-cout");
+  s = opt(argc, argv, "-knn");
+  knn = s ? atoi(s) : 5;
+  if (knn > 10) { fprintf(stderr, "Can use only %d neighbors", 10); knn = 10; }   /* elimin.c:51-54 */
+  if (knn < 1) knn = 1;
+  data = pak_load(din, 1, 1);
+  if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+  if (find_winners(data, data, knn, &w)) return 1;
+  out = pak_alloc(data->dim, data->n);
+  if (!out) return 1;
+  out->topol = data->topol; out->neigh = data->neigh; out->xdim = data->xdim; out->ydim = data->ydim;
+  if (data->mask) out->mask = (unsigned char *)calloc((size_t)data->n * data->dim, 1);
+  out->lab_pool = (int *)malloc(sizeof(int) * (size_t)(data->lab_off[data->n] > 0 ? data->lab_off[data->n] : 1));
+  if (!out->lab_pool || (data->mask && !out->mask)) return 1;
+  for (i = 0; i < data->n; i++) {
+    long correct = 0, incorrect = 0, l;
+    const int datalabel = pak_label(data, i);
+    if (w.nfound[i] != knn) continue;                                /* did not find winners */
+    for (t = 0; t < knn; t++) {
+      const int j = w.idx[i * knn + t];
+      if (j >= 0 && pak_label(data, j) == datalabel) correct++;
+      else incorrect++;
+    }
+    if (correct <= incorrect) continue;
+    memcpy(out->points + (size_t)kept * data->dim, data->points + (size_t)i * data->dim, sizeof(float) * data->dim);
+    if (data->mask) memcpy(out->mask + (size_t)kept * data->dim, data->mask + (size_t)i * data->dim, (size_t)data->dim);
+    for (l = data->lab_off[i]; l < data->lab_off[i + 1]; l++) out->lab_pool[nl++] = data->lab_pool[l];
+    kept++;
+    out->lab_off[kept] = nl;
+  }
+  out->n = kept;
+  pak_save(out, cout_name);
+  lra_name(cout_name, lra, sizeof lra);                              /* elimin.c:209 invalidate_alphafile */
+  {
+    FILE *fp = fopen(lra, "r");
+    if (fp) {
+      if (verbose_level >= 1) fprintf(stdout, "Removing the learning rate file %s\n", lra);
+      fclose(fp);
+      if (remove(lra)) fprintf(stderr, "Can not remove %s", lra);
+    }
+  }
+  winners_free(&w);
+  pak_free(data);
+  pak_free(out);
   return 0;
 }
 

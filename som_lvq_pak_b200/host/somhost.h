@@ -73,6 +73,9 @@ int vcal_main(int argc, char **argv);
 int accuracy_main(int argc, char **argv);
 int classify_main(int argc, char **argv);
 int knntest_main(int argc, char **argv);
+int cmatr_main(int argc, char **argv);
+int setlabel_main(int argc, char **argv);
+int elimin_main(int argc, char **argv);
 int lvqtrain_main(int argc, char **argv, const char *progname);
 int pakcat_main(int argc, char **argv);   /* load + save: exercises the file layer alone */
 

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Golden outputs of three more programs whose loops sit on the BMU path -- cmatr, setlabel, elimin
+ -- produced by the UNMODIFIED reference binaries in oracle/_ref/bin from the inputs
+already stored in demo.npz.  Run in the build container (needs /root/reference for `make -C oracle ref`):
+    python tests/golden/make_golden_extra.py        ->  tests/golden/demo_extra.npz"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+
+def run(cmd, cwd):
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if p.returncode:
+        raise RuntimeError("%s failed: %s" % (cmd, p.stderr))
+    return p.stdout
+
+
+def main():
+    if not os.path.isdir(REF_BIN):
+        sys.exit("build the reference first: make -C oracle ref (needs /root/reference)")
+    demo = np.load(os.path.join(HERE, "demo.npz"))
+    td = tempfile.mkdtemp()
+    for f in ("ex1.dat", "ex2.dat"):
+        open(os.path.join(td, f), "w").write(str(demo["in_" + f]))
+    open(os.path.join(td, "ex1l.cod"), "w").write(str(demo["lvq_l_cod"]))
+    b = lambda p: os.path.join(REF_BIN, p)  # noqa: E731
+    out = {}
+    out["cmatr_stdout"] = np.array(run([b("cmatr"), "-din", "ex2.dat", "-cin", "ex1l.cod", "-cfout", "cm.cf"], td))
+    out["cmatr_cfout"] = np.array(open(os.path.join(td, "cm.cf")).read())
+    run([b("setlabel"), "-din", "ex1.dat", "-cin", "ex1l.cod", "-cout", "sl.cod", "-knn", "5"], td)
+    out["setlabel_cod"] = np.array(open(os.path.join(td, "sl.cod")).read())
+    run([b("setlabel"), "-din", "ex2.dat", "-cin", "ex1l.cod", "-cout", "sl3.cod", "-knn", "3"], td)
+    out["setlabel3_cod"] = np.array(open(os.path.join(td, "sl3.cod")).read())
+    run([b("elimin"), "-din", "ex1.dat", "-cout", "el.cod", "-knn", "5"], td)
+    out["elimin_cod"] = np.array(open(os.path.join(td, "el.cod")).read())
+    run([b("elimin"), "-din", "ex2.dat", "-cout", "el10.cod", "-knn", "10"], td)
+    out["elimin10_cod"] = np.array(open(os.path.join(td, "el10.cod")).read())
+    shutil.rmtree(td)
+    np.savez_compressed(os.path.join(HERE, "demo_extra.npz"), **out)
+    print({k: len(str(v)) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
