@@ -5,8 +5,10 @@
  */
 #include "somhost.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 /* ------------------------------------------------------------------ label table */
 static char **g_labels = NULL;
@@ -86,25 +88,6 @@ static int name_id(const char **names, int count, const char *s) {
   return 0;
 }
 
-/* whole line without the newline, any length (fileio.c:283-375); NULL at end of file */
-static char *read_line(FILE *fp, char **buf, size_t *cap) {
-  size_t len = 0;
-  int c;
-  if (!*buf) { *cap = 4096; *buf = (char *)malloc(*cap); if (!*buf) return NULL; }
-  while ((c = fgetc(fp)) != EOF && c != '\n') {
-    if (len + 2 > *cap) {
-      char *t = (char *)realloc(*buf, *cap * 2);
-      if (!t) return NULL;
-      *buf = t;
-      *cap *= 2;
-    }
-    (*buf)[len++] = (char)c;
-  }
-  (*buf)[len] = '\0';
-  if (c == EOF && len == 0) return NULL;
-  return *buf;
-}
-
 /* the n-th token (0-based) of the header line, split at blanks only (datafile.c:947-1023) */
 static char *header_token(const char *line, int n, char *out, size_t outsz) {
   char *dup = strdup(line), *tok;
@@ -118,141 +101,341 @@ static char *header_token(const char *line, int n, char *out, size_t outsz) {
   return out[0] ? out : NULL;
 }
 
-struct grow {       /* growing arrays while the number of entries is unknown */
-  long cap, labcap, nlab;
+/* Decimal -> float.  scanf's %f is strtof, and glibc's strtof costs ~180 ns per value; almost every
+ * token of a .dat file is a short decimal, for which the correctly rounded result is reachable
+ * with one exact double operation (Clinger's fast path).  Towards float this needs one more
+ * guard: mantissa < 2^53 and |exp10| <= 22 make mant * 10^e exact (checked against a table) or
+ * mant / 10^e correct to half a double ulp; the second rounding double -> float is then the
+ * correct rounding of the decimal unless the double lies within an ulp of a float rounding
+ * midpoint (or is subnormal for float), and those tokens -- like anything unusual (inf, nan,
+ * hex, > 18 digits) -- go to strtof.  tests/test_host_files.py compares against libc's strtof. */
+static const double k_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+static float pak_strtof(const char *s, char **end) {
+  const char *p = s;
+  unsigned long long mant = 0;
+  int neg = 0, nd = 0, dp = 0, seen = 0, e10 = 0;
+  double q;
+  unsigned long long bits, r;
+  if (*p == '-') { neg = 1; p++; } else if (*p == '+') p++;
+  if (p[0] == '0' && (p[1] == 'x' || p[1] == 'X')) goto slow;       /* hexadecimal floats */
+  while (*p >= '0' && *p <= '9') { if (nd < 19) { mant = mant * 10 + (unsigned)(*p - '0'); if (mant) nd++; } else goto slow; seen = 1; p++; }
+  if (*p == '.') {
+    p++;
+    while (*p >= '0' && *p <= '9') { if (nd < 19) { mant = mant * 10 + (unsigned)(*p - '0'); if (mant) nd++; dp++; } else goto slow; seen = 1; p++; }
+  }
+  if (!seen) goto slow;
+  if (*p == 'e' || *p == 'E') {
+    const char *pe = p + 1;
+    int eneg = 0, ev = 0, ed = 0;
+    if (*pe == '-') { eneg = 1; pe++; } else if (*pe == '+') pe++;
+    while (*pe >= '0' && *pe <= '9') { if (ev < 10000) ev = ev * 10 + (*pe - '0'); ed = 1; pe++; }
+    if (ed) { e10 = eneg ? -ev : ev; p = pe; }
+  }
+  e10 -= dp;
+  if (mant == 0) { *end = (char *)p; return neg ? -0.0f : 0.0f; }
+  if (mant >= (1ull << 53) || e10 > 22 || e10 < -22) goto slow;
+  if (e10 >= 0) {
+    q = (double)mant * k_pow10[e10];
+    if (q >= 9007199254740992.0) goto slow;              /* product not exactly representable */
+  } else {
+    q = (double)mant / k_pow10[-e10];
+  }
+  if (q < 1.1754943508222875e-38 || q > 3.4028234e38) goto slow;      /* float subnormal / overflow range */
+  memcpy(&bits, &q, sizeof bits);
+  r = bits & ((1ull << 29) - 1);
+  if (r >= (1ull << 28) - 2 && r <= (1ull << 28) + 2) goto slow;        /* next to a float rounding midpoint */
+  *end = (char *)p;
+  return neg ? -(float)q : (float)q;
+slow:
+  return strtof(s, end);
+}
+
+/* ---- loader.  The reference parses one line at a time with sscanf("%f") (datafile.c:552-748),
+ * which at the 10 M-row scale of the batch search costs minutes while the search itself takes
+ * milliseconds.  Here the file is read into memory once, cut at line
+ * boundaries into blocks, and the blocks are parsed in parallel (pthreads; strtof converts
+ * exactly like scanf's %f); the blocks are then stitched together in file order, and labels
+ * are interned in file order so that the label table does not depend on the thread count. */
+struct blk {
+  char *beg, *end;                  /* [beg, end): whole lines */
+  int dim, labels_needed, skip_empty;
+  const char *mask_str, *name;
+  long n, cap, nlab, labcap, lines;
+  float *points;
+  unsigned char *mask;              /* NULL until the block sees a masked component */
+  long *lab_off;                    /* cap + 1 */
+  char **labs;                      /* label tokens (pointers into the buffer) */
+  short *weight, *fixed_xy;
+  int err;                          /* 0 ok, 1 unreadable component, 2 out of memory, 3 bad fixed=, 4 label missing */
+  int err_comp;
+  long err_line;                    /* line inside the block */
 };
 
-static int grow_entries(struct pak_entries *e, struct grow *g, int have_mask) {
-  long ncap = g->cap ? g->cap * 2 : 1024;
-  float *p = (float *)realloc(e->points, sizeof(float) * (size_t)ncap * e->dim);
-  long *lo;
-  short *w, *f;
-  if (!p) return 1;
-  e->points = p;
-  if (have_mask) {
-    unsigned char *m = (unsigned char *)realloc(e->mask, (size_t)ncap * e->dim);
+static int blk_grow(struct blk *b) {
+  const long ncap = b->cap ? b->cap * 2 : 1024;
+  float *p = (float *)realloc(b->points, sizeof(float) * (size_t)ncap * b->dim);
+  long *lo = (long *)realloc(b->lab_off, sizeof(long) * (size_t)(ncap + 1));
+  short *w = (short *)realloc(b->weight, sizeof(short) * (size_t)ncap);
+  short *f = (short *)realloc(b->fixed_xy, sizeof(short) * 2 * (size_t)ncap);
+  if (p) b->points = p;
+  if (lo) b->lab_off = lo;
+  if (w) b->weight = w;
+  if (f) b->fixed_xy = f;
+  if (!p || !lo || !w || !f) return 1;
+  if (b->mask) {
+    unsigned char *m = (unsigned char *)realloc(b->mask, (size_t)ncap * b->dim);
     if (!m) return 1;
-    memset(m + (size_t)g->cap * e->dim, 0, (size_t)(ncap - g->cap) * e->dim);
-    e->mask = m;
+    memset(m + (size_t)b->cap * b->dim, 0, (size_t)(ncap - b->cap) * b->dim);
+    b->mask = m;
   }
-  lo = (long *)realloc(e->lab_off, sizeof(long) * (size_t)(ncap + 1));
-  w = (short *)realloc(e->weight, sizeof(short) * (size_t)ncap);
-  f = (short *)realloc(e->fixed_xy, sizeof(short) * 2 * (size_t)ncap);
-  if (lo) e->lab_off = lo;
-  if (w) e->weight = w;
-  if (f) e->fixed_xy = f;
-  if (!lo || !w || !f) return 1;
-  g->cap = ncap;
+  if (b->cap == 0) b->lab_off[0] = 0;
+  b->cap = ncap;
   return 0;
 }
 
-struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
-  FILE *fp = strcmp(name, "-") == 0 ? stdin : fopen(name, "r");
-  char *buf = NULL, *line, tokbuf[64];
-  size_t cap = 0;
-  long row = 0;
-  struct pak_entries *e = NULL;
-  struct grow g = {0, 0, 0};
-  int dim;
-  if (!fp) return NULL;
-  /* header: first line that is not a comment (datafile.c:112-148) */
-  do {
-    line = read_line(fp, &buf, &cap);
-    row++;
-    if (!line) { fprintf(stderr, "Can't read file %s", name); goto fail; }
-  } while (line[0] == '#');
-  if (sscanf(line, "%d", &dim) <= 0 || dim <= 0) {
-    fprintf(stderr, "Can't read dimension parameter in file %s", name);
-    goto fail;
+static void *blk_parse(void *arg) {
+  struct blk *b = (struct blk *)arg;
+  char *line = b->beg;
+  const int dim = b->dim;
+  {                                           /* one allocation per array: entries <= lines */
+    long nlines = 1;
+    const char *q = b->beg;
+    while (q < b->end && (q = (const char *)memchr(q, '\n', (size_t)(b->end - q))) != NULL) { nlines++; q++; }
+    b->cap = 0;
+    while (b->cap < nlines) {
+      const long want = nlines;
+      b->points = (float *)malloc(sizeof(float) * (size_t)want * dim);
+      b->lab_off = (long *)malloc(sizeof(long) * (size_t)(want + 1));
+      b->weight = (short *)malloc(sizeof(short) * (size_t)want);
+      b->fixed_xy = (short *)malloc(sizeof(short) * 2 * (size_t)want);
+      if (!b->points || !b->lab_off || !b->weight || !b->fixed_xy) { b->err = 2; return NULL; }
+      b->lab_off[0] = 0;
+      b->cap = want;
+    }
   }
-  e = (struct pak_entries *)calloc(1, sizeof(*e));
-  if (!e) goto fail;
-  e->dim = dim;
-  e->topol = name_id(topol_names, 5, header_token(line, 1, tokbuf, sizeof tokbuf));
-  e->xdim = header_token(line, 2, tokbuf, sizeof tokbuf) ? atoi(tokbuf) : 0;
-  e->ydim = header_token(line, 3, tokbuf, sizeof tokbuf) ? atoi(tokbuf) : 0;
-  e->neigh = name_id(neigh_names, 3, header_token(line, 4, tokbuf, sizeof tokbuf));
-  e->lab_off = (long *)calloc(1, sizeof(long));
-  if (!e->lab_off) goto fail;
-
-  /* entries (datafile.c:552-748) */
-  while ((line = read_line(fp, &buf, &cap)) != NULL) {
-    char *tok;
+  while (line < b->end) {
+    char *nl = (char *)memchr(line, '\n', (size_t)(b->end - line));
+    char *next = nl ? nl + 1 : b->end, *save = NULL, *tok;
     int i, maskcnt = 0, label_found = 0;
     float *pt;
     unsigned char *mk;
-    long first_lab;
-    row++;
-    if (line[0] == '#') continue;
-    tok = strtok(line, " \r\t");
-    if (!tok) continue;                                           /* empty line */
-    if (e->n == g.cap && grow_entries(e, &g, e->mask != NULL)) goto fail;
-    pt = e->points + (size_t)e->n * dim;
-    mk = e->mask ? e->mask + (size_t)e->n * dim : NULL;
+    if (nl) *nl = '\0';                       /* the caller guarantees a terminator after the last line */
+    b->lines++;
+    if (line[0] == '#') { line = next; continue; }
+    tok = strtok_r(line, " \r\t", &save);
+    if (!tok) { line = next; continue; }      /* empty line */
+    if (b->n == b->cap && blk_grow(b)) { b->err = 2; return NULL; }
+    pt = b->points + (size_t)b->n * dim;
+    mk = b->mask ? b->mask + (size_t)b->n * dim : NULL;
     if (mk) memset(mk, 0, (size_t)dim);
     for (i = 0; i < dim; i++) {
-      if (i > 0) tok = strtok(NULL, " \r\t");
-      if (!tok) {
-        fprintf(stderr, "load_entry: can't read entry in file %s on line %ld, component %d\n", name, row, i);
-        goto fail;
-      }
-      if (strcmp(tok, pak_mask_string) == 0) {
-        if (!e->mask) {                                           /* first masked component of the file */
-          e->mask = (unsigned char *)calloc((size_t)g.cap * dim, 1);
-          if (!e->mask) goto fail;
-          mk = e->mask + (size_t)e->n * dim;
+      if (i > 0) tok = strtok_r(NULL, " \r\t", &save);
+      if (tok && strcmp(tok, b->mask_str) == 0) {
+        if (!b->mask) {                       /* first masked component of the block */
+          b->mask = (unsigned char *)calloc((size_t)b->cap * dim, 1);
+          if (!b->mask) { b->err = 2; return NULL; }
+          mk = b->mask + (size_t)b->n * dim;
         }
         mk[i] = 1;
         maskcnt++;
         pt[i] = 0.0f;
-      } else if (sscanf(tok, "%f", &pt[i]) <= 0) {
-        fprintf(stderr, "load_entry: can't read entry in file %s on line %ld, component %d\n", name, row, i);
-        goto fail;
+      } else {
+        char *endp = NULL;
+        if (tok) pt[i] = pak_strtof(tok, &endp);  /* same value as sscanf("%f"), prefix match included */
+        if (!tok || endp == tok) {
+          b->err = 1;
+          b->err_comp = i;
+          b->err_line = b->lines;
+          return NULL;
+        }
       }
     }
-    if (maskcnt == dim && skip_empty) continue;                    /* datafile.c:677-690 */
-    e->weight[e->n] = 0;
-    e->fixed_xy[2 * e->n] = e->fixed_xy[2 * e->n + 1] = -1;
-    first_lab = g.nlab;
-    while ((tok = strtok(NULL, " \r\t")) != NULL) {
+    if (maskcnt == dim && b->skip_empty) { line = next; continue; }      /* datafile.c:677-690 */
+    b->weight[b->n] = 0;
+    b->fixed_xy[2 * b->n] = b->fixed_xy[2 * b->n + 1] = -1;
+    while ((tok = strtok_r(NULL, " \r\t", &save)) != NULL) {
       if (strncmp(tok, "weight=", 7) == 0) {
-        e->weight[e->n] = (short)atoi(tok + 7);
+        b->weight[b->n] = (short)atoi(tok + 7);
       } else if (strncmp(tok, "fixed=", 6) == 0) {
         const char *comma = strchr(tok, ',');
-        if (!comma) { fprintf(stderr, "bad fixed point, line %ld of file %s\n", row, name); goto fail; }
-        e->fixed_xy[2 * e->n] = (short)atoi(tok + 6);
-        e->fixed_xy[2 * e->n + 1] = (short)atoi(comma + 1);
-      } else {
-        int lab = label_index(tok);
-        if (lab == LABEL_EMPTY) continue;
-        if (g.nlab == g.labcap) {
-          long ncap = g.labcap ? g.labcap * 2 : 1024;
-          int *t = (int *)realloc(e->lab_pool, sizeof(int) * (size_t)ncap);
-          if (!t) goto fail;
-          e->lab_pool = t;
-          g.labcap = ncap;
+        if (!comma) {
+          b->err = 3;
+          b->err_line = b->lines;
+          return NULL;
         }
-        e->lab_pool[g.nlab++] = lab;
+        b->fixed_xy[2 * b->n] = (short)atoi(tok + 6);
+        b->fixed_xy[2 * b->n + 1] = (short)atoi(comma + 1);
+      } else {
+        if (b->nlab == b->labcap) {
+          const long ncap = b->labcap ? b->labcap * 2 : 1024;
+          char **t = (char **)realloc(b->labs, sizeof(char *) * (size_t)ncap);
+          if (!t) { b->err = 2; return NULL; }
+          b->labs = t;
+          b->labcap = ncap;
+        }
+        b->labs[b->nlab++] = tok;
         label_found++;
       }
     }
-    (void)first_lab;
-    if (labels_needed && !label_found) {
-      fprintf(stderr, "Required label missing on line %ld of file %s\n", row, name);
-      goto fail;
+    if (b->labels_needed && !label_found) {
+      b->err = 4;
+      b->err_line = b->lines;
+      return NULL;
     }
-    e->n++;
-    e->lab_off[e->n] = g.nlab;
+    b->n++;
+    b->lab_off[b->n] = b->nlab;
+    line = next;
   }
-  if (e->n == 0 && !e->points) {               /* keep the invariants of pak_alloc for empty files */
-    if (grow_entries(e, &g, 0)) goto fail;
+  return NULL;
+}
+
+static void blk_release(struct blk *b) {
+  free(b->points); free(b->mask); free(b->lab_off); free(b->labs); free(b->weight); free(b->fixed_xy);
+}
+
+/* whole file (or stdin) into one buffer with a terminating NUL */
+static char *slurp(FILE *fp, size_t *len) {
+  size_t cap = 1 << 20, n = 0, got;
+  char *buf = (char *)malloc(cap + 1);
+  if (!buf) return NULL;
+  while ((got = fread(buf + n, 1, cap - n, fp)) > 0) {
+    n += got;
+    if (n == cap) {
+      char *t = (char *)realloc(buf, cap * 2 + 1);
+      if (!t) { free(buf); return NULL; }
+      buf = t;
+      cap *= 2;
+    }
   }
-  free(buf);
+  buf[n] = '\0';
+  *len = n;
+  return buf;
+}
+
+struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
+  FILE *fp = strcmp(name, "-") == 0 ? stdin : fopen(name, "r");
+  char *buf, *p, *endbuf, tokbuf[64];
+  size_t len = 0;
+  long header_lines = 0, total = 0, totlab = 0, i;
+  struct pak_entries *e = NULL;
+  struct blk *blks = NULL;
+  pthread_t *tids = NULL;
+  int dim, nthreads, nb = 0, t, any_mask = 0, failed = 0;
+  const char *env = getenv("BMU_PAK_THREADS");
+  if (!fp) return NULL;
+  buf = slurp(fp, &len);
   if (fp != stdin) fclose(fp);
+  if (!buf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
+  endbuf = buf + len;
+  /* header: first line that is not a comment (datafile.c:112-148) */
+  p = buf;
+  for (;;) {
+    char *nl;
+    if (p >= endbuf) { fprintf(stderr, "Can't read file %s", name); free(buf); return NULL; }
+    nl = (char *)memchr(p, '\n', (size_t)(endbuf - p));
+    if (nl) *nl = '\0';
+    header_lines++;
+    if (p[0] != '#') {
+      char *line = p;
+      p = nl ? nl + 1 : endbuf;
+      if (sscanf(line, "%d", &dim) <= 0 || dim <= 0) {
+        fprintf(stderr, "Can't read dimension parameter in file %s", name);
+        free(buf);
+        return NULL;
+      }
+      e = (struct pak_entries *)calloc(1, sizeof(*e));
+      if (!e) { free(buf); return NULL; }
+      e->dim = dim;
+      e->topol = name_id(topol_names, 5, header_token(line, 1, tokbuf, sizeof tokbuf));
+      e->xdim = header_token(line, 2, tokbuf, sizeof tokbuf) ? atoi(tokbuf) : 0;
+      e->ydim = header_token(line, 3, tokbuf, sizeof tokbuf) ? atoi(tokbuf) : 0;
+      e->neigh = name_id(neigh_names, 3, header_token(line, 4, tokbuf, sizeof tokbuf));
+      break;
+    }
+    p = nl ? nl + 1 : endbuf;
+  }
+  /* blocks of whole lines, at least 1 MiB each */
+  nthreads = env ? atoi(env) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  if ((size_t)(endbuf - p) / nthreads < (1u << 20)) nthreads = (int)((size_t)(endbuf - p) >> 20) + 1;
+  blks = (struct blk *)calloc((size_t)nthreads, sizeof(*blks));
+  tids = (pthread_t *)calloc((size_t)nthreads, sizeof(*tids));
+  if (!blks || !tids) goto fail;
+  {
+    char *start = p;
+    const size_t chunk = (size_t)(endbuf - p) / nthreads + 1;
+    while (start < endbuf) {
+      char *stop = start + chunk < endbuf ? start + chunk : endbuf;
+      if (stop < endbuf) {                                 /* extend to the end of the line */
+        char *nl = (char *)memchr(stop, '\n', (size_t)(endbuf - stop));
+        stop = nl ? nl + 1 : endbuf;
+      }
+      blks[nb].beg = start; blks[nb].end = stop;
+      blks[nb].dim = dim; blks[nb].labels_needed = labels_needed; blks[nb].skip_empty = skip_empty;
+      blks[nb].mask_str = pak_mask_string; blks[nb].name = name;
+      nb++;
+      start = stop;
+    }
+  }
+  for (t = 1; t < nb; t++)
+    if (pthread_create(&tids[t], NULL, blk_parse, &blks[t])) { blk_parse(&blks[t]); tids[t] = 0; }
+  if (nb > 0) blk_parse(&blks[0]);
+  for (t = 1; t < nb; t++)
+    if (tids[t]) pthread_join(tids[t], NULL);
+  /* first error in file order, with its line number in the file */
+  {
+    long lines_before = header_lines;
+    for (t = 0; t < nb; t++) {
+      const long ln = lines_before + blks[t].err_line;
+      if (blks[t].err == 1)
+        fprintf(stderr, "load_entry: can't read entry in file %s on line %ld, component %d\n", name, ln, blks[t].err_comp);
+      if (blks[t].err == 2) fprintf(stderr, "out of memory while reading %s\n", name);
+      if (blks[t].err == 3) fprintf(stderr, "bad fixed point, line %ld of file %s\n", ln, name);
+      if (blks[t].err == 4) fprintf(stderr, "Required label missing on line %ld of file %s\n", ln, name);
+      if (blks[t].err) { failed = 1; break; }
+      lines_before += blks[t].lines;
+    }
+  }
+  if (failed) goto fail;
+  /* stitch the blocks together in file order */
+  for (t = 0; t < nb; t++) { total += blks[t].n; totlab += blks[t].nlab; if (blks[t].mask) any_mask = 1; }
+  e->n = total;
+  e->points = (float *)malloc(sizeof(float) * (size_t)(total > 0 ? total : 1) * dim);
+  e->lab_off = (long *)calloc((size_t)total + 1, sizeof(long));
+  e->lab_pool = (int *)malloc(sizeof(int) * (size_t)(totlab > 0 ? totlab : 1));
+  e->weight = (short *)calloc((size_t)(total > 0 ? total : 1), sizeof(short));
+  e->fixed_xy = (short *)malloc(sizeof(short) * 2 * (size_t)(total > 0 ? total : 1));
+  if (any_mask) e->mask = (unsigned char *)calloc((size_t)(total > 0 ? total : 1) * dim, 1);
+  if (!e->points || !e->lab_off || !e->lab_pool || !e->weight || !e->fixed_xy || (any_mask && !e->mask)) goto fail;
+  memset(e->fixed_xy, 0xff, sizeof(short) * 2 * (size_t)(total > 0 ? total : 1));
+  {
+    long row = 0, lab = 0;
+    for (t = 0; t < nb; t++) {
+      struct blk *b = &blks[t];
+      if (b->n == 0) continue;
+      memcpy(e->points + (size_t)row * dim, b->points, sizeof(float) * (size_t)b->n * dim);
+      if (b->mask) memcpy(e->mask + (size_t)row * dim, b->mask, (size_t)b->n * dim);
+      memcpy(e->weight + row, b->weight, sizeof(short) * (size_t)b->n);
+      memcpy(e->fixed_xy + 2 * row, b->fixed_xy, sizeof(short) * 2 * (size_t)b->n);
+      for (i = 0; i < b->n; i++) {
+        long l;
+        for (l = b->lab_off[i]; l < b->lab_off[i + 1]; l++) {
+          const int id = label_index(b->labs[l]);          /* file order: same table for any thread count */
+          if (id != LABEL_EMPTY) e->lab_pool[lab++] = id;
+        }
+        e->lab_off[row + i + 1] = lab;
+      }
+      row += b->n;
+    }
+  }
+  for (t = 0; t < nb; t++) blk_release(&blks[t]);
+  free(blks); free(tids); free(buf);
   return e;
 fail:
-  free(buf);
-  if (fp != stdin) fclose(fp);
+  if (blks) for (t = 0; t < nb; t++) blk_release(&blks[t]);
+  free(blks); free(tids); free(buf);
   pak_free(e);
   return NULL;
 }

@@ -687,6 +687,30 @@ int lvqtrain_main(int argc, char **argv, const char *progname) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ pakstat */
+/* load only: entries, dimension, a checksum of the values and the time the loader took */
+int pakstat_main(int argc, char **argv) {
+  struct pak_entries *e;
+  struct timespec t0, t1;
+  double sum = 0.0;
+  long i, nmask = 0;
+  global_options(argc, argv);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  e = pak_load(need(argc, argv, "-din"), 0, !flag(argc, argv, "-noskip"));
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (!e) return 1;
+  for (i = 0; i < e->n * e->dim; i++) { sum += e->points[i]; if (e->mask && e->mask[i]) nmask++; }
+  if (opt(argc, argv, "-rawout")) {                               /* the parsed values as raw float32 */
+    FILE *fp = fopen(opt(argc, argv, "-rawout"), "wb");
+    if (!fp || fwrite(e->points, sizeof(float), (size_t)e->n * e->dim, fp) != (size_t)e->n * e->dim) return 1;
+    fclose(fp);
+  }
+  fprintf(stdout, "entries %ld dim %d masked %ld labels %ld sum %.9g load_seconds %.4f\n", e->n, e->dim, nmask,
+          e->lab_off[e->n], sum, (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+  pak_free(e);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ pakcat */
 int pakcat_main(int argc, char **argv) {
   struct pak_entries *e;

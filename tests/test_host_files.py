@@ -60,3 +60,86 @@ def test_grammar_details(tmp_path):
     assert keep == "3 hexa 2 1 bubble\n1 2.5 x A B \nx x x dropped \n0.1 -7 1e+10 \n"
     alt = pakcat(tmp_path, "2\n1 NA\n", ["-mask_str", "NA"])
     assert alt == "2\n1 NA \n"
+
+
+def _big_file(rows, dim, seed=0):
+    rng = np.random.default_rng(seed)
+    vals = rng.normal(size=(rows, dim)).astype(np.float32)
+    lines = ["# generated", "%d" % dim]
+    for r in range(rows):
+        toks = ["%g" % v for v in vals[r]]
+        if r % 17 == 0:
+            toks[r % dim] = "x"
+        if r % 1001 == 0:
+            toks = ["x"] * dim                     # dropped entry (all components masked)
+        if r % 5 == 0:
+            toks.append("L%d" % (r % 13))
+        if r % 29 == 0:
+            toks += ["second", "weight=%d" % (r % 7), "fixed=%d,%d" % (r % 9, r % 4)]
+        lines.append(" ".join(toks))
+        if r % 97 == 0:
+            lines.append("")
+        if r % 211 == 0:
+            lines.append("# a comment in the middle")
+    return "\n".join(lines) + "\n"
+
+
+def test_parallel_loader_is_thread_count_independent(tmp_path):
+    """the block-parallel parser (pthreads) must give the same entries, masks and labels as one thread"""
+    text = _big_file(90_000, 24)                   # ~20 MB: enough for several 1 MiB blocks
+    src = tmp_path / "big.dat"
+    src.write_text(text)
+    outs = []
+    for threads in ("1", "3", "8"):
+        dst = tmp_path / ("out%s.dat" % threads)
+        env = dict(os.environ, BMU_PAK_THREADS=threads)
+        subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(dst)], check=True, env=env)
+        outs.append(dst.read_bytes())
+    assert outs[0] == outs[1] == outs[2]
+    kept = [l for l in text.splitlines()[2:] if l and not l.startswith("#") and set(l.split()[:24]) != {"x"}]
+    assert outs[0].count(b"\n") == len(kept) + 1
+
+
+def test_parallel_loader_reports_the_file_line(tmp_path):
+    text = _big_file(60_000, 24).splitlines()
+    bad_line = 41_234
+    text[bad_line - 1] = "oops " + text[bad_line - 1]
+    src = tmp_path / "bad.dat"
+    src.write_text("\n".join(text) + "\n")
+    p = subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(tmp_path / "o")], stderr=subprocess.PIPE,
+                       text=True, env=dict(os.environ, BMU_PAK_THREADS="6"))
+    assert p.returncode != 0
+    assert "on line %d, component 0" % bad_line in p.stderr
+
+
+def test_fast_decimal_parser_equals_strtof(tmp_path):
+    """every token form a .dat file can hold must convert exactly like libc's strtof (= scanf %f)"""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    rng = np.random.default_rng(11)
+    toks = []
+    for v in rng.normal(size=20000):
+        toks += ["%g" % v, "%.9g" % v, "%.3f" % (v * 1000), "%e" % (v * 1e-20), "%.17g" % v]
+    toks += ["%d" % i for i in rng.integers(-10**9, 10**9, 5000)]
+    toks += ["0", "-0", "+.5", "5.", "1e5", "1E-5", "1e", "1e+", "3.4028235e38", "3.5e38", "1e-45", "1.17549435e-38",
+             "1.4e-45", "123456789012345678901234567890", "0.000000000000000000000000000001", "16777217", "16777216.5",
+             "8388608.5", "8388609.5", "0.1", "0.3", "1.0000001192092896", "1.00000017881393432617187500",
+             "inf", "-inf", "nan", "0x1.8p1", "1.5abc", "7e2x"]
+    # float rounding midpoints: (2k+1) * 2^-1 around 2^24, written exactly and just beside
+    for k in range(200):
+        m = (1 << 24) + 2 * k + 1
+        toks += ["%d.0" % m, "%d.5" % (m >> 1), "%.1f" % (m / 2 + 1e-7), "%d" % (m * 4), "%de-1" % (m * 5)]
+    dim = 8
+    toks = toks[:len(toks) // dim * dim]
+    rows = [toks[i:i + dim] for i in range(0, len(toks), dim)]
+    src = tmp_path / "tok.dat"
+    src.write_text("%d\n" % dim + "\n".join(" ".join(r) for r in rows) + "\n")
+    raw = tmp_path / "tok.f32"
+    subprocess.run([PAK, "pakstat", "-din", str(src), "-rawout", str(raw)], check=True, stdout=subprocess.PIPE)
+    got = np.fromfile(raw, dtype=np.float32)
+    exp = np.array([libc.strtof(t.encode(), None) for t in toks], dtype=np.float32)
+    assert got.shape == exp.shape
+    same = (got.view(np.int32) == exp.view(np.int32)) | (np.isnan(got) & np.isnan(exp))
+    assert same.all(), [(toks[i], got[i], exp[i]) for i in np.nonzero(~same)[0][:5]]
