@@ -672,14 +672,14 @@ __device__ __forceinline__ uint32_t k2r_idesc() {
 template <int R, int NK>
 __global__ void __launch_bounds__(K2R_THREADS, 1)
 k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
-              const RowStats *__restrict__ rs, long N, long M, int Kp,
+              const RowStats *__restrict__ rs, long N, long M, int Kp, int nst,
               int32_t *__restrict__ cand, float *__restrict__ thr) {
   static_assert(R == 4, "one epilogue group and one 128-column accumulator per row tile");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t a_tile_bytes = (uint32_t)K2_TM * Kp * 2, b_tile_bytes = (uint32_t)K2_TN * Kp * 2;
   unsigned char *sA = smem;                                   // R row tiles
-  unsigned char *sB = smem + (size_t)R * a_tile_bytes;        // K2R_BST code tiles
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)K2R_BST * b_tile_bytes);
+  unsigned char *sB = smem + (size_t)R * a_tile_bytes;        // nst (<= K2R_BST) code tiles
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)nst * b_tile_bytes);
   uint64_t *full = bars, *empty = bars + K2R_BST;
   uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + R;
   uint64_t *afull = tempty + R, *aempty = afull + 1;
@@ -718,8 +718,8 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 #pragma unroll
         for (int r = 0; r < R; r++) bulk_g2s(sA + (size_t)r * a_tile_bytes, gA + (size_t)r * a_tile_bytes, a_tile_bytes, afull);
         for (int ct = 0; ct < nct; ct++, bseq++) {
-          const int s = bseq % K2R_BST;
-          mbar_wait(&empty[s], ((bseq / K2R_BST) & 1) ^ 1);
+          const int s = bseq % nst;
+          mbar_wait(&empty[s], ((bseq / nst) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], b_tile_bytes);
           bulk_g2s(sB + (size_t)s * b_tile_bytes,
                    reinterpret_cast<const unsigned char *>(Bimg) + (size_t)ct * b_tile_bytes, b_tile_bytes, &full[s]);
@@ -741,8 +741,8 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
       mbar_wait(afull, tcount & 1);
       tc_fence_after();
       for (int ct = 0; ct < nct; ct++, bseq++) {
-        const int s = bseq % K2R_BST;
-        mbar_wait(&full[s], (bseq / K2R_BST) & 1);
+        const int s = bseq % nst;
+        mbar_wait(&full[s], (bseq / nst) & 1);
         tc_fence_after();
         const uint64_t dbs = db0 + (uint64_t)s * b_tile_step;
 #pragma unroll
@@ -1120,8 +1120,15 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
   return k2_run_rerank<TG>(c, a, s, st);
 }
 
+// staged code tiles: as many as fit next to the four resident row tiles (3 up to K = 80, 2 at K = 96)
+static int k2r_stages(int Kp) {
+  const size_t a = (size_t)K2R_R * K2_TM * Kp * 2, b = (size_t)K2_TN * Kp * 2;
+  int n = K2R_BST;
+  while (n > 2 && a + n * b + 256 > 227 * 1024) n--;
+  return n;
+}
 static size_t k2r_smem_bytes(int Kp) {
-  return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)K2R_BST * K2_TN * Kp * 2 + 256;
+  return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)k2r_stages(Kp) * K2_TN * Kp * 2 + 256;
 }
 
 template <int NK>
@@ -1134,7 +1141,7 @@ static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scra
   const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
   const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
   k2_rec_kernel<K2R_R, NK><<<grid, K2R_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
-                                                           s.cand, s.thr);
+                                                           k2r_stages(Kp), s.cand, s.thr);
   return cudaGetLastError();
 }
 

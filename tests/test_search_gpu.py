@@ -126,3 +126,21 @@ def test_filter_path_certifies_most_rows(engine, oracle):
         assert_bits_equal(diff, e[1], "k2 diff")
         assert bd["k2_certified"] >= 0.97 * N, bd
         assert bd["k2_certified"] + bd["k2_failed"] == N, bd
+
+
+@pytest.mark.parametrize("D", [5, 20, 40, 56, 64, 77, 88, 89])
+def test_record_kernel_every_k_depth(engine, oracle, D):
+    """k = 1 on the filter path: D <= 88 runs k2_rec_kernel with 1..6 unrolled MMAs per accumulation
+    (operand K = 16..96), D = 89 is the first shape of the streaming kernel; ragged M and N"""
+    rng = np.random.default_rng(100 + D)
+    M, N = 777, 2100
+    codes = rng.random((M, D), dtype=np.float32) - np.float32(0.5)
+    data = rng.random((N, D), dtype=np.float32) - np.float32(0.5)
+    data[7] = codes[300]                                    # an exact hit
+    engine.set_search_path(2)
+    try:
+        check(engine, codes, data, 1, None, oracle.search(codes, data, 1), "rec D=%d" % D)
+        bd = engine.last_search_breakdown()
+    finally:
+        engine.set_search_path(0)
+    assert bd["k2_certified"] + bd["k2_failed"] == N and bd["k2_certified"] >= 0.9 * N, bd
