@@ -162,6 +162,12 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
 /* lvq_pak.c:459-473 + datafile.c:1152-1188: order[i] = row used at list position i after
  * `-rand seed` (seed != 0; the reference maps seed 0 to time()). */
 void bmu_rand_order(long n, int seed, int32_t *order);
+/* randinit_codes (som_rout.c:34-157): M = xdim*ydim code vectors drawn uniformly between the
+ * per-component minimum and maximum of the (unmasked) data with the reference's generator seeded
+ * by `seed` (init_random, lvq_pak.c:478-484); components without data become 0.  Used by the
+ * multi-trial map search (vfind.c:247-306), one trial per seed. */
+void bmu_randinit_codes(const float *data, const unsigned char *mask, long N, int D, long M, int seed,
+                        float *codes);
 /* fill sample/talp/trad for steps [le0, le1) of a run of `length` steps.  order: NULL =
  * identity; weight: NULL or N shorts (vsom -weights, som_rout.c:622-624). */
 void bmu_som_schedule(long le0, long le1, long length, float alpha, float radius,

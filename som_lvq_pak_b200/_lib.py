@@ -53,6 +53,7 @@ PROTOTYPES = {
     "bmu_som_schedule": (None, [C.c_long, C.c_long, C.c_long, C.c_float, C.c_float, C.c_int,
                                 C.c_long, vp, vp, vp, vp, vp]),
     "bmu_replay_qerror": (C.c_float, [vp, vp, C.c_long, C.c_int]),
+    "bmu_randinit_codes": (None, [vp, vp, C.c_long, C.c_int, C.c_long, C.c_int, vp]),
     "bmu_lvq_schedule": (None, [C.c_long, C.c_long, C.c_long, C.c_float, C.c_int, C.c_long, vp,
                                 vp, vp]),
 }

@@ -2,6 +2,7 @@
 // search entry points (host- and device-pointer), per-shard statistics and the pure-C host
 // helpers (sample order, schedules).  No CPU fallback: without a usable sm_100 device every
 // entry point fails with BMU_ERR_NODEV / BMU_ERR_CUDA.
+#include <float.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -458,6 +459,38 @@ void bmu_rand_order(long n, int seed, int32_t *order) {
     order[i] = order[j];
     order[j] = t;
   }
+}
+
+// som_rout.c:97-152.  The maximum starts at FLT_MIN (the smallest POSITIVE float), a quirk kept on
+// purpose; the value expression mixes float and double exactly as the reference's does:
+//   mival + (maval - mival) * ((float) orand() / 32768.0)
+void bmu_randinit_codes(const float *data, const unsigned char *mask, long N, int D, long M, int seed,
+                        float *codes) {
+  float *mx = (float *)malloc(sizeof(float) * 2 * (size_t)D), *mn = mx + D;
+  long *cnt = (long *)calloc((size_t)D, sizeof(long));
+  unsigned long state = (unsigned long)seed;
+  if (!mx || !cnt) { free(mx); free(cnt); return; }
+  for (int i = 0; i < D; i++) { mx[i] = FLT_MIN; mn[i] = FLT_MAX; }
+  for (long n = 0; n < N; n++)
+    for (int i = 0; i < D; i++) {
+      if (mask && mask[n * (long)D + i]) continue;
+      const float v = data[n * (long)D + i];
+      cnt[i]++;
+      if (mx[i] < v) mx[i] = v;
+      if (mn[i] > v) mn[i] = v;
+    }
+  for (long u = 0; u < M; u++)
+    for (int i = 0; i < D; i++) {
+      if (cnt[i] > 0) {
+        state = (state * 23UL) % 100000001UL;
+        const long r = (long)(int)(state % 32767UL);
+        codes[u * (long)D + i] = (float)((double)mn[i] + (double)(mx[i] - mn[i]) * ((double)(float)r / 32768.0));
+      } else {
+        codes[u * (long)D + i] = 0.0f;
+      }
+    }
+  free(mx);
+  free(cnt);
 }
 
 static float alpha_at(long le, long length, float alpha, int alpha_type) {

@@ -71,3 +71,57 @@ def gather_rows(local, n_rows, group=None):
     bufs = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
     dist.gather(padded.contiguous(), bufs, dst=0, group=group)
     return torch.cat([b[:n] for b, n in zip(bufs, sizes)]) if rank == 0 else None
+
+
+# ---------------------------------------------------------------------------- vfind
+def trial_numbers(trials, rank, world):
+    """trials are numbered trials..1 and run in that order (vfind.c:250-306); rank r takes every
+    world-th one, so that the union over ranks is the reference's sequence"""
+    return [n for k, n in enumerate(range(trials, 0, -1)) if k % world == rank]
+
+
+def select_best(results):
+    """results: (qerror float32, trial number) pairs from all ranks.  The reference keeps a map only
+    on a strictly smaller error while counting the trial number DOWN (vfind.c:288), so among equal
+    errors the LARGEST trial number wins."""
+    best = None
+    for q, n in sorted(results, key=lambda t: -t[1]):
+        if best is None or q < best[0]:
+            best = (q, n)
+    return best
+
+
+def vfind(data, test, xdim, ydim, topol, neigh, trials, length1, alpha1, radius1, length2, alpha2, radius2,
+          alpha_type=1, qetype=0, group=None):
+    """Multi-trial map search, one trial stream per GPU: every rank trains its share of the trials
+    (randinit with seed = trial number, two training phases, quantization error on `test`), the
+    (error, trial) pairs are all-gathered and the owner of the best map broadcasts it.  Training
+    itself does not shard; this is the one place more GPUs help it.
+    Returns (codes, qerror_sum, trial)."""
+    import torch
+    import torch.distributed as dist
+    from . import engine as E
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = None
+    for n in trial_numbers(trials, rank, world):
+        codes = E.randinit_codes(data, xdim, ydim, n)
+        codes = E.som_training(codes, data, xdim, ydim, topol, neigh, length1, alpha1, radius1, alpha_type)
+        codes = E.som_training(codes, data, xdim, ydim, topol, neigh, length2, alpha2, radius2, alpha_type)
+        q = E.find_qerror2(codes, test, xdim, ydim, topol, neigh, radius2)[0] if qetype else E.find_qerror(codes, test)
+        if mine is None or q < mine[0]:
+            mine = (np.float32(q), n, codes)
+    if world == 1:
+        return mine[2], mine[0], mine[1]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    pair = torch.tensor([float(mine[0]) if mine else float("inf"), float(mine[1]) if mine else 0.0],
+                        dtype=torch.float64, device=dev)
+    allp = [torch.empty_like(pair) for _ in range(world)]
+    dist.all_gather(allp, pair, group=group)
+    cands = [(np.float32(p[0].item()), int(p[1].item())) for p in allp if p[1].item() > 0]
+    q, n = select_best(cands)
+    owner = [r for r in range(world) if n in trial_numbers(trials, r, world)][0]
+    M, D = xdim * ydim, np.asarray(data).shape[1]
+    buf = torch.from_numpy(mine[2].copy() if rank == owner else np.empty((M, D), np.float32)).to(dev)
+    dist.broadcast(buf, owner, group=group)
+    return buf.cpu().numpy(), q, n

@@ -166,6 +166,16 @@ def rand_order(n, seed):
     return order
 
 
+def randinit_codes(data, xdim, ydim, seed, mask=None):
+    """randinit_codes (som_rout.c:34-157) after init_random(seed): the map `randinit -rand seed` writes"""
+    data = _f32(data)
+    mask = _opt(mask, np.uint8)
+    N, D = data.shape
+    codes = np.empty((xdim * ydim, D), np.float32)
+    _lib.load().bmu_randinit_codes(_ptr(data), _ptr(mask), N, D, xdim * ydim, int(seed), _ptr(codes))
+    return codes
+
+
 def som_schedule(le0, le1, length, alpha, radius, alpha_type, N, order=None, weight=None):
     n = le1 - le0
     sample = np.empty(n, np.int32)

@@ -13,12 +13,14 @@
  *   eliminate_codes             elimin.c:42-126       bmu_search (k) of the data set against itself
  *   som_training                som_rout.c:556-671    bmu_som_schedule + bmu_som_train
  *   lvq1/olvq1/lvq2/lvq3        lvq_rout.c:498-916    bmu_lvq_schedule + bmu_lvq_train
+ *   vfind trials                vfind.c:247-306       bmu_randinit_codes + 2 x bmu_som_train + qerror, per trial
  *
  * Not carried over (outside SURVEY.md section 8): -buffer (files are loaded whole), -selfuncs,
  * snapshots, compressed / piped file names.
  */
 #include "somhost.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -684,6 +686,142 @@ int lvqtrain_main(int argc, char **argv, const char *progname) {
   free(code_label); free(data_label); free(unit_alpha);
   pak_free(data);
   pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ vfind */
+/* vfind.c:138-330: answers are read from stdin after the same prompts; every trial is
+ * randinit (seed = trial number) -> two training phases -> quantization error on the test file;
+ * the best map is saved.  Trials are independent: with BMU_TRIAL_STRIDE / BMU_TRIAL_OFFSET (set
+ * by a launcher, one process per GPU) a process runs every stride-th trial and reports its best
+ * on stdout, so that the launcher can pick the overall best (som_lvq_pak_b200/distributed.py). */
+static long ask_int(const char *q, long def) {
+  char str[100];
+  printf("%s: ", q);
+  if (!fgets(str, sizeof str, stdin)) return def;
+  return atol(str);
+}
+static float ask_float(const char *q, float def) {
+  char str[100];
+  printf("%s: ", q);
+  if (!fgets(str, sizeof str, stdin)) return def;
+  return (float)atof(str);
+}
+static char *ask_str(const char *q) {
+  char str[100], *t;
+  printf("%s: ", q);
+  if (!fgets(str, sizeof str, stdin)) { printf("Can't read required data\n"); exit(1); }
+  t = strdup(str);
+  if (strchr(t, ' ')) *strchr(t, ' ') = '\0';
+  if (strchr(t, '\n')) *strchr(t, '\n') = '\0';
+  return t;
+}
+static int name_to_id(const char *s, const char *a, int ia, const char *b, int ib) {
+  if (strcasecmp(s, a) == 0) return ia;
+  if (strcasecmp(s, b) == 0) return ib;
+  return 0;
+}
+
+int vfind_main(int argc, char **argv) {
+  struct pak_entries *data, *test, *best = NULL;
+  long trials, bnot = 0, length1, length2, lmax, not;
+  int xdim, ydim, topol, neigh, alpha_type, use_fixed, use_weights, qmode, stride = 1, offset = 0;
+  float alpha1, radius1, alpha2, radius2, qerrorb = FLT_MAX;
+  char *din, *tin, *cout_name;
+  const char *s;
+  int32_t *sample;
+  float *talp, *trad, *per = NULL;
+  global_options(argc, argv);
+  printf("Repeated initialization, training and testing of a Self-Organizing Map (vfind); the best map\n"
+         "(smallest quantization error on the test file) is saved.\n\n");
+  trials = ask_int("Give the number of trials", 0);
+  din = ask_str("Give the input data file name");
+  tin = ask_str("Give the input test file name");
+  cout_name = ask_str("Give the output map file name");
+  topol = name_to_id(ask_str("Give the topology type"), "hexa", TOPOL_HEXA, "rect", TOPOL_RECT);
+  if (!topol) topol = TOPOL_HEXA;
+  neigh = name_to_id(ask_str("Give the neighborhood type"), "bubble", NEIGH_BUBBLE, "gaussian", NEIGH_GAUSSIAN);
+  if (!neigh) neigh = NEIGH_BUBBLE;
+  xdim = (int)ask_int("Give the x-dimension", 0);
+  ydim = (int)ask_int("Give the y-dimension", 0);
+  length1 = ask_int("Give the training length of first part", 0);
+  alpha1 = ask_float("Give the training rate of first part", 0.0f);
+  radius1 = ask_float("Give the radius in first part", 0.0f);
+  length2 = ask_int("Give the training length of second part", 0);
+  alpha2 = ask_float("Give the training rate of second part", 0.0f);
+  radius2 = ask_float("Give the radius in second part", 0.0f);
+  printf("\n");
+  s = opt(argc, argv, "-fixed");   use_fixed = s ? atoi(s) : 0;        /* vfind.c:186-187: valued options */
+  s = opt(argc, argv, "-weights"); use_weights = s ? atoi(s) : 0;
+  s = opt(argc, argv, "-qetype");  qmode = s ? atoi(s) : 0;
+  if (alpha_type_of(argc, argv, &alpha_type)) return 1;
+  if ((s = getenv("BMU_TRIAL_STRIDE")) != NULL && atoi(s) > 0) stride = atoi(s);
+  if ((s = getenv("BMU_TRIAL_OFFSET")) != NULL) offset = atoi(s);
+  data = pak_load(din, 0, 1);
+  if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  test = pak_load(tin, 0, 1);
+  if (!test) { fprintf(stderr, "Can't open test data file '%s'\n", tin); return 1; }
+  if ((long)xdim * ydim <= 0 || xdim < 0) { fprintf(stderr, "Dimensions of map (%d %d) are incorrect\n", xdim, ydim); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+  lmax = length1 > length2 ? length1 : length2;
+  sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)(lmax > 0 ? lmax : 1));
+  talp = (float *)malloc(sizeof(float) * (size_t)(lmax > 0 ? lmax : 1));
+  trad = (float *)malloc(sizeof(float) * (size_t)(lmax > 0 ? lmax : 1));
+  if (qmode > 0) per = (float *)malloc(sizeof(float) * (size_t)(test->n > 0 ? test->n : 1));
+  if (!sample || !talp || !trad || (qmode > 0 && !per)) return 1;
+  for (not = trials; not > 0; not--) {                                  /* vfind.c:247-306 */
+    struct pak_entries *codes;
+    float qerror = 0.0f;
+    int phase;
+    if ((int)((trials - not) % stride) != offset) continue;
+    codes = pak_alloc(data->dim, (long)xdim * ydim);
+    if (!codes) return 1;
+    codes->topol = topol; codes->neigh = neigh; codes->xdim = xdim; codes->ydim = ydim;
+    bmu_randinit_codes(data->points, data->mask, data->n, data->dim, codes->n, (int)not, codes->points);
+    for (phase = 0; phase < 2; phase++) {
+      const long len = phase ? length2 : length1;
+      if (len <= 0 || data->n == 0) continue;
+      bmu_som_schedule(0, len, len, phase ? alpha2 : alpha1, phase ? radius2 : radius1, alpha_type, data->n, NULL,
+                       use_weights ? data->weight : NULL, sample, talp, trad);
+      if (bmu_som_train(codes->points, codes->n, codes->dim, xdim, ydim, topol, neigh, data->points, data->mask,
+                        data->n, use_fixed ? data->fixed_xy : NULL, sample, talp, trad, len))
+        return engine_failed("bmu_som_train");
+    }
+    {
+      bmu_codebook *cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
+      if (!cb) return engine_failed("bmu_codebook_create");
+      if (qmode > 0) {
+        long i;
+        if (bmu_qerror2(cb, xdim, ydim, topol, neigh, radius2, test->points, test->mask, test->n, per))
+          return engine_failed("bmu_qerror2");
+        for (i = 0; i < test->n; i++) qerror += per[i];
+      } else {
+        struct winners w;
+        bmu_codebook_destroy(cb);
+        cb = NULL;
+        if (find_winners(codes, test, 1, &w)) return 1;
+        qerror = bmu_replay_qerror(w.diff, w.nfound, test->n, 1);
+        winners_free(&w);
+      }
+      if (cb) bmu_codebook_destroy(cb);
+    }
+    if (qerror < qerrorb) {
+      qerrorb = qerror;
+      bnot = not;
+      pak_free(best);
+      best = codes;
+    } else {
+      pak_free(codes);
+    }
+    if (verbose_level >= 1) fprintf(stderr, "%3ld: %f\n", not, qerror / (float)test->n);
+  }
+  if (best) {
+    pak_save(best, cout_name);
+    if (verbose_level >= 1)
+      fprintf(stdout, "Smallest error with random seed %3ld: %f\n", bnot, qerrorb / (float)test->n);
+  }
+  pak_free(best); pak_free(data); pak_free(test);
+  free(sample); free(talp); free(trad); free(per);
   return 0;
 }
 

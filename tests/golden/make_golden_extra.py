@@ -4,6 +4,7 @@
 already stored in demo.npz.  Run in the build container (needs /root/reference for `make -C oracle ref`):
     python tests/golden/make_golden_extra.py        ->  tests/golden/demo_extra.npz"""
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -43,6 +44,18 @@ def main():
     out["elimin_cod"] = np.array(open(os.path.join(td, "el.cod")).read())
     run([b("elimin"), "-din", "ex2.dat", "-cout", "el10.cod", "-knn", "10"], td)
     out["elimin10_cod"] = np.array(open(os.path.join(td, "el10.cod")).read())
+    # vfind: 4 trials of a 6x4 map on ex.dat (answers on stdin, vfind.c:138-185), both qerror types
+    open(os.path.join(td, "ex.dat"), "w").write(str(demo["in_ex.dat"]))
+    for tag, extra in (("vfind", []), ("vfind_q1", ["-qetype", "1", "-alpha_type", "inverse_t"])):
+        answers = "\n".join(["4", "ex.dat", "ex.dat", tag + ".cod", "hexa", "bubble" if tag == "vfind" else "gaussian",
+                             "6", "4", "300", "0.05", "4", "600", "0.02", "2"]) + "\n"
+        p = subprocess.run([b("vfind")] + extra, cwd=td, input=answers, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True)
+        if p.returncode:
+            raise RuntimeError("vfind failed: " + p.stderr)
+        out[tag + "_cod"] = np.array(open(os.path.join(td, tag + ".cod")).read())
+        out[tag + "_trials"] = np.array("".join(re.findall(r"(?m)^ *\d+: [0-9.]+\n", p.stderr.replace("\r", "\n"))))
+        out[tag + "_summary"] = np.array(p.stdout.splitlines()[-1] + "\n")
     shutil.rmtree(td)
     np.savez_compressed(os.path.join(HERE, "demo_extra.npz"), **out)
     print({k: len(str(v)) for k, v in out.items()})

@@ -85,3 +85,18 @@ def test_schedules_match_oracle(oracle):
         if ww > 0:
             a = np.float32(1.0 - np.float64(np.float32(np.power(1.0 - np.float64(a), np.float64(ww)))))
         assert ta[le] == a
+
+
+def test_randinit_codes_matches_reference_randinit(golden):
+    """pure host helper (no device): the map `randinit -rand 123 -xdim 12 -ydim 8` wrote for ex.dat
+    and `-rand 7 -xdim 10 -ydim 7` (tests/golden/demo.npz), compared through the %g formatting"""
+    import numpy as np
+    import datfile
+    import som_lvq_pak_b200 as b
+    g = golden.demo
+    data = datfile.parse(str(g["in_ex.dat"]))
+    for key, xdim, ydim, seed in (("som_init_cod", 12, 8, 123), ("som_g_init_cod", 10, 7, 7)):
+        ref = datfile.parse(str(g[key]))
+        got = b.randinit_codes(data.points, xdim, ydim, seed, data.mask)
+        assert got.shape == ref.points.shape
+        assert [["%g" % v for v in row] for row in got] == [["%g" % v for v in row] for row in ref.points]

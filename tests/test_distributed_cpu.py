@@ -85,3 +85,15 @@ def test_replay_qerror_is_the_sequential_float_sum():
             q = np.float32(np.float64(q) + np.sqrt(np.float64(d)))
     got = _lib.load().bmu_replay_qerror(diff.ctypes.data, nf.ctypes.data, 5000, 1)
     assert np.float32(got) == q
+
+
+def test_vfind_trial_split_and_selection():
+    from som_lvq_pak_b200.distributed import select_best, trial_numbers
+    for trials in (1, 4, 7, 16):
+        for world in (1, 2, 3, 8):
+            parts = [trial_numbers(trials, r, world) for r in range(world)]
+            assert sorted(sum(parts, []), reverse=True) == list(range(trials, 0, -1))
+            assert all(p == sorted(p, reverse=True) for p in parts)
+    # strictly-smaller rule while counting down: ties go to the larger trial number
+    assert select_best([(np.float32(3.0), 1), (np.float32(2.0), 2), (np.float32(2.0), 4), (np.float32(5.0), 3)]) == (np.float32(2.0), 4)
+    assert select_best([(np.float32(1.5), 1)]) == (np.float32(1.5), 1)

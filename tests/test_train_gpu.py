@@ -122,3 +122,15 @@ def test_som_large_dim_fused_kernel(engine, oracle, xdim, ydim, D, topol, neigh)
         if neigh == 2:
             nbad = int((out.view(np.int32) != exp.view(np.int32)).sum())
             assert nbad <= out.size // 100000 + 2, "%d of %d floats differ" % (nbad, out.size)
+
+
+def test_vfind_python_orchestration(engine, golden):
+    """distributed.vfind at world size 1 must find the reference vfind's map (tests/golden/demo_extra.npz)"""
+    import datfile
+    from som_lvq_pak_b200 import distributed as Dm
+    data = datfile.parse(str(golden.demo["in_ex.dat"]))
+    ref = datfile.parse(str(golden.demo_extra["vfind_cod"]))
+    codes, q, n = Dm.vfind(data.points, data.points, 6, 4, 3, 1, 4, 300, 0.05, 4.0, 600, 0.02, 2.0)
+    assert n == 4
+    assert "%f" % (q / np.float32(data.points.shape[0])) == "9.632525"
+    assert [["%g" % v for v in row] for row in codes] == [["%g" % v for v in row] for row in ref.points]
