@@ -825,6 +825,57 @@ int vfind_main(int argc, char **argv) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ randinit */
+/* mapinit.c:52-181 with the random initialisation (randinit / mapinit -init rand); the linear
+ * initialisation (eigenvectors of the data) is not on the BMU path and is not carried over */
+int randinit_main(int argc, char **argv, const char *progname) {
+  struct pak_entries *data, *codes;
+  const char *din, *cout_name, *s;
+  int topol, neigh, xdim, ydim;
+  long seed;
+  FILE *fp;
+  long i;
+  int c;
+  global_options(argc, argv);
+  din = need(argc, argv, "-din");
+  cout_name = need(argc, argv, "-cout");
+  s = opt(argc, argv, "-rand");
+  seed = s ? atol(s) : 0;
+  s = need(argc, argv, "-topol");
+  topol = name_to_id(s, "hexa", TOPOL_HEXA, "rect", TOPOL_RECT);
+  if (!topol) { fprintf(stderr, "Unknown topology type %s\n", s); return 1; }
+  s = need(argc, argv, "-neigh");
+  neigh = name_to_id(s, "bubble", NEIGH_BUBBLE, "gaussian", NEIGH_GAUSSIAN);
+  if (!neigh) { fprintf(stderr, "Unknown neighborhood type %s\n", s); return 1; }
+  xdim = atoi(need(argc, argv, "-xdim"));
+  ydim = atoi(need(argc, argv, "-ydim"));
+  s = opt(argc, argv, "-init");
+  if ((s && strcmp(s, "rand") != 0) || (!s && strcasecmp(progname, "randinit") != 0)) {
+    fprintf(stderr, "Unknown initialization type %s (only the random initialisation is provided)\n", s ? s : progname);
+    return 1;
+  }
+  if ((long)xdim * ydim <= 0 || xdim < 0) { fprintf(stderr, "Dimensions of map (%d %d) are incorrect\n", xdim, ydim); return 1; }
+  data = pak_load(din, 0, 1);
+  if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  codes = pak_alloc(data->dim, (long)xdim * ydim);
+  if (!codes) return 1;
+  codes->topol = topol; codes->neigh = neigh; codes->xdim = xdim; codes->ydim = ydim;
+  bmu_randinit_codes(data->points, data->mask, data->n, data->dim, codes->n,
+                     (int)(seed ? seed : (long)time(NULL)), codes->points);       /* init_random, lvq_pak.c:478-484 */
+  fp = fopen(cout_name, "w");
+  if (!fp) { fprintf(stderr, "save_entries: Can't open file '%s'\n", cout_name); return 1; }
+  pak_write_header(fp, codes);
+  fprintf(fp, "# random seed: %ld\n", seed);                                      /* mapinit.c:176-177 */
+  for (i = 0; i < codes->n; i++) {
+    for (c = 0; c < codes->dim; c++) fprintf(fp, "%g ", codes->points[(size_t)i * codes->dim + c]);
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+  pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ pakstat */
 /* load only: entries, dimension, a checksum of the values and the time the loader took */
 int pakstat_main(int argc, char **argv) {

@@ -143,3 +143,14 @@ def test_fast_decimal_parser_equals_strtof(tmp_path):
     assert got.shape == exp.shape
     same = (got.view(np.int32) == exp.view(np.int32)) | (np.isnan(got) & np.isnan(exp))
     assert same.all(), [(toks[i], got[i], exp[i]) for i in np.nonzero(~same)[0][:5]]
+
+
+def test_randinit_program(tmp_path, demo):
+    """randinit needs no GPU: ex.dat -> the reference's `randinit -rand 123` map, comment line included"""
+    (tmp_path / "ex.dat").write_text(str(demo["in_ex.dat"]))
+    subprocess.run([PAK, "randinit", "-din", "ex.dat", "-cout", "ex.cod", "-xdim", "12", "-ydim", "8", "-topol", "hexa",
+                    "-neigh", "bubble", "-rand", "123"], check=True, cwd=tmp_path)
+    assert (tmp_path / "ex.cod").read_text() == str(demo["som_init_cod"])
+    subprocess.run([PAK, "mapinit", "-init", "rand", "-din", "ex.dat", "-cout", "g.cod", "-xdim", "10", "-ydim", "7",
+                    "-topol", "rect", "-neigh", "gaussian", "-rand", "7"], check=True, cwd=tmp_path)
+    assert (tmp_path / "g.cod").read_text() == str(demo["som_g_init_cod"])
