@@ -14,6 +14,7 @@
  *   som_training                som_rout.c:556-671    bmu_som_schedule + bmu_som_train
  *   lvq1/olvq1/lvq2/lvq3        lvq_rout.c:498-916    bmu_lvq_schedule + bmu_lvq_train
  *   vfind trials                vfind.c:247-306       bmu_randinit_codes + 2 x bmu_som_train + qerror, per trial
+ *   pick_inside_codes           lvq_rout.c:151-211    bmu_search (k) of the data set against itself (eveninit / propinit)
  *
  * Not carried over (outside SURVEY.md section 8): -buffer (files are loaded whole), -selfuncs,
  * snapshots, compressed / piped file names.
@@ -872,6 +873,197 @@ int randinit_main(int argc, char **argv, const char *progname) {
   }
   fclose(fp);
   pak_free(data);
+  pak_free(codes);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ eveninit / propinit */
+/* eveninit.c:46-160 + pick_inside_codes / correct_by_knn (lvq_rout.c:38-211): codebook vectors are
+ * picked from the data, class by class, among the entries that their own knn nearest neighbours in
+ * the data set classify correctly.  The reference runs one k-NN search per visited entry; here the
+ * whole self-search is ONE bmu_search call and the picking loop replays it in data order. */
+static void pick_inside(const struct pak_entries *data, const unsigned char *inside, struct pak_hitlist *classes,
+                        long *picked, long *npicked) {
+  long total = 0, i, c;
+  for (c = 0; c < classes->n; c++) total += classes->freq[c];
+  for (i = 0; i < data->n && total > 0; i++) {
+    const long lab = pak_label(data, i);
+    for (c = 0; c < classes->n; c++)
+      if (classes->label[c] == lab) break;
+    if (c == classes->n || classes->freq[c] <= 0 || !inside[i]) continue;
+    total--;
+    picked[(*npicked)++] = i;
+    classes->freq[c]--;
+  }
+}
+
+int eveninit_main(int argc, char **argv, const char *progname) {
+  struct pak_entries *data, *out;
+  struct winners w;
+  struct pak_hitlist classes, hits;
+  const char *din, *cout_name, *s;
+  unsigned char *inside;
+  long noc, nol, tot, nic, emp = 0, i, c, npicked = 0, *picked, nl = 0;
+  int knn, prop = -1, t;
+  char lra[2048];
+  global_options(argc, argv);
+  if (strcasecmp(progname, "propinit") == 0) prop = 1;
+  else if (strcasecmp(progname, "eveninit") == 0) prop = 0;
+  s = opt(argc, argv, "-type");
+  if (s && strcasecmp(s, "propinit") == 0) prop = 1;
+  else if (s && strcasecmp(s, "eveninit") == 0) prop = 0;
+  if (prop < 0) { fprintf(stderr, "unknown init type\n"); return 1; }
+  din = need(argc, argv, "-din");
+  cout_name = need(argc, argv, "-cout");
+  noc = atol(need(argc, argv, "-noc"));
+  s = opt(argc, argv, "-knn");
+  knn = s ? atoi(s) : 5;
+  if (knn < 1) knn = 1;
+  if (knn > BMU_KMAX) { fprintf(stderr, "-knn %d is larger than the engine's limit %d\n", knn, BMU_KMAX); return 1; }
+  data = pak_load(din, 1, 1);
+  if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+  if (find_winners(data, data, knn, &w)) return 1;
+  /* correct_by_knn for every entry: majority label of its knn neighbours == its own label */
+  inside = (unsigned char *)calloc((size_t)(data->n > 0 ? data->n : 1), 1);
+  picked = (long *)malloc(sizeof(long) * (size_t)(data->n > 0 ? data->n : 1));
+  if (!inside || !picked) return 1;
+  hit_init(&hits);
+  for (i = 0; i < data->n; i++) {
+    if (w.nfound[i] != knn) { inside[i] = 1; continue; }          /* -1 from correct_by_knn counts as true (lvq_rout.c:173) */
+    hit_clear(&hits);
+    for (t = 0; t < knn; t++) hit_add(&hits, pak_label(data, w.idx[i * knn + t]));
+    inside[i] = hits.n > 0 && hits.label[0] == pak_label(data, i);
+  }
+  hit_init(&classes);
+  for (i = 0; i < data->n; i++) hit_add(&classes, pak_label(data, i));
+  nol = classes.n;
+  tot = data->n;
+  if (nol > noc) fprintf(stderr, "There are more different classes than requested codes");
+  nic = nol ? noc / nol : 0;
+  for (c = 0; c < nol; c++) {                                      /* eveninit.c:86-94 */
+    if (prop) {
+      classes.freq[c] = (long)(classes.freq[c] * (float)noc / tot);
+      if (classes.freq[c] < 1) classes.freq[c] = 1;
+    } else {
+      classes.freq[c] = nic;
+    }
+  }
+  pick_inside(data, inside, &classes, picked, &npicked);
+  for (c = 0; c < nol; c++) if (classes.freq[c] == 0) emp++;
+  if (npicked < noc) {                                             /* eveninit.c:116-143: second pass */
+    float frac = 0.0f, err = 0.0f;
+    long first = npicked;
+    if (emp != 0) frac = (noc - npicked) / (float)emp;
+    for (c = 0; c < nol; c++) {
+      if (classes.freq[c] == 0) {
+        classes.freq[c] = (int)(frac + err);
+        err = frac + err - classes.freq[c];
+      } else {
+        classes.freq[c] = 0;
+      }
+    }
+    pick_inside(data, inside, &classes, picked, &npicked);
+    (void)first;
+  }
+  out = pak_alloc(data->dim, npicked);
+  if (!out) return 1;
+  out->topol = TOPOL_LVQ;
+  out->neigh = data->neigh; out->xdim = data->xdim; out->ydim = data->ydim;
+  if (data->mask) out->mask = (unsigned char *)calloc((size_t)(npicked > 0 ? npicked : 1) * data->dim, 1);
+  out->lab_pool = (int *)malloc(sizeof(int) * (size_t)(data->lab_off[data->n] > 0 ? data->lab_off[data->n] : 1));
+  if (!out->lab_pool || (data->mask && !out->mask)) return 1;
+  for (i = 0; i < npicked; i++) {
+    const long r = picked[i];
+    long l;
+    memcpy(out->points + (size_t)i * data->dim, data->points + (size_t)r * data->dim, sizeof(float) * data->dim);
+    if (data->mask) memcpy(out->mask + (size_t)i * data->dim, data->mask + (size_t)r * data->dim, (size_t)data->dim);
+    for (l = data->lab_off[r]; l < data->lab_off[r + 1]; l++) out->lab_pool[nl++] = data->lab_pool[l];
+    out->lab_off[i + 1] = nl;
+  }
+  pak_save(out, cout_name);
+  lra_name(cout_name, lra, sizeof lra);                              /* eveninit.c:229 invalidate_alphafile */
+  {
+    FILE *fp = fopen(lra, "r");
+    if (fp) {
+      if (verbose_level >= 1) fprintf(stdout, "Removing the learning rate file %s\n", lra);
+      fclose(fp);
+      if (remove(lra)) fprintf(stderr, "Can not remove %s", lra);
+    }
+  }
+  hit_free(&hits); hit_free(&classes);
+  free(inside); free(picked);
+  winners_free(&w);
+  pak_free(data);
+  pak_free(out);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ mindist */
+/* med_distances (lvq_rout.c:383-492): per class, the median over its entries of the distance to
+ * the nearest LATER entry of the same class (vector_dist_euc, lvq_pak.c:291-316), as `mindist`
+ * prints it (mindist.c:93-105).  Host arithmetic: O(M^2 D) on a codebook, not on the data. */
+static float host_vector_dist(const struct pak_entries *e, long a, long b) {
+  const float *x = e->points + (size_t)a * e->dim, *y = e->points + (size_t)b * e->dim;
+  const unsigned char *ma = e->mask ? e->mask + (size_t)a * e->dim : NULL, *mb = e->mask ? e->mask + (size_t)b * e->dim : NULL;
+  float difference = 0.0f;
+  int i, masked = 0;
+  for (i = 0; i < e->dim; i++) {
+    if ((ma && ma[i]) || (mb && mb[i])) { masked++; continue; }
+    {
+      const float diff = x[i] - y[i];
+      difference += diff * diff;
+    }
+  }
+  if (masked == e->dim) return -1.0f;
+  return (float)sqrt((double)difference);
+}
+static int cmp_float(const void *a, const void *b) {
+  const float x = *(const float *)a, y = *(const float *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+int mindist_main(int argc, char **argv) {
+  struct pak_entries *codes;
+  struct pak_hitlist classes;
+  const char *cin_name;
+  float *meds;
+  long c, i, j;
+  global_options(argc, argv);
+  cin_name = need(argc, argv, "-cin");
+  if (opt(argc, argv, "-din")) fprintf(stderr, "note: standard deviations (-din) are not provided by the B200 host\n");
+  codes = pak_load(cin_name, 1, 1);
+  if (!codes) { fprintf(stderr, "Can't read code file '%s'\n", cin_name); return 1; }
+  hit_init(&classes);
+  for (i = 0; i < codes->n; i++) hit_add(&classes, pak_label(codes, i));
+  meds = (float *)malloc(sizeof(float) * (size_t)(codes->n > 0 ? codes->n : 1));
+  if (!meds) return 1;
+  for (c = 0; c < classes.n; c++) {
+    const long lab = classes.label[c];
+    long not = 0;
+    float dist = 0.0f;
+    for (i = 0; i < codes->n; i++) {
+      float dissf = FLT_MAX;
+      int fou = 0;
+      if (pak_label(codes, i) != lab) continue;
+      for (j = i + 1; j < codes->n; j++) {
+        if (pak_label(codes, j) != lab) continue;
+        fou = 1;
+        {
+          const float d = host_vector_dist(codes, j, i);
+          if (d < dissf) dissf = d;
+        }
+      }
+      if (fou) meds[not++] = dissf;
+    }
+    if (not > 0) {
+      qsort(meds, (size_t)not, sizeof(float), cmp_float);
+      dist = meds[not / 2];
+    }
+    fprintf(stdout, "In class %9s %3d units, min dist.: %6.3f\n", label_string((int)lab), (int)classes.freq[c], dist);
+  }
+  free(meds);
+  hit_free(&classes);
   pak_free(codes);
   return 0;
 }

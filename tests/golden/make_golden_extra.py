@@ -44,6 +44,14 @@ def main():
     out["elimin_cod"] = np.array(open(os.path.join(td, "el.cod")).read())
     run([b("elimin"), "-din", "ex2.dat", "-cout", "el10.cod", "-knn", "10"], td)
     out["elimin10_cod"] = np.array(open(os.path.join(td, "el10.cod")).read())
+    # mindist on two codebooks, propinit (eveninit's output is demo.npz's lvq_e_cod)
+    open(os.path.join(td, "ex1b.cod"), "w").write(str(demo["lvq_b_cod"]))
+    out["mindist_b_stdout"] = np.array(run([b("mindist"), "-cin", "ex1b.cod"], td))
+    out["mindist_l_stdout"] = np.array(run([b("mindist"), "-cin", "ex1l.cod"], td))
+    run([b("propinit"), "-din", "ex1.dat", "-cout", "p.cod", "-noc", "150", "-knn", "3"], td)
+    out["propinit_cod"] = np.array(open(os.path.join(td, "p.cod")).read())
+    run([b("eveninit"), "-din", "ex2.dat", "-cout", "e2.cod", "-noc", "317"], td)
+    out["eveninit2_cod"] = np.array(open(os.path.join(td, "e2.cod")).read())
     # vfind: 4 trials of a 6x4 map on ex.dat (answers on stdin, vfind.c:138-185), both qerror types
     open(os.path.join(td, "ex.dat"), "w").write(str(demo["in_ex.dat"]))
     for tag, extra in (("vfind", []), ("vfind_q1", ["-qetype", "1", "-alpha_type", "inverse_t"])):
