@@ -943,7 +943,7 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
 // group l / GW; those lanes take the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and the
 // leader evaluates the certificate against thr (lower bound of every code outside the groups).
 __global__ void __launch_bounds__(256)
-k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ grp, long N, long M,
+k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ grp, long N, long M, long row0,
                        int D, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
                        const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
                        const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
@@ -1010,7 +1010,7 @@ k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__
     }
   }
   if (!ok) {
-    listW[atomicAdd(&counters[0], 1)] = (int)n;
+    listW[atomicAdd(&counters[0], 1)] = (int)(row0 + n);     // all other arrays are passed pre-offset by row0
     atomicAdd(&counters[3], 1);
     return;
   }
@@ -1131,40 +1131,82 @@ static size_t k2r_smem_bytes(int Kp) {
   return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)k2r_stages(Kp) * K2_TN * Kp * 2 + 256;
 }
 
+// rows [row0, row0 + n) of the call; row0 is a multiple of the 512-row pass of the kernel
 template <int NK>
-static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, long row0, long n,
+                                    cudaStream_t st) {
   const int Kp = c->Kp;
   const size_t smem = k2r_smem_bytes(Kp);
   cudaError_t e = cudaFuncSetAttribute(k2_rec_kernel<K2R_R, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long ntiles = (a.N + K2_TM - 1) / K2_TM;
+  const long ntiles = (n + K2_TM - 1) / K2_TM;
   const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
   const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
-  k2_rec_kernel<K2R_R, NK><<<grid, K2R_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
-                                                           k2r_stages(Kp), s.cand, s.thr);
+  k2_rec_kernel<K2R_R, NK><<<grid, K2R_THREADS, smem, st>>>(s.Aimg + (size_t)row0 * Kp, (const __half *)c->d_ops,
+                                                           s.rs + row0, n, a.M, Kp, k2r_stages(Kp),
+                                                           s.cand + row0 * K2R_NG, s.thr + row0);
   return cudaGetLastError();
 }
 
+// Large calls are cut into sub-batches: the re-rank of sub-batch i (L2-gather bound, no shared memory,
+// 36 registers) runs on a second stream beside the GEMM kernel of sub-batch i+1 (tensor / ALU bound,
+// 205 KB shared memory, 46 K registers), two re-rank blocks fit next to a GEMM CTA on every SM.
+static cudaStream_t g_k2aux = nullptr;
+static cudaEvent_t g_k2sub[16], g_k2join = nullptr;
+
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
-  cudaError_t e;
-  switch (c->Kp / 16) {                                 // K2R_MAX_KP / 16 = 6 unrolled issue loops
-    case 1: e = k2_launch_record<1>(c, a, s, st); break;
-    case 2: e = k2_launch_record<2>(c, a, s, st); break;
-    case 3: e = k2_launch_record<3>(c, a, s, st); break;
-    case 4: e = k2_launch_record<4>(c, a, s, st); break;
-    case 5: e = k2_launch_record<5>(c, a, s, st); break;
-    default: e = k2_launch_record<6>(c, a, s, st); break;
-  }
-  k1_count_launch(1);
-  if (e != cudaSuccess) return e;
-  cudaEventRecord(g_k2ev[2], st);
+  cudaError_t e = cudaSuccess;
   constexpr int RPW = 32 / (K2R_NG * K2R_GW);           // rows per warp of the group re-rank
-  const long rr_warps = (a.N + RPW - 1) / RPW;
-  k2_rerank_group_kernel<<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
-      a.data, c->d_grp, a.N, a.M, a.D, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr, a.listW,
-      a.counters, a.idx, a.diff, a.nfound);
-  k1_count_launch(1);
-  return cudaGetLastError();
+  const long pass = (long)K2R_R * K2_TM;                // rows per kernel pass (512)
+  int nsub = (int)(a.N / 1500000);                      // sub-batches of >= 1.5 M rows, at most 8
+  if (nsub < 1) nsub = 1;
+  if (nsub > 8) nsub = 8;
+  if (nsub > 1 && !g_k2aux) {
+    if ((e = cudaStreamCreateWithFlags(&g_k2aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int i = 0; i < 16; i++)
+      if ((e = cudaEventCreateWithFlags(&g_k2sub[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&g_k2join, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  const long per = ((a.N + nsub - 1) / nsub + pass - 1) / pass * pass;
+  if (nsub > 1) {                                       // the aux stream starts after everything queued so far
+    cudaEventRecord(g_k2join, st);
+    cudaStreamWaitEvent(g_k2aux, g_k2join, 0);
+  }
+  for (int i = 0; i < nsub; i++) {
+    const long row0 = i * per;
+    const long n = a.N - row0 < per ? a.N - row0 : per;
+    if (n <= 0) break;
+    switch (c->Kp / 16) {                               // K2R_MAX_KP / 16 = 6 unrolled issue loops
+      case 1: e = k2_launch_record<1>(c, a, s, row0, n, st); break;
+      case 2: e = k2_launch_record<2>(c, a, s, row0, n, st); break;
+      case 3: e = k2_launch_record<3>(c, a, s, row0, n, st); break;
+      case 4: e = k2_launch_record<4>(c, a, s, row0, n, st); break;
+      case 5: e = k2_launch_record<5>(c, a, s, row0, n, st); break;
+      default: e = k2_launch_record<6>(c, a, s, row0, n, st); break;
+    }
+    k1_count_launch(1);
+    if (e != cudaSuccess) return e;
+    cudaStream_t rr = st;
+    if (nsub > 1) {
+      cudaEventRecord(g_k2sub[i], st);
+      cudaStreamWaitEvent(g_k2aux, g_k2sub[i], 0);
+      rr = g_k2aux;
+    } else {
+      cudaEventRecord(g_k2ev[2], st);
+    }
+    const long rr_warps = (n + RPW - 1) / RPW;
+    k2_rerank_group_kernel<<<(unsigned)((rr_warps + 7) / 8), 256, 0, rr>>>(
+        a.data + row0 * a.D, c->d_grp, n, a.M, row0, a.D, a.flags + row0, s.rs + row0, (const CbStats *)c->d_norm,
+        s.cand + row0 * K2R_NG, s.thr + row0, a.listW, a.counters, a.idx + row0, a.diff + row0, a.nfound + row0);
+    k1_count_launch(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (nsub > 1) {
+    cudaEventRecord(g_k2ev[2], st);                     // end of the last GEMM (re-ranks of earlier sub-batches overlap it)
+    cudaEventRecord(g_k2join, g_k2aux);
+    cudaStreamWaitEvent(st, g_k2join, 0);
+  }
+  return cudaSuccess;
 }
 
 cudaError_t k2_last_kernel_ms(float out[4]) {
