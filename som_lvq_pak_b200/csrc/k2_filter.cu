@@ -46,7 +46,8 @@ constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, wa
 constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp (streaming kernel)
 
 constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel = epilogue groups = accumulators
-constexpr int K2R_BST = 3;        // staged code tiles
+constexpr int K2R_BST = 2;        // staged code tiles (3 measured no faster; 2 leave 60 KB of the SM's shared memory
+                                  // to the prep / re-rank blocks that run beside the GEMM CTA)
 constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM)
 constexpr int K2R_THREADS = 576;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA
 constexpr int K2R_GW = 4;         // candidate granularity: groups of 4 consecutive codes
@@ -206,7 +207,7 @@ constexpr int K2_PS = 32;     // components per row-prep slab
 
 // pack_bits: low mantissa bits the GEMM epilogue overwrites with the column index (0 or 8)
 __global__ void __launch_bounds__(256)
-k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restrict__ mask, long N,
+k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restrict__ mask, long N, long row0,
                    int D, int k, int pack_bits, const float *__restrict__ mean,
                    const CbStats *__restrict__ cst, __half *__restrict__ Aimg,
                    RowStats *__restrict__ rs, unsigned char *__restrict__ flags,
@@ -376,9 +377,9 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
       nfound[n] = 0;
       for (int t = 0; t < k; t++) { idx[n * k + t] = -1; diff[n * k + t] = (k == 1) ? -1.0f : FLT_MAX; }
     } else if (f & ROW_NONFINITE) {
-      listS[atomicAdd(&counters[1], 1)] = (int)n;
+      listS[atomicAdd(&counters[1], 1)] = (int)(row0 + n);      // list entries are rows of the whole call
     } else if (f & (ROW_TINY | ROW_MASKED | ROW_RANGE)) {
-      listW[atomicAdd(&counters[0], 1)] = (int)n;
+      listW[atomicAdd(&counters[0], 1)] = (int)(row0 + n);
     }
   }
 }
@@ -1148,11 +1149,25 @@ static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scra
   return cudaGetLastError();
 }
 
-// Large calls are cut into sub-batches: the re-rank of sub-batch i (L2-gather bound, no shared memory,
-// 36 registers) runs on a second stream beside the GEMM kernel of sub-batch i+1 (tensor / ALU bound,
-// 205 KB shared memory, 46 K registers), two re-rank blocks fit next to a GEMM CTA on every SM.
+static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratch &s, long row0, long n, int pack_bits,
+                                  cudaStream_t st) {
+  const long ntiles = (n + K2_TM - 1) / K2_TM;
+  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(
+      a.data + row0 * a.D, a.mask ? a.mask + row0 * a.D : nullptr, n, row0, a.D, a.k, pack_bits, c->d_norm + 16,
+      (const CbStats *)c->d_norm, s.Aimg + (size_t)row0 * c->Kp, s.rs + row0, a.flags + row0, a.listW, a.listS,
+      a.counters, a.idx + row0 * a.k, a.diff + row0 * a.k, a.nfound + row0);
+  k1_count_launch(1);
+  return cudaGetLastError();
+}
+
+// Record path (k == 1, short K).  Large calls are cut into sub-batches: while the GEMM kernel of
+// sub-batch i runs (tensor / ALU bound, 164 KB shared memory, 46 K registers per SM), a second stream
+// runs the re-rank of sub-batch i-1 (L2-gather bound, no shared memory, 36 registers), two blocks of
+// which fit next to the GEMM CTA on every SM.  Measured on C3: 15.7 -> 14.5 ms per step.  Running the
+// row prep of sub-batch i+1 beside the GEMM as well was measured and rejected (15.0 - 15.9 ms): the prep
+// kernel is issue bound and takes more from the GEMM's epilogue than its own 1 ms.
 static cudaStream_t g_k2aux = nullptr;
-static cudaEvent_t g_k2sub[16], g_k2join = nullptr;
+static cudaEvent_t g_k2sub[8], g_k2join = nullptr;
 
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
@@ -1163,18 +1178,21 @@ static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch
   if (nsub > 8) nsub = 8;
   if (nsub > 1 && !g_k2aux) {
     if ((e = cudaStreamCreateWithFlags(&g_k2aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    for (int i = 0; i < 16; i++)
+    for (int i = 0; i < 8; i++)
       if ((e = cudaEventCreateWithFlags(&g_k2sub[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&g_k2join, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
   const long per = ((a.N + nsub - 1) / nsub + pass - 1) / pass * pass;
-  if (nsub > 1) {                                       // the aux stream starts after everything queued so far
+  auto rows_of = [&](int i) { const long r0 = i * per; return a.N - r0 < per ? a.N - r0 : per; };
+  // row prep of the whole call first; the aux stream starts behind everything queued so far
+  if ((e = k2_launch_prep(c, a, s, 0, a.N, 0, st)) != cudaSuccess) return e;
+  cudaEventRecord(g_k2ev[1], st);
+  if (nsub > 1) {
     cudaEventRecord(g_k2join, st);
     cudaStreamWaitEvent(g_k2aux, g_k2join, 0);
   }
   for (int i = 0; i < nsub; i++) {
-    const long row0 = i * per;
-    const long n = a.N - row0 < per ? a.N - row0 : per;
+    const long row0 = i * per, n = rows_of(i);
     if (n <= 0) break;
     switch (c->Kp / 16) {                               // K2R_MAX_KP / 16 = 6 unrolled issue loops
       case 1: e = k2_launch_record<1>(c, a, s, row0, n, st); break;
@@ -1253,14 +1271,13 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
 
   if ((e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[0], st);
-  k2_row_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, record ? 0 : 8,
-                                                      c->d_norm + 16, (const CbStats *)c->d_norm, s.Aimg,
-                                                      s.rs, a.flags, a.listW, a.listS, a.counters, a.idx,
-                                                      a.diff, a.nfound);
-  k1_count_launch(1);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  cudaEventRecord(g_k2ev[1], st);
-  if (record) e = k2_run_record(c, a, s, st);
+  if (record) {
+    e = k2_run_record(c, a, s, st);                     // prep, GEMM and re-rank, pipelined over sub-batches
+  } else {
+    if ((e = k2_launch_prep(c, a, s, 0, a.N, 8, st)) != cudaSuccess) return e;
+    cudaEventRecord(g_k2ev[1], st);
+  }
+  if (record) {}
   else if (a.k == 1) e = k2_run_stream<4, 3>(c, a, s, st);
   else if (a.k <= 5) e = k2_run_stream<10, 4>(c, a, s, st);
   else e = k2_run_stream<20, 4>(c, a, s, st);
