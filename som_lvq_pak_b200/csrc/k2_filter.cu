@@ -846,7 +846,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 // row; the group leader then orders the candidates and evaluates the certificate.
 template <int TG, int LPR>
 __global__ void __launch_bounds__(256)
-k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M, int D,
+k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes, long N, long M, long row0, int D,
                  int k, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
                  const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
                  const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
@@ -926,7 +926,7 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
   if (M <= TG && nc == (int)M) ok = true;          // every code is a candidate: nothing to certify
   if (ok && k == 1 && !(cd[0] < FLT_MAX)) ok = false;
   if (!ok) {
-    listW[atomicAdd(&counters[0], 1)] = (int)n;
+    listW[atomicAdd(&counters[0], 1)] = (int)(row0 + n);     // the other arrays are passed pre-offset by row0
     atomicAdd(&counters[3], 1);
     return;
   }
@@ -1093,13 +1093,37 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
 static cudaEvent_t g_k2ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 static bool g_k2ev_valid = false;
 
+// Sub-batch pipeline shared by both GEMM kernels: the re-rank of sub-batch i runs on a second stream
+// beside the GEMM kernel of sub-batch i+1 (see k2_run_record).
+static cudaStream_t g_k2aux = nullptr;
+static cudaEvent_t g_k2sub[8], g_k2join = nullptr;
+
+static cudaError_t k2_pipeline_init() {
+  cudaError_t e;
+  if (g_k2aux) return cudaSuccess;
+  if ((e = cudaStreamCreateWithFlags(&g_k2aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  for (int i = 0; i < 8; i++)
+    if ((e = cudaEventCreateWithFlags(&g_k2sub[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+  return cudaEventCreateWithFlags(&g_k2join, cudaEventDisableTiming);
+}
+// Sub-batches of WHOLE waves of the persistent kernel (passes = a multiple of the SM count, so no
+// sub-batch ends with a partly filled wave), at least ~16 waves each and at most 8 of them.
+// Returns the number of sub-batches and the passes per sub-batch.
+static int k2_subbatches(long passes, int num_sms, long *passes_per) {
+  const long waves = (passes + num_sms - 1) / num_sms;
+  long n = waves / 16;
+  n = n < 1 ? 1 : (n > 8 ? 8 : n);
+  *passes_per = (waves + n - 1) / n * num_sms;
+  return (int)n;
+}
+
 template <int TG>
-static cudaError_t k2_run_rerank(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+static cudaError_t k2_run_rerank(K2Codebook *c, const K1Args &a, const K2Scratch &s, long row0, long n, cudaStream_t st) {
   constexpr int LPR = TG <= 4 ? 4 : (TG <= 16 ? 16 : 32);
-  const long rr_warps = (a.N + (32 / LPR) - 1) / (32 / LPR);
+  const long rr_warps = (n + (32 / LPR) - 1) / (32 / LPR);
   k2_rerank_kernel<TG, LPR><<<(unsigned)((rr_warps + 7) / 8), 256, 0, st>>>(
-      a.data, a.codes, a.N, a.M, a.D, a.k, a.flags, s.rs, (const CbStats *)c->d_norm, s.cand, s.thr,
-      a.listW, a.counters, a.idx, a.diff, a.nfound);
+      a.data + row0 * a.D, a.codes, n, a.M, row0, a.D, a.k, a.flags + row0, s.rs + row0, (const CbStats *)c->d_norm,
+      s.cand + row0 * TG, s.thr + row0, a.listW, a.counters, a.idx + row0 * a.k, a.diff + row0 * a.k, a.nfound + row0);
   k1_count_launch(1);
   return cudaGetLastError();
 }
@@ -1111,14 +1135,41 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
   const size_t smem = K2Smem::bytes(Kp, a_res);
   cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long ntiles = (a.N + K2_TM - 1) / K2_TM;
-  const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
-  k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg, (const __half *)c->d_ops, s.rs, a.N, a.M, Kp,
-                                                        a_res ? 1 : 0, a.k, s.cand, s.thr);
-  k1_count_launch(1);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  cudaEventRecord(g_k2ev[2], st);
-  return k2_run_rerank<TG>(c, a, s, st);
+  const long ntiles_all = (a.N + K2_TM - 1) / K2_TM;
+  long passes_per;
+  const int nsub = k2_subbatches(ntiles_all, a.num_sms, &passes_per);
+  if (nsub > 1 && (e = k2_pipeline_init()) != cudaSuccess) return e;
+  const long per = passes_per * K2_TM;
+  if (nsub > 1) {
+    cudaEventRecord(g_k2join, st);
+    cudaStreamWaitEvent(g_k2aux, g_k2join, 0);
+  }
+  for (int i = 0; i < nsub; i++) {
+    const long row0 = i * per, n = a.N - row0 < per ? a.N - row0 : per;
+    if (n <= 0) break;
+    const long ntiles = (n + K2_TM - 1) / K2_TM;
+    const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
+    k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg + (size_t)row0 * Kp, (const __half *)c->d_ops,
+                                                          s.rs + row0, n, a.M, Kp, a_res ? 1 : 0, a.k,
+                                                          s.cand + row0 * TG, s.thr + row0);
+    k1_count_launch(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    cudaStream_t rr = st;
+    if (nsub > 1) {
+      cudaEventRecord(g_k2sub[i], st);
+      cudaStreamWaitEvent(g_k2aux, g_k2sub[i], 0);
+      rr = g_k2aux;
+    } else {
+      cudaEventRecord(g_k2ev[2], st);
+    }
+    if ((e = k2_run_rerank<TG>(c, a, s, row0, n, rr)) != cudaSuccess) return e;
+  }
+  if (nsub > 1) {
+    cudaEventRecord(g_k2ev[2], st);
+    cudaEventRecord(g_k2join, g_k2aux);
+    cudaStreamWaitEvent(st, g_k2join, 0);
+  }
+  return cudaSuccess;
 }
 
 // staged code tiles: as many as fit next to the four resident row tiles (3 up to K = 80, 2 at K = 96)
@@ -1166,23 +1217,14 @@ static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratc
 // which fit next to the GEMM CTA on every SM.  Measured on C3: 15.7 -> 14.5 ms per step.  Running the
 // row prep of sub-batch i+1 beside the GEMM as well was measured and rejected (15.0 - 15.9 ms): the prep
 // kernel is issue bound and takes more from the GEMM's epilogue than its own 1 ms.
-static cudaStream_t g_k2aux = nullptr;
-static cudaEvent_t g_k2sub[8], g_k2join = nullptr;
-
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
   constexpr int RPW = 32 / (K2R_NG * K2R_GW);           // rows per warp of the group re-rank
   const long pass = (long)K2R_R * K2_TM;                // rows per kernel pass (512)
-  int nsub = (int)(a.N / 1500000);                      // sub-batches of >= 1.5 M rows, at most 8
-  if (nsub < 1) nsub = 1;
-  if (nsub > 8) nsub = 8;
-  if (nsub > 1 && !g_k2aux) {
-    if ((e = cudaStreamCreateWithFlags(&g_k2aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    for (int i = 0; i < 8; i++)
-      if ((e = cudaEventCreateWithFlags(&g_k2sub[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&g_k2join, cudaEventDisableTiming)) != cudaSuccess) return e;
-  }
-  const long per = ((a.N + nsub - 1) / nsub + pass - 1) / pass * pass;
+  long passes_per;
+  const int nsub = k2_subbatches((a.N + pass - 1) / pass, a.num_sms, &passes_per);
+  if (nsub > 1 && (e = k2_pipeline_init()) != cudaSuccess) return e;
+  const long per = passes_per * pass;
   auto rows_of = [&](int i) { const long r0 = i * per; return a.N - r0 < per ? a.N - r0 : per; };
   // row prep of the whole call first; the aux stream starts behind everything queued so far
   if ((e = k2_launch_prep(c, a, s, 0, a.N, 0, st)) != cudaSuccess) return e;
