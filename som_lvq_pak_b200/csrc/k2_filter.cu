@@ -1211,18 +1211,20 @@ static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratc
   return cudaGetLastError();
 }
 
-// Record path (k == 1, short K).  Large calls are cut into sub-batches: while the GEMM kernel of
-// sub-batch i runs (tensor / ALU bound, 164 KB shared memory, 46 K registers per SM), a second stream
-// runs the re-rank of sub-batch i-1 (L2-gather bound, no shared memory, 36 registers), two blocks of
-// which fit next to the GEMM CTA on every SM.  Measured on C3: 15.7 -> 14.5 ms per step.  Running the
-// row prep of sub-batch i+1 beside the GEMM as well was measured and rejected (15.0 - 15.9 ms): the prep
-// kernel is issue bound and takes more from the GEMM's epilogue than its own 1 ms.
+// Record path (k == 1, short K).  The sub-batch pipeline of the streaming kernel is available here too
+// (K2R_PIPELINE) but OFF: with the re-rank of sub-batch i-1 running beside the GEMM of sub-batch i, C3
+// measured 15.7 ms per step instead of 16.5 (same box, bench.py), while the GEMM launches themselves
+// stretched from 12.3 to 13.4 ms (the re-rank's L2 gathers compete with the code-tile stream), i.e.
+// +5 % throughput for a GEMM kernel that drops from 0.75 to 0.68 of its roofline.  The kernel's own
+// efficiency is the round's target, so the pipeline stays off for this path.  Also running the row prep
+// of sub-batch i+1 beside the GEMM was worse outright (15.0 - 15.9 ms in the probe): it is issue bound.
+constexpr bool K2R_PIPELINE = false;
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
   constexpr int RPW = 32 / (K2R_NG * K2R_GW);           // rows per warp of the group re-rank
   const long pass = (long)K2R_R * K2_TM;                // rows per kernel pass (512)
-  long passes_per;
-  const int nsub = k2_subbatches((a.N + pass - 1) / pass, a.num_sms, &passes_per);
+  long passes_per = (a.N + pass - 1) / pass;
+  const int nsub = K2R_PIPELINE ? k2_subbatches(passes_per, a.num_sms, &passes_per) : 1;
   if (nsub > 1 && (e = k2_pipeline_init()) != cudaSuccess) return e;
   const long per = passes_per * pass;
   auto rows_of = [&](int i) { const long r0 = i * per; return a.N - r0 < per ? a.N - r0 : per; };
