@@ -339,10 +339,8 @@ def main_gpu(args, w):
                     "note": "algorithmic 2*M*D flop per search over the live CUDA-event duration of %s vs the "
                             "sustained fp16/bf16 cuBLAS peak (%s); the kernel issues %.2fx that many MMA flops "
                             "(K %d -> %d: 3 norm columns + padding to 16; M %d -> %d), so the tensor pipe itself "
-                            "runs at %.3f of that peak.  The call is cut into sub-batches and the duration is taken from "
-                            "the first GEMM launch to the end of the last one, with the re-rank kernels of earlier "
-                            "sub-batches running beside it on a second stream.  traffic = ncu dram bytes of the "
-                            "GEMM launches of one step (profiles/), null when no capture exists for this shape"
+                            "runs at %.3f of that peak.  traffic = ncu dram bytes of one launch (profiles/), "
+                            "null when no capture exists for this shape"
                             % (kname, "measured" if "bf16_tflops_sustained" in peaks else "fallback",
                                (kp / D) * (m_pad / M), D, kp, M, m_pad, issued / peak),
                     "mma_issued_tflops": issued,
