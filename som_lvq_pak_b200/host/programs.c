@@ -17,7 +17,7 @@
  *   pick_inside_codes           lvq_rout.c:151-211    bmu_search (k) of the data set against itself (eveninit / propinit)
  *
  * Not carried over (outside SURVEY.md section 8): -buffer (files are loaded whole), -selfuncs,
- * snapshots, compressed / piped file names.
+ * background (forked) snapshots, compressed / piped file names.
  */
 #include "somhost.h"
 
@@ -56,8 +56,8 @@ static void global_options(int argc, char **argv) {                     /* lvq_p
   if (s) pak_mask_string = s;
   s = opt(argc, argv, "-v");
   verbose_level = s ? atoi(s) : 1;
-  if (opt(argc, argv, "-buffer") || opt(argc, argv, "-selfuncs") || opt(argc, argv, "-snapinterval"))
-    fprintf(stderr, "note: -buffer, -selfuncs and snapshots are not supported by the B200 host; ignored\n");
+  if (opt(argc, argv, "-buffer") || opt(argc, argv, "-selfuncs"))
+    fprintf(stderr, "note: -buffer and -selfuncs are not supported by the B200 host; ignored\n");
 }
 
 static void lra_name(const char *codefile, char *out, size_t outsz);
@@ -548,6 +548,69 @@ static int32_t *sample_order(int argc, char **argv, long n) {
   return order;
 }
 
+/* ---- snapshots (lvq_pak.c:663-764, som_rout.c:650-658): every `interval` steps the codebook is
+ * written out.  The resident trainer (bmu_trainer_*) keeps data and codebook on the device between
+ * the chunks of steps, so a snapshot costs one download of the codebook. */
+struct snap {
+  long interval;           /* 0 = none */
+  const char *pattern;     /* file name, may hold one %d / %ld for the iteration */
+  int keepopen;            /* -snaptype keepopen: all snapshots in one file between #start n / #end */
+  FILE *fp;
+  int counter;
+};
+static int snap_setup(struct snap *sn, int argc, char **argv, const char *default_name) {
+  const char *s = opt(argc, argv, "-snapinterval");
+  memset(sn, 0, sizeof *sn);
+  sn->interval = s ? atol(s) : 0;
+  if (!sn->interval) return 0;
+  sn->pattern = opt(argc, argv, "-snapfile");
+  if (!sn->pattern) {
+    sn->pattern = default_name;
+    fprintf(stderr, "snapshot file not specified, using '%s'", default_name);
+  }
+  s = opt(argc, argv, "-snaptype");
+  if (s && strcasecmp(s, "keepopen") == 0) sn->keepopen = 1;
+  else if (s && strcasecmp(s, "file") != 0) fprintf(stderr, "note: snapshot type %s is written synchronously\n", s);
+  return 0;
+}
+static int snap_save(struct snap *sn, const struct pak_entries *codes, long iter, long length) {
+  FILE *fp = sn->fp;
+  long i, l;
+  int c;
+  sn->counter++;
+  if (!fp) {
+    char name[1024];
+    snprintf(name, sizeof name, sn->pattern, iter);
+    fp = fopen(name, "w");
+    if (!fp) return 1;
+    if (sn->keepopen) sn->fp = fp;
+  }
+  if (sn->keepopen) fprintf(fp, "#start %d\n", sn->counter);
+  pak_write_header(fp, codes);
+  fprintf(fp, "#SNAPSHOT FILE\n#iterations: %ld/%ld\n", iter, length);
+  for (i = 0; i < codes->n; i++) {
+    const float *pt = codes->points + (size_t)i * codes->dim;
+    const unsigned char *mk = codes->mask ? codes->mask + (size_t)i * codes->dim : NULL;
+    for (c = 0; c < codes->dim; c++) {
+      if (mk && mk[c]) fprintf(fp, "%s ", pak_mask_string);
+      else fprintf(fp, "%g ", pt[c]);
+    }
+    for (l = codes->lab_off[i]; l < codes->lab_off[i + 1]; l++) fprintf(fp, "%s ", label_string(codes->lab_pool[l]));
+    fprintf(fp, "\n");
+  }
+  if (sn->keepopen) { fprintf(fp, "#end\n"); fflush(fp); }
+  else fclose(fp);
+  return 0;
+}
+/* first step index >= from after which a snapshot is due (le % interval == 0 && le > 0), or -1 */
+static long snap_next(const struct snap *sn, long from, long length) {
+  long le;
+  if (!sn->interval) return -1;
+  le = from < 1 ? 1 : from;
+  le = (le + sn->interval - 1) / sn->interval * sn->interval;
+  return le < length ? le : -1;
+}
+
 int vsom_main(int argc, char **argv) {
   struct pak_entries *data = NULL, *codes = NULL;
   const char *cout_name;
@@ -556,6 +619,7 @@ int vsom_main(int argc, char **argv) {
   int alpha_type, use_fixed, use_weights, rc;
   int32_t *order, *sample;
   float *talp, *trad;
+  struct snap sn;
   global_options(argc, argv);
   cout_name = need(argc, argv, "-cout");
   length = atol(need(argc, argv, "-rlen"));
@@ -565,6 +629,7 @@ int vsom_main(int argc, char **argv) {
   use_weights = flag(argc, argv, "-weights");
   if (alpha_type_of(argc, argv, &alpha_type)) return 1;
   if (open_pair(argc, argv, 0, 0, 1, 1, &data, &codes)) return 1;
+  snap_setup(&sn, argc, argv, cout_name);
   if (length > 0 && data->n > 0) {
     order = sample_order(argc, argv, data->n);
     sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)length);
@@ -573,10 +638,29 @@ int vsom_main(int argc, char **argv) {
     if (!sample || !talp || !trad) { fprintf(stderr, "out of memory\n"); return 1; }
     bmu_som_schedule(0, length, length, alpha, radius, alpha_type, data->n, order,
                      use_weights ? data->weight : NULL, sample, talp, trad);
-    rc = bmu_som_train(codes->points, codes->n, codes->dim, codes->xdim, codes->ydim, codes->topol, codes->neigh,
-                       data->points, data->mask, data->n, use_fixed ? data->fixed_xy : NULL, sample, talp, trad,
-                       length);
-    if (rc) return engine_failed("bmu_som_train");
+    if (!sn.interval) {
+      rc = bmu_som_train(codes->points, codes->n, codes->dim, codes->xdim, codes->ydim, codes->topol, codes->neigh,
+                         data->points, data->mask, data->n, use_fixed ? data->fixed_xy : NULL, sample, talp, trad,
+                         length);
+      if (rc) return engine_failed("bmu_som_train");
+    } else {
+      bmu_trainer *t = bmu_trainer_create(codes->points, codes->n, codes->dim, data->points, data->mask, data->n);
+      long le0 = 0;
+      if (!t || bmu_trainer_set_som(t, codes->xdim, codes->ydim, codes->topol, codes->neigh,
+                                    use_fixed ? data->fixed_xy : NULL))
+        return engine_failed("bmu_trainer");
+      while (le0 < length) {
+        const long due = snap_next(&sn, le0, length), le1 = due >= 0 ? due + 1 : length;
+        if (bmu_trainer_steps(t, sample + le0, talp + le0, trad + le0, le1 - le0)) return engine_failed("bmu_trainer_steps");
+        if (due >= 0) {
+          if (bmu_trainer_get_codes(t, codes->points)) return engine_failed("bmu_trainer_get_codes");
+          if (snap_save(&sn, codes, due, length)) fprintf(stderr, "snapshot failed, continuing teaching\n");
+        }
+        le0 = le1;
+      }
+      if (bmu_trainer_get_codes(t, codes->points)) return engine_failed("bmu_trainer_get_codes");
+      bmu_trainer_destroy(t);
+    }
     free(order); free(sample); free(talp); free(trad);
   }
   pak_save(codes, cout_name);
@@ -600,6 +684,7 @@ int lvqtrain_main(int argc, char **argv, const char *progname) {
   float alpha = 0.0f, winlen = 0.0f, epsilon = 0.0f, win_thr = 0.0f, *talp, *unit_alpha = NULL;
   int algo, alpha_type, rc;
   int32_t *order, *sample, *code_label, *data_label;
+  struct snap sn;
   char lra[2048];
   global_options(argc, argv);
   s = opt(argc, argv, "-type");
@@ -656,9 +741,29 @@ int lvqtrain_main(int argc, char **argv, const char *progname) {
     talp = (float *)malloc(sizeof(float) * (size_t)length);
     if (!sample || !talp) { fprintf(stderr, "out of memory\n"); return 1; }
     bmu_lvq_schedule(0, length, length, alpha, alpha_type, data->n, order, sample, talp);
-    rc = bmu_lvq_train(algo, codes->points, code_label, codes->n, codes->dim, data->points, data->mask, data_label,
-                       data->n, sample, talp, length, win_thr, epsilon, alpha, unit_alpha);
-    if (rc) return engine_failed("bmu_lvq_train");
+    snap_setup(&sn, argc, argv, cout_name);
+    if (!sn.interval) {
+      rc = bmu_lvq_train(algo, codes->points, code_label, codes->n, codes->dim, data->points, data->mask, data_label,
+                         data->n, sample, talp, length, win_thr, epsilon, alpha, unit_alpha);
+      if (rc) return engine_failed("bmu_lvq_train");
+    } else {                                                         /* lvq_rout.c:560-568 and alike */
+      bmu_trainer *t = bmu_trainer_create(codes->points, codes->n, codes->dim, data->points, data->mask, data->n);
+      long le0 = 0;
+      if (!t || bmu_trainer_set_lvq(t, algo, code_label, data_label, win_thr, epsilon, alpha, unit_alpha))
+        return engine_failed("bmu_trainer");
+      while (le0 < length) {
+        const long due = snap_next(&sn, le0, length), le1 = due >= 0 ? due + 1 : length;
+        if (bmu_trainer_steps(t, sample + le0, talp + le0, NULL, le1 - le0)) return engine_failed("bmu_trainer_steps");
+        if (due >= 0) {
+          if (bmu_trainer_get_codes(t, codes->points)) return engine_failed("bmu_trainer_get_codes");
+          if (snap_save(&sn, codes, due, length)) fprintf(stderr, "snapshot failed\n");
+        }
+        le0 = le1;
+      }
+      if (bmu_trainer_get_codes(t, codes->points)) return engine_failed("bmu_trainer_get_codes");
+      if (algo == BMU_OLVQ1 && bmu_trainer_get_unit_alpha(t, unit_alpha)) return engine_failed("bmu_trainer_get_unit_alpha");
+      bmu_trainer_destroy(t);
+    }
     free(order); free(sample); free(talp);
   }
   if (algo == BMU_OLVQ1) {                                          /* lvq_rout.c:694, datafile.c:1061-1086 */

@@ -52,6 +52,19 @@ def main():
     out["propinit_cod"] = np.array(open(os.path.join(td, "p.cod")).read())
     run([b("eveninit"), "-din", "ex2.dat", "-cout", "e2.cod", "-noc", "317"], td)
     out["eveninit2_cod"] = np.array(open(os.path.join(td, "e2.cod")).read())
+    # snapshots (som_rout.c:650-658, lvq_pak.c:663-764): one file per snapshot, and -snaptype keepopen
+    open(os.path.join(td, "ex.dat"), "w").write(str(demo["in_ex.dat"]))
+    open(os.path.join(td, "ex.cod"), "w").write(str(demo["som_init_cod"]))
+    run([b("vsom"), "-din", "ex.dat", "-cin", "ex.cod", "-cout", "sn.cod", "-rlen", "1000", "-alpha", "0.05",
+         "-radius", "10", "-snapinterval", "300", "-snapfile", "snap_%d.cod"], td)
+    for it in (300, 600, 900):
+        out["snap_%d" % it] = np.array(open(os.path.join(td, "snap_%d.cod" % it)).read())
+    out["snap_final"] = np.array(open(os.path.join(td, "sn.cod")).read())
+    open(os.path.join(td, "ex1o.cod"), "w").write(str(demo["lvq_o_cod"]))
+    run([b("lvq1"), "-din", "ex1.dat", "-cin", "ex1o.cod", "-cout", "l.cod", "-alpha", "0.05", "-rlen", "2500",
+         "-snapinterval", "1000", "-snapfile", "lsnap.txt", "-snaptype", "keepopen"], td)
+    out["lvq_snap_keepopen"] = np.array(open(os.path.join(td, "lsnap.txt")).read())
+    out["lvq_snap_final"] = np.array(open(os.path.join(td, "l.cod")).read())
     # vfind: 4 trials of a 6x4 map on ex.dat (answers on stdin, vfind.c:138-185), both qerror types
     open(os.path.join(td, "ex.dat"), "w").write(str(demo["in_ex.dat"]))
     for tag, extra in (("vfind", []), ("vfind_q1", ["-qetype", "1", "-alpha_type", "inverse_t"])):
