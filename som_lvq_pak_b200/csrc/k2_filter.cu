@@ -1316,15 +1316,14 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   if ((e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[0], st);
   if (record) {
-    e = k2_run_record(c, a, s, st);                     // prep, GEMM and re-rank, pipelined over sub-batches
+    e = k2_run_record(c, a, s, st);                     // row prep, record GEMM, group re-rank
   } else {
     if ((e = k2_launch_prep(c, a, s, 0, a.N, 8, st)) != cudaSuccess) return e;
     cudaEventRecord(g_k2ev[1], st);
+    if (a.k == 1) e = k2_run_stream<4, 3>(c, a, s, st);
+    else if (a.k <= 5) e = k2_run_stream<10, 4>(c, a, s, st);
+    else e = k2_run_stream<20, 4>(c, a, s, st);
   }
-  if (record) {}
-  else if (a.k == 1) e = k2_run_stream<4, 3>(c, a, s, st);
-  else if (a.k <= 5) e = k2_run_stream<10, 4>(c, a, s, st);
-  else e = k2_run_stream<20, 4>(c, a, s, st);
   if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[3], st);
   // rows that failed the certificate + masked / tiny rows, then the non-finite rows

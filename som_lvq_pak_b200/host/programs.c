@@ -1058,7 +1058,6 @@ int eveninit_main(int argc, char **argv, const char *progname) {
   for (c = 0; c < nol; c++) if (classes.freq[c] == 0) emp++;
   if (npicked < noc) {                                             /* eveninit.c:116-143: second pass */
     float frac = 0.0f, err = 0.0f;
-    long first = npicked;
     if (emp != 0) frac = (noc - npicked) / (float)emp;
     for (c = 0; c < nol; c++) {
       if (classes.freq[c] == 0) {
@@ -1069,7 +1068,6 @@ int eveninit_main(int argc, char **argv, const char *progname) {
       }
     }
     pick_inside(data, inside, &classes, picked, &npicked);
-    (void)first;
   }
   out = pak_alloc(data->dim, npicked);
   if (!out) return 1;
