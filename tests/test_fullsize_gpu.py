@@ -103,3 +103,26 @@ def test_c5_schedule_prefix(engine, oracle):
     np.testing.assert_allclose(got, exp, rtol=1e-6, atol=0)
     nbad = int((got.view(np.int32) != exp.view(np.int32)).sum())
     assert nbad <= got.size // 1_000_000 + 4, "%d of %d floats differ" % (nbad, got.size)
+
+
+def test_host_pointer_search_through_filter_path(engine, oracle):
+    """bmu_search() with host buffers: 2.3 M x 64 rows are cut into three 256 MB chunks whose copies
+    overlap the kernels; every chunk goes through the tensor-core filter.  A sample must agree with
+    the oracle bit for bit and the chunk seams must not lose or duplicate rows."""
+    rng = np.random.default_rng(9)
+    N, D, M = 2_300_003, 64, 3000
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    idx, diff, nf = engine.find_winner_euc(codes, data)            # AUTO -> K2 (M >= 512, N >= 4096)
+    bd = engine.last_search_breakdown()
+    assert bd["k2_certified"] > 0
+    assert (nf == 1).all() and idx.min() >= 0 and idx.max() < M
+    seam = 1_048_576                                               # rows per 256 MB chunk at D = 64
+    sub = np.r_[0:300, seam - 150:seam + 150, 2 * seam - 150:2 * seam + 150, N - 300:N]
+    e = oracle.search(codes, data[sub], 1)
+    assert_bits_equal(idx[sub], e[0])
+    assert_bits_equal(diff[sub], e[1])
+    # every reported distance is the exact distance to the reported code (float64 check on a sample)
+    s = rng.integers(0, N, 2000)
+    d64 = ((data[s].astype(np.float64) - codes[idx[s, 0]].astype(np.float64)) ** 2).sum(-1)
+    assert np.allclose(d64, diff[s, 0], rtol=1e-5)
