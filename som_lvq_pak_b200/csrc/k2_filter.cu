@@ -49,7 +49,8 @@ constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel
 constexpr int K2R_BST = 2;        // staged code tiles (3 measured no faster; 2 leave 60 KB of the SM's shared memory
                                   // to the prep / re-rank blocks that run beside the GEMM CTA)
 constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM)
-constexpr int K2R_THREADS = 576;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA
+constexpr int K2R_THREADS = 704;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA,
+                                  // warps 18-21 exact re-rank of the pass the epilogue finished before
 constexpr int K2R_GW = 4;         // candidate granularity: groups of 4 consecutive codes
 constexpr int K2R_NG = 2;         // candidate groups kept per row
 constexpr int K2R_MAX_KP = 96;    // code tile (256 x Kp fp16) <= 48 KB
@@ -670,11 +671,98 @@ __device__ __forceinline__ uint32_t k2r_idesc() {
 // records the GROUP holding the minimum; the exact distances of the <= 2 x 8 codes of the
 // recorded groups are computed by k2_rerank_group_kernel.  Invariant for the certificate: a
 // group that is not recorded has a minimum >= min(final best + delta, lost).
+// Exact re-rank of ONE row inside the record kernel (one thread): the reference's sum (lvq_pak.c:63-73)
+// over the <= 2 x K2R_GW codes of the recorded groups, first-minimum rule (lvq_pak.c:79), then the
+// certificate.  Returns false when the row has to be answered by the exact kernel K1.
+struct K2RRerankArgs {
+  const float *data, *grp;
+  const unsigned char *flags;
+  const RowStats *rs;
+  const CbStats *cst;
+  int *listW, *counters;
+  int32_t *idx, *nfound;
+  float *diff;
+  long N, M;
+  int D;
+};
+__device__ __forceinline__ void k2r_rerank_row(const K2RRerankArgs &A, long n, int g0, int g1, float thr) {
+  if (n >= A.N || A.flags[n] != 0) return;               // flagged rows are answered by K1 (lists)
+  const int D = A.D, Dq = (D + 3) / 4;
+  const float *x = A.data + n * (long)D;
+  float dbest = INFINITY;
+  int jbest = -1;
+#pragma unroll 1
+  for (int gsel = 0; gsel < K2R_NG; gsel++) {
+    const int gfirst = gsel ? g1 : g0;
+    if (gfirst < 0) continue;
+    const float4 *c4 = reinterpret_cast<const float4 *>(A.grp) + ((long)(gfirst / K2R_GW) * Dq) * K2R_GW;
+    float acc[K2R_GW];
+#pragma unroll
+    for (int l = 0; l < K2R_GW; l++) acc[l] = 0.0f;
+    if ((D & 3) == 0) {
+      const float4 *x4 = reinterpret_cast<const float4 *>(x);
+#pragma unroll 2
+      for (int i = 0; i < Dq; i++) {
+        const float4 xv = __ldg(x4 + i);
+#pragma unroll
+        for (int l = 0; l < K2R_GW; l++) {
+          const float4 cv = __ldg(c4 + i * K2R_GW + l);
+          acc[l] = sq_acc(acc[l], cv.x, xv.x);           // component order, one rounding per operation
+          acc[l] = sq_acc(acc[l], cv.y, xv.y);
+          acc[l] = sq_acc(acc[l], cv.z, xv.z);
+          acc[l] = sq_acc(acc[l], cv.w, xv.w);
+        }
+      }
+    } else {
+      for (int i = 0; i < Dq; i++) {
+#pragma unroll
+        for (int l = 0; l < K2R_GW; l++) {
+          const float4 cv = __ldg(c4 + i * K2R_GW + l);
+          const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (4 * i + e < D) acc[l] = sq_acc(acc[l], cc[e], __ldg(x + 4 * i + e));
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < K2R_GW; l++) {
+      const int j = gfirst + l;
+      // only d < FLT_MAX can win; equal distances: the lower index
+      if (j < A.M && acc[l] < FLT_MAX && (acc[l] < dbest || (acc[l] == dbest && j < jbest))) { dbest = acc[l]; jbest = j; }
+    }
+  }
+  bool ok = false;
+  if (jbest >= 0) {
+    // in scaled units every code outside the candidate groups has ||s x' - s m'||^2 >= nx2 + thr - E
+    const RowStats s = A.rs[n];
+    const CbStats cs = *A.cst;
+    const double Lc = s.nx2 + (double)thr - (double)s.E;
+    const double eta = ldexp((double)s.nx + (double)cs.nm, -23);
+    if (Lc > 0.0) {
+      const double r = sqrt(Lc) - eta;
+      if (r > 0.0) {
+        const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;
+        const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6) * (double)cs.inv_s2;
+        ok = (double)dbest < L;
+      }
+    }
+  }
+  if (!ok) {
+    A.listW[atomicAdd(&A.counters[0], 1)] = (int)n;
+    atomicAdd(&A.counters[3], 1);
+    return;
+  }
+  atomicAdd(&A.counters[2], 1);
+  A.idx[n] = jbest;
+  A.diff[n] = dbest;
+  A.nfound[n] = 1;
+}
+
 template <int R, int NK>
 __global__ void __launch_bounds__(K2R_THREADS, 1)
 k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
-              const RowStats *__restrict__ rs, long N, long M, int Kp, int nst,
-              int32_t *__restrict__ cand, float *__restrict__ thr) {
+              const RowStats *__restrict__ rs, long N, long M, int Kp, int nst, const K2RRerankArgs RA) {
   static_assert(R == 4, "one epilogue group and one 128-column accumulator per row tile");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t a_tile_bytes = (uint32_t)K2_TM * Kp * 2, b_tile_bytes = (uint32_t)K2_TN * Kp * 2;
@@ -684,7 +772,9 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
   uint64_t *full = bars, *empty = bars + K2R_BST;
   uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + R;
   uint64_t *afull = tempty + R, *aempty = afull + 1;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(aempty + 1);
+  uint64_t *rfull = aempty + 1, *rempty = rfull + 2;               // hand-off to the re-rank warps, double buffered
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(rempty + 2);
+  int4 *hand = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [2][R * 128] {g0, g1, thr, -}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long ntiles = (N + K2_TM - 1) / K2_TM;
@@ -696,6 +786,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
     for (int b = 0; b < R; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     mbar_init(afull, 1);
     mbar_init(aempty, 1);
+    for (int b = 0; b < 2; b++) { mbar_init(&rfull[b], 16); mbar_init(&rempty[b], 4); }
     fence_barrier_init();
   }
   if (warp == 17) {
@@ -771,13 +862,31 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
       if (leader) umma_commit(aempty);
       __syncwarp();
     }
+  } else if (warp >= 18) {
+    // ===================== exact re-rank of the pass the epilogue handed over =====================
+    // 128 threads, 4 rows each (one per row tile of the pass).  FMA-pipe work (sub, mul, add) on rows
+    // fetched through L2, beside an epilogue that is bound by the ALU pipe: it costs the GEMM almost
+    // nothing and replaces a separate kernel that re-read candidates, thresholds and row statistics.
+    const int t = threadIdx.x - 18 * 32;                  // 0 .. 127
+    unsigned cnt = 0;
+    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, cnt++) {
+      const int par = cnt & 1;
+      mbar_wait(&rfull[par], (cnt >> 1) & 1);
+#pragma unroll 1
+      for (int r = 0; r < R; r++) {
+        const int4 h = hand[par * (R * K2_TM) + r * K2_TM + t];
+        k2r_rerank_row(RA, (st * R + r) * K2_TM + t, h.x, h.y, __int_as_float(h.z));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rempty[par]);
+    }
   } else {
     // ===================== epilogue: group g = warp / 4 owns row tile g and accumulator g =====
     const int g = warp >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + g * K2R_TNH;
-    unsigned use = 0;
-    for (long st = blockIdx.x; st < nsuper; st += gridDim.x) {
+    unsigned use = 0, cnt = 0;
+    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, cnt++) {
       const long n = (st * R + g) * K2_TM + row;
       const float delta = n < N ? rs[n].delta : 0.0f;
       K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
@@ -826,12 +935,20 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[g]);
       }
-      if (n < N) {
+      {
+        // hand the row over to the re-rank warps (the buffer of two passes ago must have been drained)
+        const int par = cnt & 1;
+        mbar_wait(&rempty[par], ((cnt >> 1) & 1) ^ 1);
         const float bound = r.thr;                      // final best + delta (rounded up)
-        cand[n * K2R_NG] = (r.k0 < bound && r.i0 < M) ? r.i0 : -1;
-        cand[n * K2R_NG + 1] = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
+        int4 h;
+        h.x = (r.k0 < bound && r.i0 < M) ? r.i0 : -1;
+        h.y = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
         // groups never recorded: minimum >= best + delta; recorded and dropped: >= lost
-        thr[n] = fminf(bound, r.lost);
+        h.z = __float_as_int(fminf(bound, r.lost));
+        h.w = 0;
+        hand[par * (R * K2_TM) + g * K2_TM + row] = h;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rfull[par]);
       }
     }
   }
@@ -937,88 +1054,6 @@ k2_rerank_kernel(const float *__restrict__ data, const float *__restrict__ codes
     else { idx[n * k + t] = have ? ci[t] : -1; diff[n * k + t] = have ? cd[t] : FLT_MAX; }
   }
   nfound[n] = k;
-}
-
-// ---------------------------------------------------------------- group re-rank (record kernel, k == 1)
-// K2R_NG * K2R_GW lanes per row: lane l computes the exact distance to code l % GW of candidate
-// group l / GW; those lanes take the (diff, index) minimum -- first minimum wins, lvq_pak.c:79 -- and the
-// leader evaluates the certificate against thr (lower bound of every code outside the groups).
-__global__ void __launch_bounds__(256)
-k2_rerank_group_kernel(const float *__restrict__ data, const float *__restrict__ grp, long N, long M, long row0,
-                       int D, const unsigned char *__restrict__ flags, const RowStats *__restrict__ rs,
-                       const CbStats *__restrict__ cst, const int32_t *__restrict__ cand,
-                       const float *__restrict__ thr, int *__restrict__ listW, int *__restrict__ counters,
-                       int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  constexpr int LPR = K2R_NG * K2R_GW;                  // lanes per row
-  const int lane = threadIdx.x & 31, sub = lane % LPR;
-  const long warp_id = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  const long n = warp_id * (32 / LPR) + lane / LPR;
-  const bool row_ok = n < N && flags[n] == 0;           // other rows are answered by K1
-  u64 key = ~0ull;
-  if (row_ok) {
-    const int g0 = cand[n * K2R_NG + sub / K2R_GW];          // first code of the group (multiple of GW)
-    const int l = sub % K2R_GW;
-    const long j = (long)g0 + l;
-    if (g0 >= 0 && j < M) {
-      const float *x = data + n * (long)D;
-      const int Dq = (D + 3) / 4;
-      const float4 *c4 = reinterpret_cast<const float4 *>(grp) + ((long)(g0 / K2R_GW) * Dq) * K2R_GW + l;
-      float acc = 0.0f;
-      if ((D & 3) == 0) {
-        const float4 *x4 = reinterpret_cast<const float4 *>(x);
-#pragma unroll 4
-        for (int i = 0; i < Dq; i++) {
-          const float4 xv = __ldg(x4 + i), cv = __ldg(c4 + i * K2R_GW);
-          acc = sq_acc(acc, cv.x, xv.x);               // the reference's sum, component order
-          acc = sq_acc(acc, cv.y, xv.y);
-          acc = sq_acc(acc, cv.z, xv.z);
-          acc = sq_acc(acc, cv.w, xv.w);
-        }
-      } else {
-        for (int i = 0; i < Dq; i++) {
-          const float4 cv = __ldg(c4 + i * K2R_GW);
-          const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-          for (int e = 0; e < 4; e++)
-            if (4 * i + e < D) acc = sq_acc(acc, cc[e], __ldg(x + 4 * i + e));
-        }
-      }
-      // only d < FLT_MAX can win; non-negative floats order like their bit patterns
-      if (acc < FLT_MAX) key = ((u64)__float_as_uint(acc) << 32) | (unsigned)j;
-    }
-  }
-#pragma unroll
-  for (int off = LPR / 2; off >= 1; off >>= 1) {
-    const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
-    key = o < key ? o : key;
-  }
-  if (!row_ok || sub != 0) return;
-  bool ok = false;
-  const float dbest = __uint_as_float((unsigned)(key >> 32));
-  if (key != ~0ull) {
-    // in scaled units every code outside the candidate groups has ||s x' - s m'||^2 >= nx2 + thr - E
-    const RowStats s = rs[n];
-    const CbStats cs = *cst;
-    const double Lc = s.nx2 + (double)thr[n] - (double)s.E;
-    const double eta = ldexp((double)s.nx + (double)cs.nm, -23);
-    if (Lc > 0.0) {
-      const double r = sqrt(Lc) - eta;
-      if (r > 0.0) {
-        const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01;
-        const double L = r * r * (1.0 - gamma) * (1.0 - 1e-6) * (double)cs.inv_s2;
-        ok = (double)dbest < L;
-      }
-    }
-  }
-  if (!ok) {
-    listW[atomicAdd(&counters[0], 1)] = (int)(row0 + n);     // all other arrays are passed pre-offset by row0
-    atomicAdd(&counters[3], 1);
-    return;
-  }
-  atomicAdd(&counters[2], 1);
-  idx[n] = (int)(unsigned)key;
-  diff[n] = dbest;
-  nfound[n] = 1;
 }
 
 // ---------------------------------------------------------------- host side
@@ -1176,17 +1211,17 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
 static int k2r_stages(int Kp) {
   const size_t a = (size_t)K2R_R * K2_TM * Kp * 2, b = (size_t)K2_TN * Kp * 2;
   int n = K2R_BST;
-  while (n > 2 && a + n * b + 256 > 227 * 1024) n--;
+  while (n > 2 && a + n * b + 256 + 2 * (size_t)K2R_R * K2_TM * 16 > 227 * 1024) n--;
   return n;
 }
 static size_t k2r_smem_bytes(int Kp) {
-  return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)k2r_stages(Kp) * K2_TN * Kp * 2 + 256;
+  return (size_t)K2R_R * K2_TM * Kp * 2 + (size_t)k2r_stages(Kp) * K2_TN * Kp * 2 + 256 +
+         2 * (size_t)K2R_R * K2_TM * sizeof(int4);        // + hand-off to the re-rank warps
 }
 
-// rows [row0, row0 + n) of the call; row0 is a multiple of the 512-row pass of the kernel
 template <int NK>
-static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, long row0, long n,
-                                    cudaStream_t st) {
+static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
+  const long row0 = 0, n = a.N;
   const int Kp = c->Kp;
   const size_t smem = k2r_smem_bytes(Kp);
   cudaError_t e = cudaFuncSetAttribute(k2_rec_kernel<K2R_R, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1194,9 +1229,13 @@ static cudaError_t k2_launch_record(K2Codebook *c, const K1Args &a, const K2Scra
   const long ntiles = (n + K2_TM - 1) / K2_TM;
   const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
   const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
+  K2RRerankArgs ra;
+  ra.data = a.data + row0 * a.D; ra.grp = c->d_grp; ra.flags = a.flags + row0; ra.rs = s.rs + row0;
+  ra.cst = (const CbStats *)c->d_norm; ra.listW = a.listW; ra.counters = a.counters;
+  ra.idx = a.idx + row0; ra.nfound = a.nfound + row0; ra.diff = a.diff + row0;
+  ra.N = n; ra.M = a.M; ra.D = a.D;
   k2_rec_kernel<K2R_R, NK><<<grid, K2R_THREADS, smem, st>>>(s.Aimg + (size_t)row0 * Kp, (const __half *)c->d_ops,
-                                                           s.rs + row0, n, a.M, Kp, k2r_stages(Kp),
-                                                           s.cand + row0 * K2R_NG, s.thr + row0);
+                                                           s.rs + row0, n, a.M, Kp, k2r_stages(Kp), ra);
   return cudaGetLastError();
 }
 
@@ -1211,64 +1250,26 @@ static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratc
   return cudaGetLastError();
 }
 
-// Record path (k == 1, short K).  The sub-batch pipeline of the streaming kernel is available here too
-// (K2R_PIPELINE) but OFF: with the re-rank of sub-batch i-1 running beside the GEMM of sub-batch i, C3
-// measured 15.7 ms per step instead of 16.5 (same box, bench.py), while the GEMM launches themselves
-// stretched from 12.3 to 13.4 ms (the re-rank's L2 gathers compete with the code-tile stream), i.e.
-// +5 % throughput for a GEMM kernel that drops from 0.75 to 0.68 of its roofline.  The kernel's own
-// efficiency is the round's target, so the pipeline stays off for this path.  Also running the row prep
-// of sub-batch i+1 beside the GEMM was worse outright (15.0 - 15.9 ms in the probe): it is issue bound.
-constexpr bool K2R_PIPELINE = false;
+// Record path (k == 1, short K): row prep, then ONE kernel that does the GEMM filter and the exact
+// re-rank.  History (measured on C3, same box): a separate re-rank kernel after the GEMM 16.5 ms per
+// step; that kernel on a second stream beside the GEMM of the next sub-batch 15.7 ms, but the GEMM
+// launches stretched from 12.3 to 13.4 ms (its L2 gathers competed with the code-tile stream and the
+// pipeline needed sub-batch tails); re-rank warps inside the GEMM kernel: see DESIGN.md.
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
-  constexpr int RPW = 32 / (K2R_NG * K2R_GW);           // rows per warp of the group re-rank
-  const long pass = (long)K2R_R * K2_TM;                // rows per kernel pass (512)
-  long passes_per = (a.N + pass - 1) / pass;
-  const int nsub = K2R_PIPELINE ? k2_subbatches(passes_per, a.num_sms, &passes_per) : 1;
-  if (nsub > 1 && (e = k2_pipeline_init()) != cudaSuccess) return e;
-  const long per = passes_per * pass;
-  auto rows_of = [&](int i) { const long r0 = i * per; return a.N - r0 < per ? a.N - r0 : per; };
-  // row prep of the whole call first; the aux stream starts behind everything queued so far
-  if ((e = k2_launch_prep(c, a, s, 0, a.N, 0, st)) != cudaSuccess) return e;
+  cudaError_t e = k2_launch_prep(c, a, s, 0, a.N, 0, st);
+  if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[1], st);
-  if (nsub > 1) {
-    cudaEventRecord(g_k2join, st);
-    cudaStreamWaitEvent(g_k2aux, g_k2join, 0);
+  switch (c->Kp / 16) {                                 // K2R_MAX_KP / 16 = 6 unrolled issue loops
+    case 1: e = k2_launch_record<1>(c, a, s, st); break;
+    case 2: e = k2_launch_record<2>(c, a, s, st); break;
+    case 3: e = k2_launch_record<3>(c, a, s, st); break;
+    case 4: e = k2_launch_record<4>(c, a, s, st); break;
+    case 5: e = k2_launch_record<5>(c, a, s, st); break;
+    default: e = k2_launch_record<6>(c, a, s, st); break;
   }
-  for (int i = 0; i < nsub; i++) {
-    const long row0 = i * per, n = rows_of(i);
-    if (n <= 0) break;
-    switch (c->Kp / 16) {                               // K2R_MAX_KP / 16 = 6 unrolled issue loops
-      case 1: e = k2_launch_record<1>(c, a, s, row0, n, st); break;
-      case 2: e = k2_launch_record<2>(c, a, s, row0, n, st); break;
-      case 3: e = k2_launch_record<3>(c, a, s, row0, n, st); break;
-      case 4: e = k2_launch_record<4>(c, a, s, row0, n, st); break;
-      case 5: e = k2_launch_record<5>(c, a, s, row0, n, st); break;
-      default: e = k2_launch_record<6>(c, a, s, row0, n, st); break;
-    }
-    k1_count_launch(1);
-    if (e != cudaSuccess) return e;
-    cudaStream_t rr = st;
-    if (nsub > 1) {
-      cudaEventRecord(g_k2sub[i], st);
-      cudaStreamWaitEvent(g_k2aux, g_k2sub[i], 0);
-      rr = g_k2aux;
-    } else {
-      cudaEventRecord(g_k2ev[2], st);
-    }
-    const long rr_warps = (n + RPW - 1) / RPW;
-    k2_rerank_group_kernel<<<(unsigned)((rr_warps + 7) / 8), 256, 0, rr>>>(
-        a.data + row0 * a.D, c->d_grp, n, a.M, row0, a.D, a.flags + row0, s.rs + row0, (const CbStats *)c->d_norm,
-        s.cand + row0 * K2R_NG, s.thr + row0, a.listW, a.counters, a.idx + row0, a.diff + row0, a.nfound + row0);
-    k1_count_launch(1);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
-  if (nsub > 1) {
-    cudaEventRecord(g_k2ev[2], st);                     // end of the last GEMM (re-ranks of earlier sub-batches overlap it)
-    cudaEventRecord(g_k2join, g_k2aux);
-    cudaStreamWaitEvent(st, g_k2join, 0);
-  }
-  return cudaSuccess;
+  k1_count_launch(1);
+  cudaEventRecord(g_k2ev[2], st);                       // the re-rank is inside the kernel: its phase is empty
+  return e;
 }
 
 cudaError_t k2_last_kernel_ms(float out[4]) {
