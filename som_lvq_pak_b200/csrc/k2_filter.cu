@@ -16,19 +16,20 @@
 //              columns of ones) are folded into the B operand: the accumulator IS the score.
 //   scaling    s = 2^e with s^2 max||m'||^2 in [2^11, 2^13): products stay far from the fp16
 //              range limits; rows whose scaled values overflow fp16 go to K1.
-//   GEMM       tcgen05.mma.cta_group::1.kind::f16, M=128 x N=256 x K=16 per instruction, FP32
-//              accumulators double-buffered in TMEM (2 x 256 columns), operands staged by
-//              cp.async.bulk (UBLKCP) from images pre-arranged in the canonical no-swizzle
-//              K-major core-matrix layout, mbarrier rings, one MMA-issuing thread.
-//   k2_rec_kernel  (k == 1, short contractions): 4 row tiles share every staged code tile
-//              (L2 -> smem traffic / 4); 8 epilogue warps; "record" epilogue: a 3-input min
-//              tree per 32 columns (0.5 ALU op per score) and, only when a row's chunk minimum
-//              is below its running threshold best+delta, a slow path that inserts the columns
-//              below the threshold.  Everything never inserted is >= final best+delta.
-//   k2_gemm_kernel (k >= 2 or long contractions): K streamed in slabs; epilogue keeps the TT
-//              smallest keys per code tile with the column index packed into the low mantissa
-//              bits.
-//   re-rank    exact distances of the candidates, reference tie rules, certificate
+//   GEMM       tcgen05.mma.cta_group::1.kind::f16 (K = 16 per instruction), FP32 accumulators in TMEM,
+//              operands staged by cp.async.bulk (UBLKCP) from images pre-arranged in the canonical
+//              no-swizzle K-major core-matrix layout, mbarrier rings, one elected MMA-issuing lane.
+//   k2_rec_kernel  (k == 1, short contractions; C3): 704 threads.  4 row tiles share every staged code
+//              tile (L2 -> smem traffic / 4); 128x128 MMAs into four 128-column accumulators, one per
+//              row tile; 16 epilogue warps with the "record" epilogue: minima of 4-code groups per 32
+//              columns (0.62 ALU op per score) and, only when a row's chunk minimum is below its running
+//              threshold best+delta, a short predicated update that records the group of the minimum;
+//              4 re-rank warps compute the exact distances of the recorded groups of the previous pass
+//              and evaluate the certificate inside the same kernel.
+//   k2_gemm_kernel (k >= 2 or long contractions; C4): 128x256 MMAs, K streamed in slabs, two 256-column
+//              accumulators; epilogue keeps the TT smallest keys per code tile with the column index packed
+//              into the low mantissa bits; k2_rerank_kernel orders the candidates by the reference's k-NN
+//              rule and evaluates the certificate, overlapped with the next sub-batch's GEMM.
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -162,7 +163,7 @@ k2_cb_prep_kernel(const float *__restrict__ codes, long M, int D, const float *_
   }
 }
 
-// FP32 codebook regrouped for k2_rerank_group_kernel: [group of K2R_GW codes][4-component chunk]
+// FP32 codebook regrouped for the re-rank warps of k2_rec_kernel: [group of K2R_GW codes][4-component chunk]
 // [code in group][4 comps], so that the lanes of a group read contiguous bytes per float4
 __global__ void k2_cb_regroup_kernel(const float *__restrict__ codes, long M, int D, float *__restrict__ grp) {
   const int Dq = (D + 3) / 4;
@@ -669,7 +670,7 @@ __device__ __forceinline__ uint32_t k2r_idesc() {
 // (18 FMNMX3/FMNMX, 0.56 ALU op per score).  Only if some lane's chunk minimum is below its
 // running threshold thr = best + delta (vote) does the warp run the short predicated update that
 // records the GROUP holding the minimum; the exact distances of the <= 2 x 8 codes of the
-// recorded groups are computed by k2_rerank_group_kernel.  Invariant for the certificate: a
+// recorded groups are computed by the re-rank warps (k2r_rerank_row).  Invariant for the certificate: a
 // group that is not recorded has a minimum >= min(final best + delta, lost).
 // Exact re-rank of ONE row inside the record kernel (one thread): the reference's sum (lvq_pak.c:63-73)
 // over the <= 2 x K2R_GW codes of the recorded groups, first-minimum rule (lvq_pak.c:79), then the
