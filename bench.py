@@ -40,7 +40,8 @@ MASK64 = (1 << 64) - 1
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
 # committed ncu --set full capture of exactly this shape (profiles/): (kernel, rows, D, M) -> bytes
-NCU_TRAFFIC = {("k2_rec_kernel", 10_000_000, 64, 10_000): 1843645000 + 117973504}   # profiles/r01_k2_rec_ncu_full.txt
+NCU_TRAFFIC = {("k2_rec_kernel", 10_000_000, 64, 10_000): 4423710000 + 122496768}   # profiles/r01_k2_rec_ncu_full.txt
+# (fp16 A image 1.6 GB + the FP32 rows 2.56 GB the fused re-rank reads + codebook misses)
 
 
 # ------------------------------------------------------------------ synthetic data
@@ -339,8 +340,10 @@ def main_gpu(args, w):
                     "note": "algorithmic 2*M*D flop per search over the live CUDA-event duration of %s vs the "
                             "sustained fp16/bf16 cuBLAS peak (%s); the kernel issues %.2fx that many MMA flops "
                             "(K %d -> %d: 3 norm columns + padding to 16; M %d -> %d), so the tensor pipe itself "
-                            "runs at %.3f of that peak.  traffic = ncu dram bytes of one launch (profiles/), "
-                            "null when no capture exists for this shape"
+                            "runs at %.3f of that peak.  For k = 1 the timed kernel also contains the exact re-rank "
+                            "(4 extra warps; FMA-pipe work that replaced a separate 2.3 ms kernel), which the flop "
+                            "count above does not credit.  traffic = ncu dram bytes of one launch (profiles/), null "
+                            "when no capture exists for this shape"
                             % (kname, "measured" if "bf16_tflops_sustained" in peaks else "fallback",
                                (kp / D) * (m_pad / M), D, kp, M, m_pad, issued / peak),
                     "mma_issued_tflops": issued,

@@ -23,13 +23,16 @@ diff = torch.empty((rows, k), dtype=torch.float32, device=dev)
 nf = torch.empty(rows, dtype=torch.int32, device=dev)
 b.set_search_path(path)
 cb = b.Codebook(codes.cpu().numpy())
-for it in range(4):
+iters = int(os.environ.get('PROBE_ITERS', '4'))
+for it in range(iters):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     cb.search_dev(data.data_ptr(), rows, k, idx.data_ptr(), diff.data_ptr(), nf.data_ptr())
     e1.record()
     torch.cuda.synchronize()
+    if iters > 4:
+        print('  it %d: %.3f ms  gemm %.3f' % (it, e0.elapsed_time(e1), b.last_search_kernel_ms()['k2_gemm']))
 ms = e0.elapsed_time(e1)
 print("rows %d M %d D %d k %d path %d: %.3f ms  %.1f M searches/s" % (rows, M, D, k, path, ms, rows / ms / 1e3))
 print("  kernels:", {n: round(v, 3) for n, v in b.last_search_kernel_ms().items() if v})
