@@ -781,6 +781,9 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
   const long ntiles = (N + K2_TM - 1) / K2_TM;
   const long nsuper = (ntiles + R - 1) / R;
   const int nct = (int)((M + K2_TN - 1) / K2_TN);
+  // 128-column accumulations per row tile: the upper half of the last code tile is skipped when it
+  // holds padding only (M = 10000: 79 instead of 80)
+  const int nacc = (int)((M + K2R_TNH - 1) / K2R_TNH);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K2R_BST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -838,8 +841,9 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         mbar_wait(&full[s], (bseq / nst) & 1);
         tc_fence_after();
         const uint64_t dbs = db0 + (uint64_t)s * b_tile_step;
-#pragma unroll
-        for (int h = 0; h < 2; h++, use++) {
+        const int nh = (2 * ct + 1 < nacc) ? 2 : 1;
+#pragma unroll 1
+        for (int h = 0; h < nh; h++, use++) {
 #pragma unroll
           for (int r = 0; r < R; r++) {
             mbar_wait(&tempty[r], (use & 1) ^ 1);          // epilogue group r drained its accumulator
@@ -891,7 +895,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
       const long n = (st * R + g) * K2_TM + row;
       const float delta = n < N ? rs[n].delta : 0.0f;
       K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
-      for (int q = 0; q < 2 * nct; q++, use++) {            // q = 2 * code tile + half
+      for (int q = 0; q < nacc; q++, use++) {               // q = 2 * code tile + half
         mbar_wait(&tfull[g], use & 1);
         tc_fence_after();
         uint32_t v[32];
