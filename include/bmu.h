@@ -158,6 +158,16 @@ void bmu_trainer_destroy(bmu_trainer *t);
 int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, float radius,
                 const float *data, const unsigned char *mask, long N, float *out);
 
+/* The pair loops of min_distances / med_distances (lvq_rout.c:325-350, 430-470; called by
+ * mindist.c:93-105 and balance.c:81-83): for every code vector i, dist[i] = the smallest
+ * vector_dist_euc(j, i) (lvq_pak.c:291-316, components masked in either vector skipped, -1 when
+ * all are) over the LATER code vectors j > i whose class label[j] equals label[i]; found[i] = 0
+ * and dist[i] = FLT_MAX when there is none (`fou` in the reference).  The per-class mean / median
+ * of dist[] over found entries stays with the caller (it follows the class hitlist order).
+ * mask: NULL or M x D. */
+int bmu_class_nearest(const float *codes, const unsigned char *mask, const int32_t *label, long M, int D,
+                      float *dist, int32_t *found);
+
 /* ---- host-side helpers (pure C arithmetic, no device) ------------------------------ */
 /* lvq_pak.c:459-473 + datafile.c:1152-1188: order[i] = row used at list position i after
  * `-rand seed` (seed != 0; the reference maps seed 0 to time()). */

@@ -363,3 +363,61 @@ long orc_hitlist_vote(const long *labels, int n)
   free(lab); free(frq);
   return r;
 }
+
+/* ---------------------------------------------------------------- class distances */
+/* lvq_rout.c:280-361 (min_distances: mean) and 375-473 (med_distances: median) with the class
+ * list built by add_hit (labels.c:370-410).  near/found (nullable, M each) receive dissf / fou
+ * of every entry.  Returns the number of classes. */
+static int cmp_float_asc(const void *a, const void *b)
+{
+  float x = *(const float *)a, y = *(const float *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+long orc_class_dists(const float *codes, const unsigned char *mask, const int *label, long M, int D,
+                     int median, int *out_class, int *out_noe, float *out_dists,
+                     float *near, int *found)
+{
+  long ncls = 0, c, i, j, k;
+  long *cls = malloc(sizeof(long) * (M > 0 ? M : 1)), *freq = malloc(sizeof(long) * (M > 0 ? M : 1));
+  float *meds = malloc(sizeof(float) * (M > 0 ? M : 1));
+  for (i = 0; i < M; i++) {                       /* add_hit */
+    for (k = 0; k < ncls && cls[k] != label[i]; k++) ;
+    if (k == ncls) { cls[ncls] = label[i]; freq[ncls++] = 1; continue; }
+    freq[k]++;
+    while (k > 0 && freq[k - 1] < freq[k]) {
+      long t = cls[k]; cls[k] = cls[k - 1]; cls[k - 1] = t;
+      t = freq[k]; freq[k] = freq[k - 1]; freq[k - 1] = t;
+      k--;
+    }
+  }
+  for (c = 0; c < ncls; c++) {
+    long note = 0;
+    float sum = 0.0f;
+    for (i = 0; i < M; i++) {
+      float dissf = FLT_MAX;
+      int fou = 0;
+      if (label[i] != cls[c]) continue;
+      for (j = i + 1; j < M; j++) {
+        float dist;
+        if (label[j] != cls[c]) continue;
+        fou = 1;
+        dist = orc_vector_dist(codes + j * (long)D, mask ? mask + j * (long)D : NULL,
+                               codes + i * (long)D, mask ? mask + i * (long)D : NULL, D);
+        if (dist < dissf) dissf = dist;
+      }
+      if (near) near[i] = dissf;
+      if (found) found[i] = fou;
+      if (fou) { sum += dissf; meds[note++] = dissf; }
+    }
+    out_class[c] = (int)cls[c];
+    out_noe[c] = (int)freq[c];
+    out_dists[c] = 0.0f;
+    if (note > 0) {
+      if (median) { qsort(meds, note, sizeof(float), cmp_float_asc); out_dists[c] = meds[note / 2]; }
+      else out_dists[c] = sum / note;
+    }
+  }
+  free(cls); free(freq); free(meds);
+  return ncls;
+}

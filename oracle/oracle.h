@@ -76,6 +76,12 @@ int orc_lvq_train(int algo, float *codes, const int *code_label, long M, int D,
  * scanning in rank order. */
 long orc_hitlist_vote(const long *labels, int n);
 
+/* lvq_rout.c:280-361 (median=0: min_distances, mean) / 375-473 (median=1: med_distances); classes in
+ * add_hit order (labels.c:370-410).  near/found nullable: dissf / fou per entry.  Returns #classes. */
+long orc_class_dists(const float *codes, const unsigned char *mask, const int *label, long M, int D,
+                     int median, int *out_class, int *out_noe, float *out_dists,
+                     float *near, int *found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,23 @@ class _Lib:
                  C.c_long(data.shape[0]), C.c_int(qetype), C.c_float(radius))
 
 
+    def class_dists(self, codes, labels, median=True, mask=None, per_entry=False):
+        codes, mask = _f32(codes), _msk(mask)
+        M, D = codes.shape
+        lab = np.ascontiguousarray(labels, np.int32)
+        cls, noe, dists = np.empty(M, np.int32), np.empty(M, np.int32), np.empty(M, np.float32)
+        near, found = np.full(M, np.nan, np.float32), np.full(M, -1, np.int32)
+        f = self.fn("class_dists")
+        f.restype = C.c_long
+        n = f(_p(codes, _f), _p(mask, _u8), _p(lab, _i), C.c_long(M), C.c_int(D), C.c_int(int(median)),
+              _p(cls, _i), _p(noe, _i), _p(dists, _f), _p(near, _f), _p(found, _i))
+        if n < 0:
+            raise RuntimeError("class_dists failed")
+        if per_entry:
+            return cls[:n], noe[:n], dists[:n], near, found
+        return cls[:n], noe[:n], dists[:n]
+
+
 class Oracle(_Lib):
     """Our C restatement (oracle/oracle.c)."""
     prefix = "orc_"

@@ -286,3 +286,27 @@ long ref_hitlist_vote(const long *labels, int n)
   free_hitlist(h);
   return r;
 }
+
+/* min_distances / med_distances (lvq_rout.c:280-492) on a flat codebook; near/found are not
+ * available from the reference (it only returns the per-class values).  Returns #classes. */
+long ref_class_dists(const float *codes, const unsigned char *mask, const int *label, long M, int D,
+                     int median, int *out_class, int *out_noe, float *out_dists,
+                     float *near, int *found)
+{
+  struct entries *e = build_entries(codes, mask, label, NULL, NULL, M, D, TOPOL_LVQ, NEIGH_UNKNOWN, 0, 0, NULL);
+  struct mindists *md;
+  long i, n;
+  (void)near; (void)found;
+  if (!e) return -1;
+  md = median ? med_distances(e, vector_dist_euc) : min_distances(e, vector_dist_euc);
+  if (!md) return -1;
+  n = md->num_classes;
+  for (i = 0; i < n; i++) {
+    out_class[i] = md->class[i];
+    out_noe[i] = md->noe[i];
+    out_dists[i] = md->dists[i];
+  }
+  free_mindists(md);
+  close_entries(e);
+  return n;
+}

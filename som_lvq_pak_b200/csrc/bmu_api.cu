@@ -15,6 +15,7 @@
 #include "k2_filter.h"
 #include "k3_train.h"
 #include "k4_qerror2.h"
+#include "k5_classdist.h"
 #include "api_internal.h"
 
 using namespace bmu;
@@ -395,6 +396,55 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
     CK(cudaMemcpyAsync(out + n0, g_q2_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_compute));
     CK(cudaStreamSynchronize(g_compute));
   }
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ class distances
+// The pair loops of min_distances / med_distances (lvq_rout.c:280-492): dist[i] = dissf of entry i,
+// the smallest vector_dist_euc(later, i) over later entries of the same class (first label).
+int bmu_class_nearest(const float *codes, const unsigned char *mask, const int32_t *label, long M, int D,
+                      float *dist, int32_t *found) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!codes || !label || !dist || !found) return fail(BMU_ERR_ARG, "NULL argument");
+  if (M < 0 || D < 1) return fail(BMU_ERR_ARG, "bad M or D");
+  if (M == 0) return BMU_OK;
+  float *d_codes = nullptr;
+  unsigned char *d_mask = nullptr;
+  int32_t *d_label = nullptr;
+  uint32_t *d_out = nullptr;           // [0, M) squared-distance bits, [M, 2M) flags
+  uint32_t *h_out = (uint32_t *)malloc((size_t)M * 8);
+  cudaError_t e = cudaSuccess;
+  if (!h_out) return fail(BMU_ERR_NOMEM, "out of host memory");
+  for (long i = 0; i < M; i++) { h_out[i] = 0x7f800000u; h_out[M + i] = 0u; }
+  if ((e = cudaMalloc((void **)&d_codes, (size_t)M * D * 4)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_label, (size_t)M * 4)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_out, (size_t)M * 8)) == cudaSuccess &&
+      (!mask || (e = cudaMalloc((void **)&d_mask, (size_t)M * D)) == cudaSuccess) &&
+      (e = cudaMemcpyAsync(d_codes, codes, (size_t)M * D * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(d_label, label, (size_t)M * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(d_out, h_out, (size_t)M * 8, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (!mask || (e = cudaMemcpyAsync(d_mask, mask, (size_t)M * D, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess) &&
+      (e = k5_class_nearest(d_codes, d_mask, d_label, M, D, d_out, d_out + M, g_compute)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(h_out, d_out, (size_t)M * 8, cudaMemcpyDeviceToHost, g_compute)) == cudaSuccess)
+    e = cudaStreamSynchronize(g_compute);
+  cudaFree(d_codes); cudaFree(d_mask); cudaFree(d_label); cudaFree(d_out);
+  if (e != cudaSuccess) {
+    free(h_out);
+    cudaGetLastError();
+    return fail(BMU_ERR_CUDA, "bmu_class_nearest: %s", cudaGetErrorString(e));
+  }
+  k1_count_launch(1);
+  for (long i = 0; i < M; i++) {
+    const uint32_t fl = h_out[M + i], bits = h_out[i];
+    float d2;
+    memcpy(&d2, &bits, 4);
+    found[i] = (fl & 1u) ? 1 : 0;
+    if (fl & 2u) dist[i] = -1.0f;                                  // an all-masked pair: -1 < anything
+    else if (!(fl & 1u) || bits == 0x7f800000u) dist[i] = FLT_MAX; // dissf never lowered
+    else dist[i] = (float)sqrt((double)d2);                        // lvq_pak.c:315
+  }
+  free(h_out);
   return BMU_OK;
 }
 

@@ -158,6 +158,57 @@ def find_qerror2(codes, data, xdim, ydim, topol, neigh, radius, mask=None):
     return np.float32(q), out
 
 
+def class_nearest(codes, labels, mask=None):
+    """dissf of min_distances / med_distances (lvq_rout.c:325-350): per code vector the distance
+    (vector_dist_euc) to the nearest LATER code vector with the same label; (dist, found)."""
+    codes = _f32(codes)
+    labels = np.ascontiguousarray(labels, np.int32)
+    mask = _opt(mask, np.uint8)
+    M, D = codes.shape
+    dist = np.empty(M, np.float32)
+    found = np.empty(M, np.int32)
+    _lib.check(_lib.load().bmu_class_nearest(_ptr(codes), _ptr(mask), _ptr(labels), M, D, _ptr(dist), _ptr(found)))
+    return dist, found
+
+
+def hitlist_order(labels):
+    """(label, count) pairs in the order add_hit (labels.c:370-410) leaves them after the labels were
+    added one by one: a count that grows past its predecessor's moves in front of it, ties keep
+    their place."""
+    lab, freq = [], []
+    for l in labels:
+        l = int(l)
+        if l in lab:
+            i = lab.index(l)
+            freq[i] += 1
+            while i > 0 and freq[i - 1] < freq[i]:
+                lab[i - 1], lab[i] = lab[i], lab[i - 1]
+                freq[i - 1], freq[i] = freq[i], freq[i - 1]
+                i -= 1
+        else:
+            lab.append(l)
+            freq.append(1)
+    return lab, freq
+
+
+def class_distances(codes, labels, median=True, mask=None):
+    """med_distances (median=True, lvq_rout.c:375-473) or min_distances (mean, lvq_rout.c:280-361):
+    one value per class in hitlist order; returns (class labels, entries per class, dists)."""
+    dist, found = class_nearest(codes, labels, mask)
+    labels = np.asarray(labels)
+    cls, noe = hitlist_order(labels)
+    out = np.zeros(len(cls), np.float32)
+    for c, l in enumerate(cls):
+        d = dist[(labels == l) & (found != 0)]
+        if d.size == 0:
+            continue
+        if median:
+            out[c] = np.sort(d)[d.size // 2]                       # meds[not/2] after qsort
+        else:
+            out[c] = np.cumsum(d, dtype=np.float32)[-1] / np.float32(d.size)   # dists[i] += dissf; /= note
+    return np.array(cls, np.int32), np.array(noe, np.int32), out
+
+
 # ---------------------------------------------------------------------------- host helpers
 def rand_order(n, seed):
     """list order after `-rand seed` (datafile.c:1152-1188 driven by lvq_pak.c:459-473)"""

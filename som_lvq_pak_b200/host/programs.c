@@ -1105,22 +1105,8 @@ int eveninit_main(int argc, char **argv, const char *progname) {
 /* ------------------------------------------------------------------ mindist */
 /* med_distances (lvq_rout.c:383-492): per class, the median over its entries of the distance to
  * the nearest LATER entry of the same class (vector_dist_euc, lvq_pak.c:291-316), as `mindist`
- * prints it (mindist.c:93-105).  Host arithmetic: O(M^2 D) on a codebook, not on the data. */
-static float host_vector_dist(const struct pak_entries *e, long a, long b) {
-  const float *x = e->points + (size_t)a * e->dim, *y = e->points + (size_t)b * e->dim;
-  const unsigned char *ma = e->mask ? e->mask + (size_t)a * e->dim : NULL, *mb = e->mask ? e->mask + (size_t)b * e->dim : NULL;
-  float difference = 0.0f;
-  int i, masked = 0;
-  for (i = 0; i < e->dim; i++) {
-    if ((ma && ma[i]) || (mb && mb[i])) { masked++; continue; }
-    {
-      const float diff = x[i] - y[i];
-      difference += diff * diff;
-    }
-  }
-  if (masked == e->dim) return -1.0f;
-  return (float)sqrt((double)difference);
-}
+ * prints it (mindist.c:93-105).  The O(M^2 D) pair loops run on the device (bmu_class_nearest);
+ * class order, medians and printing stay here. */
 static int cmp_float(const void *a, const void *b) {
   const float x = *(const float *)a, y = *(const float *)b;
   return x < y ? -1 : (x > y ? 1 : 0);
@@ -1130,42 +1116,41 @@ int mindist_main(int argc, char **argv) {
   struct pak_entries *codes;
   struct pak_hitlist classes;
   const char *cin_name;
-  float *meds;
-  long c, i, j;
+  float *meds, *near;
+  int32_t *label, *found;
+  long c, i;
   global_options(argc, argv);
   cin_name = need(argc, argv, "-cin");
   if (opt(argc, argv, "-din")) fprintf(stderr, "note: standard deviations (-din) are not provided by the B200 host\n");
   codes = pak_load(cin_name, 1, 1);
   if (!codes) { fprintf(stderr, "Can't read code file '%s'\n", cin_name); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
   hit_init(&classes);
   for (i = 0; i < codes->n; i++) hit_add(&classes, pak_label(codes, i));
-  meds = (float *)malloc(sizeof(float) * (size_t)(codes->n > 0 ? codes->n : 1));
-  if (!meds) return 1;
+  {
+    const size_t n = (size_t)(codes->n > 0 ? codes->n : 1);
+    meds = (float *)malloc(sizeof(float) * n);
+    near = (float *)malloc(sizeof(float) * n);
+    label = (int32_t *)malloc(sizeof(int32_t) * n);
+    found = (int32_t *)malloc(sizeof(int32_t) * n);
+  }
+  if (!meds || !near || !label || !found) return 1;
+  for (i = 0; i < codes->n; i++) label[i] = pak_label(codes, i);
+  if (bmu_class_nearest(codes->points, codes->mask, label, codes->n, codes->dim, near, found))
+    return engine_failed("bmu_class_nearest");
   for (c = 0; c < classes.n; c++) {
     const long lab = classes.label[c];
     long not = 0;
     float dist = 0.0f;
-    for (i = 0; i < codes->n; i++) {
-      float dissf = FLT_MAX;
-      int fou = 0;
-      if (pak_label(codes, i) != lab) continue;
-      for (j = i + 1; j < codes->n; j++) {
-        if (pak_label(codes, j) != lab) continue;
-        fou = 1;
-        {
-          const float d = host_vector_dist(codes, j, i);
-          if (d < dissf) dissf = d;
-        }
-      }
-      if (fou) meds[not++] = dissf;
-    }
+    for (i = 0; i < codes->n; i++)
+      if (label[i] == lab && found[i]) meds[not++] = near[i];
     if (not > 0) {
       qsort(meds, (size_t)not, sizeof(float), cmp_float);
       dist = meds[not / 2];
     }
     fprintf(stdout, "In class %9s %3d units, min dist.: %6.3f\n", label_string((int)lab), (int)classes.freq[c], dist);
   }
-  free(meds);
+  free(meds); free(near); free(label); free(found);
   hit_free(&classes);
   pak_free(codes);
   return 0;

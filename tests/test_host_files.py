@@ -155,11 +155,3 @@ def test_randinit_program(tmp_path, demo):
                     "-topol", "rect", "-neigh", "gaussian", "-rand", "7"], check=True, cwd=tmp_path)
     assert (tmp_path / "g.cod").read_text() == str(demo["som_g_init_cod"])
 
-
-def test_mindist_program(tmp_path, demo, golden):
-    """mindist is host arithmetic (medians of nearest same-class distances): no GPU"""
-    x = golden.demo_extra
-    for key, cod in (("mindist_b_stdout", "lvq_b_cod"), ("mindist_l_stdout", "lvq_l_cod")):
-        (tmp_path / "c.cod").write_text(str(demo[cod]))
-        p = subprocess.run([PAK, "mindist", "-cin", "c.cod"], check=True, cwd=tmp_path, stdout=subprocess.PIPE, text=True)
-        assert p.stdout == str(x[key])
