@@ -168,6 +168,18 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
 int bmu_class_nearest(const float *codes, const unsigned char *mask, const int32_t *label, long M, int D,
                       float *dist, int32_t *found);
 
+/* remove_identicals (sammon.c:83-127): the pairs (i, j), i < j, of code vectors with
+ * vector_dist_euc == 0.0, sorted by (i, j), in pairs[2*p], pairs[2*p+1]; *npairs = how many there
+ * are (BMU_ERR_ARG when more than cap).  The caller replays the reference's removal walk. */
+int bmu_identical_pairs(const float *codes, const unsigned char *mask, long M, int D, int32_t *pairs, long cap,
+                        long *npairs);
+/* sammon_iterate (sammon.c:129-262): `length` sweeps of Sammon's mapping of the M code vectors,
+ * starting from the caller's initial positions (sammon.c:159-162: x[i] = (float)(orand() % M) / M,
+ * y[i] = (float)i / M) and returning the final ones in place.  err: NULL, or `length` floats that
+ * receive the mapping error the reference prints per sweep at -v 2 (sammon.c:240-254). */
+int bmu_sammon(const float *codes, const unsigned char *mask, long M, int D, long length, float *x, float *y,
+               float *err);
+
 /* ---- host-side helpers (pure C arithmetic, no device) ------------------------------ */
 /* lvq_pak.c:459-473 + datafile.c:1152-1188: order[i] = row used at list position i after
  * `-rand seed` (seed != 0; the reference maps seed 0 to time()). */

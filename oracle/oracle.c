@@ -421,3 +421,84 @@ long orc_class_dists(const float *codes, const unsigned char *mask, const int *l
   free(cls); free(freq); free(meds);
   return ncls;
 }
+
+/* ---------------------------------------------------------------- Sammon's mapping */
+/* sammon.c:83-127: keep[i] = 0 for the entries remove_identicals drops (a later entry still in the
+ * list at distance exactly 0 from the current one).  Returns the number kept. */
+long orc_remove_identicals(const float *codes, const unsigned char *mask, long M, int D, int *keep)
+{
+  long i, j, n = 0;
+  for (i = 0; i < M; i++) keep[i] = 1;
+  for (i = 0; i < M; i++) {
+    if (!keep[i]) continue;
+    for (j = i + 1; j < M; j++) {
+      if (!keep[j]) continue;
+      if (orc_vector_dist(codes + i * (long)D, mask ? mask + i * (long)D : NULL,
+                          codes + j * (long)D, mask ? mask + j * (long)D : NULL, D) == 0.0)
+        keep[j] = 0;
+    }
+  }
+  for (i = 0; i < M; i++) n += keep[i];
+  return n;
+}
+
+/* sammon.c:129-262 from given initial positions (the reference draws them at 159-162).
+ * err: nullable, `length` mapping errors (240-254). */
+int orc_sammon(const float *codes, const unsigned char *mask, long noc, int D, long length,
+               float *x, float *y, float *err)
+{
+  long i, j, k, mutual;
+  float e1x, e1y, e2x, e2y, dpj, dq, dr, dt, xd, yd, xx, yy, e, tot, d, ee;
+  float *xu = malloc(sizeof(float) * (noc > 0 ? noc : 1)), *yu = malloc(sizeof(float) * (noc > 0 ? noc : 1));
+  float *dd = malloc(sizeof(float) * (noc > 1 ? (size_t)noc * (noc - 1) / 2 : 1));
+  if (!xu || !yu || !dd) return 1;
+  mutual = 0;
+  for (j = 1; j < noc; j++)
+    for (k = 0; k < j; k++)
+      dd[mutual++] = orc_vector_dist(codes + j * (long)D, mask ? mask + j * (long)D : NULL,
+                                     codes + k * (long)D, mask ? mask + k * (long)D : NULL, D);
+  for (i = 0; i < length; i++) {
+    for (j = 0; j < noc; j++) {
+      e1x = e1y = e2x = e2y = 0.0;
+      for (k = 0; k < noc; k++) {
+        if (j == k) continue;
+        xd = x[j] - x[k];
+        yd = y[j] - y[k];
+        dpj = (float)sqrt((double)xd * xd + yd * yd);
+        if (k > j) dt = dd[k * (k - 1) / 2 + j];
+        else dt = dd[j * (j - 1) / 2 + k];
+        dq = dt - dpj;
+        dr = dt * dpj;
+        e1x += xd * dq / dr;
+        e1y += yd * dq / dr;
+        e2x += (dq - xd * xd * (1.0 + dq / dpj) / dpj) / dr;
+        e2y += (dq - yd * yd * (1.0 + dq / dpj) / dpj) / dr;
+      }
+      xu[j] = x[j] + 0.2 * e1x / fabs(e2x);
+      yu[j] = y[j] + 0.2 * e1y / fabs(e2y);
+    }
+    xx = yy = 0.0;
+    for (j = 0; j < noc; j++) { xx += xu[j]; yy += yu[j]; }
+    xx /= noc;
+    yy /= noc;
+    for (j = 0; j < noc; j++) { x[j] = xu[j] - xx; y[j] = yu[j] - yy; }
+    if (err) {
+      e = tot = 0.0;
+      mutual = 0;
+      for (j = 1; j < noc; j++)
+        for (k = 0; k < j; k++) {
+          d = dd[mutual];
+          tot += d;
+          xd = x[j] - x[k];
+          yd = y[j] - y[k];
+          ee = d - (float)sqrt((double)xd * xd + yd * yd);
+          e += (ee * ee / d);
+          mutual++;
+        }
+      e /= tot;
+      err[i] = e;
+    }
+  }
+  free(xu); free(yu); free(dd);
+  return 0;
+}

@@ -82,6 +82,12 @@ long orc_class_dists(const float *codes, const unsigned char *mask, const int *l
                      int median, int *out_class, int *out_noe, float *out_dists,
                      float *near, int *found);
 
+/* sammon.c:83-127: keep[i] = 0 for the entries remove_identicals drops; returns the number kept */
+long orc_remove_identicals(const float *codes, const unsigned char *mask, long M, int D, int *keep);
+/* sammon.c:129-262 from the given initial positions; err nullable (`length` mapping errors, 240-254) */
+int orc_sammon(const float *codes, const unsigned char *mask, long noc, int D, long length,
+               float *x, float *y, float *err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,6 +196,28 @@ class Oracle(_Lib):
         return codes, ua
 
 
+    def remove_identicals(self, codes, mask=None):
+        codes, mask = _f32(codes), _msk(mask)
+        M, D = codes.shape
+        keep = np.empty(M, np.int32)
+        f = self.lib.orc_remove_identicals
+        f.restype = C.c_long
+        f(_p(codes, _f), _p(mask, _u8), C.c_long(M), C.c_int(D), _p(keep, _i))
+        return np.nonzero(keep)[0]
+
+    def sammon(self, codes, length, x, y, mask=None, errors=False):
+        codes, mask = _f32(codes), _msk(mask)
+        M, D = codes.shape
+        x, y = _f32(x).copy(), _f32(y).copy()
+        err = np.empty(length, np.float32) if errors else None
+        f = self.lib.orc_sammon
+        f.restype = C.c_int
+        if f(_p(codes, _f), _p(mask, _u8), C.c_long(M), C.c_int(D), C.c_long(length), _p(x, _f), _p(y, _f),
+             _p(err, _f)):
+            raise RuntimeError("orc_sammon failed")
+        return (x, y, err) if errors else (x, y)
+
+
 class Reference(_Lib):
     """The unmodified reference behind oracle/ref_driver.c (only if `make ref` was run)."""
     prefix = "ref_"
@@ -260,3 +282,16 @@ class Reference(_Lib):
         if rc:
             raise RuntimeError("ref_lvq_train failed")
         return codes
+
+    def sammon(self, codes, length, seed, mask=None):
+        """init_random(seed); remove_identicals; sammon_iterate -- positions of the surviving entries"""
+        codes, mask = _f32(codes), _msk(mask)
+        M, D = codes.shape
+        x, y = np.empty(M, np.float32), np.empty(M, np.float32)
+        f = self.lib.ref_sammon
+        f.restype = C.c_long
+        n = f(_p(codes, _f), _p(mask, _u8), C.c_long(M), C.c_int(D), C.c_long(length), C.c_int(seed),
+              _p(x, _f), _p(y, _f))
+        if n < 0:
+            raise RuntimeError("ref_sammon failed")
+        return x[:n], y[:n]

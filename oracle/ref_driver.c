@@ -310,3 +310,33 @@ long ref_class_dists(const float *codes, const unsigned char *mask, const int *l
   close_entries(e);
   return n;
 }
+
+/* the reference's sammon.c compiled with -Dmain=ref_sammon_main (oracle/Makefile): init_random(seed),
+ * remove_identicals, sammon_iterate -- exactly what its main() does (sammon.c:462-467).  x/y receive
+ * the positions of the surviving entries; returns how many survived, -1 on failure. */
+struct entries *remove_identicals(struct entries *codes, int *rem);
+struct entries *sammon_iterate(struct entries *codes, int length);
+
+long ref_sammon(const float *codes, const unsigned char *mask, long M, int D, long length, int seed,
+                float *x, float *y)
+{
+  struct entries *e = build_entries(codes, mask, NULL, NULL, NULL, M, D, TOPOL_LVQ, NEIGH_UNKNOWN, 0, 0, NULL);
+  struct entries *sp;
+  struct data_entry *de;
+  eptr p;
+  int removed, old = verbose(-1);
+  long n = 0;
+  if (!e) return -1;
+  verbose(0);
+  init_random(seed);
+  e = remove_identicals(e, &removed);
+  sp = sammon_iterate(e, (int)length);
+  verbose(old);
+  if (!sp) return -1;
+  for (de = rewind_entries(sp, &p); de != NULL; de = next_entry(&p), n++) {
+    x[n] = de->points[0];
+    y[n] = de->points[1];
+  }
+  close_entries(e);
+  return n;
+}

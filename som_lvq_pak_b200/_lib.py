@@ -50,6 +50,8 @@ PROTOTYPES = {
     "bmu_trainer_destroy": (None, [vp]),
     "bmu_qerror2": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_long, vp]),
     "bmu_class_nearest": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, vp, vp]),
+    "bmu_identical_pairs": (C.c_int, [vp, vp, C.c_long, C.c_int, vp, C.c_long, vp]),
+    "bmu_sammon": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_long, vp, vp, vp]),
     "bmu_rand_order": (None, [C.c_long, C.c_int, vp]),
     "bmu_som_schedule": (None, [C.c_long, C.c_long, C.c_long, C.c_float, C.c_float, C.c_int,
                                 C.c_long, vp, vp, vp, vp, vp]),

@@ -16,6 +16,7 @@
 #include "k3_train.h"
 #include "k4_qerror2.h"
 #include "k5_classdist.h"
+#include "k6_sammon.h"
 #include "api_internal.h"
 
 using namespace bmu;
@@ -445,6 +446,113 @@ int bmu_class_nearest(const float *codes, const unsigned char *mask, const int32
     else dist[i] = (float)sqrt((double)d2);                        // lvq_pak.c:315
   }
   free(h_out);
+  return BMU_OK;
+}
+
+// ------------------------------------------------------------------ Sammon's mapping
+// remove_identicals (sammon.c:83-127) needs the pairs at distance exactly 0; they are returned sorted
+// by (i, j) so that the caller can replay the reference's removal walk.
+static int cmp_pair(const void *a, const void *b) {
+  const int32_t *p = (const int32_t *)a, *q = (const int32_t *)b;
+  if (p[0] != q[0]) return p[0] < q[0] ? -1 : 1;
+  return p[1] < q[1] ? -1 : (p[1] > q[1] ? 1 : 0);
+}
+
+int bmu_identical_pairs(const float *codes, const unsigned char *mask, long M, int D, int32_t *pairs, long cap,
+                        long *npairs) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!codes || !npairs || (cap > 0 && !pairs)) return fail(BMU_ERR_ARG, "NULL argument");
+  if (M < 0 || D < 1 || cap < 0) return fail(BMU_ERR_ARG, "bad M, D or cap");
+  *npairs = 0;
+  if (M < 2) return BMU_OK;
+  float *d_codes = nullptr;
+  unsigned char *d_mask = nullptr;
+  int32_t *d_pairs = nullptr;
+  unsigned long long *d_n = nullptr, n = 0;
+  cudaError_t e;
+  if ((e = cudaMalloc((void **)&d_codes, (size_t)M * D * 4)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_pairs, (size_t)(cap > 0 ? cap : 1) * 8)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_n, 8)) == cudaSuccess &&
+      (!mask || (e = cudaMalloc((void **)&d_mask, (size_t)M * D)) == cudaSuccess) &&
+      (e = cudaMemcpyAsync(d_codes, codes, (size_t)M * D * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (!mask || (e = cudaMemcpyAsync(d_mask, mask, (size_t)M * D, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess) &&
+      (e = cudaMemsetAsync(d_n, 0, 8, g_compute)) == cudaSuccess &&
+      (e = k6_pair_dist(d_codes, d_mask, M, D, nullptr, d_pairs, cap, d_n, g_compute)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, g_compute)) == cudaSuccess &&
+      (e = cudaStreamSynchronize(g_compute)) == cudaSuccess) {
+    const long got = (long)n < cap ? (long)n : cap;
+    if (got > 0) e = cudaMemcpy(pairs, d_pairs, (size_t)got * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && got > 0) qsort(pairs, (size_t)got, 8, cmp_pair);
+  }
+  cudaFree(d_codes); cudaFree(d_mask); cudaFree(d_pairs); cudaFree(d_n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BMU_ERR_CUDA, "bmu_identical_pairs: %s", cudaGetErrorString(e));
+  }
+  k1_count_launch(1);
+  *npairs = (long)n;
+  if ((long)n > cap) return fail(BMU_ERR_ARG, "%ld identical pairs, room for %ld", (long)n, cap);
+  return BMU_OK;
+}
+
+// sammon_iterate (sammon.c:129-262): `length` sweeps from the caller's initial (x, y) (sammon.c:159-162).
+// err (nullable, `length` values): the mapping error the reference prints per sweep at -v 2
+// (sammon.c:240-254), sequential float sums over all pairs, computed on the host from the downloaded
+// positions (order dependent; costs a synchronisation per sweep, so leave it NULL unless needed).
+int bmu_sammon(const float *codes, const unsigned char *mask, long M, int D, long length, float *x, float *y,
+               float *err) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!codes || !x || !y) return fail(BMU_ERR_ARG, "NULL argument");
+  if (M < 1 || D < 1 || length < 0) return fail(BMU_ERR_ARG, "bad M, D or length");
+  float *d_codes = nullptr, *d_dd = nullptr, *d_xy = nullptr, *h_dd = nullptr;
+  unsigned char *d_mask = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc((void **)&d_codes, (size_t)M * D * 4)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_dd, (size_t)M * M * 4)) == cudaSuccess &&
+      (e = cudaMalloc((void **)&d_xy, (size_t)M * 16)) == cudaSuccess &&
+      (!mask || (e = cudaMalloc((void **)&d_mask, (size_t)M * D)) == cudaSuccess) &&
+      (e = cudaMemcpyAsync(d_codes, codes, (size_t)M * D * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (!mask || (e = cudaMemcpyAsync(d_mask, mask, (size_t)M * D, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess) &&
+      (e = cudaMemcpyAsync(d_xy, x, (size_t)M * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (e = cudaMemcpyAsync(d_xy + M, y, (size_t)M * 4, cudaMemcpyHostToDevice, g_compute)) == cudaSuccess &&
+      (e = k6_pair_dist(d_codes, d_mask, M, D, d_dd, nullptr, 0, nullptr, g_compute)) == cudaSuccess) {
+    k1_count_launch(1);
+    if (err && length > 0) {
+      h_dd = (float *)malloc((size_t)M * M * 4);
+      if (!h_dd) e = cudaErrorMemoryAllocation;
+      else e = cudaMemcpyAsync(h_dd, d_dd, (size_t)M * M * 4, cudaMemcpyDeviceToHost, g_compute);
+    }
+    for (long it = 0; it < length && e == cudaSuccess; it++) {
+      e = k6_sweep(d_dd, M, d_xy, d_xy + M, d_xy + 2 * M, d_xy + 3 * M, g_sms, g_compute);
+      k1_count_launch(2);
+      if (err && e == cudaSuccess) {
+        if ((e = cudaMemcpyAsync(x, d_xy, (size_t)M * 4, cudaMemcpyDeviceToHost, g_compute)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(y, d_xy + M, (size_t)M * 4, cudaMemcpyDeviceToHost, g_compute)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(g_compute)) != cudaSuccess) break;
+        float ee = 0.0f, tot = 0.0f;
+        for (long j = 1; j < M; j++)
+          for (long k = 0; k < j; k++) {                             // sammon.c:243-252
+            const float d = h_dd[j * M + k];
+            tot += d;
+            const float xd = x[j] - x[k], yd = y[j] - y[k];
+            const float df = d - (float)sqrt((double)xd * xd + yd * yd);
+            ee += (df * df / d);
+          }
+        err[it] = ee / tot;
+      }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x, d_xy, (size_t)M * 4, cudaMemcpyDeviceToHost, g_compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y, d_xy + M, (size_t)M * 4, cudaMemcpyDeviceToHost, g_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+  }
+  free(h_dd);
+  cudaFree(d_codes); cudaFree(d_mask); cudaFree(d_dd); cudaFree(d_xy);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? BMU_ERR_NOMEM : BMU_ERR_CUDA, "bmu_sammon: %s", cudaGetErrorString(e));
+  }
   return BMU_OK;
 }
 

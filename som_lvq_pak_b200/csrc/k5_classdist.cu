@@ -13,77 +13,29 @@
 // sums are non-negative, so unsigned order is float order; NaN and +Inf sort above FLT_MAX and are
 // never taken, like `dist < dissf` in the reference).  FP32 issue bound, 3 lane-ops per element.
 #include "common.cuh"
+#include "pairtile.cuh"
 #include "k5_classdist.h"
 
 namespace bmu {
 
-#define K5_T 64          // pairs tile edge
-#define K5_DC 32         // components per stage
-#define K5_LD (K5_T + 1) // padded row of the [component][vector] tiles
+#define K5_T PT_T
 
 template <bool MASKED>
 __global__ void __launch_bounds__(256)
 k5_class_nearest_kernel(const float *__restrict__ codes, const unsigned char *__restrict__ mask,
                         const int32_t *__restrict__ label, long M, int D, int ntiles,
                         uint32_t *__restrict__ d2bits, uint32_t *__restrict__ flags) {
-  __shared__ float sa[K5_DC * K5_LD], sb[K5_DC * K5_LD];
-  __shared__ unsigned char ma[MASKED ? K5_DC * K5_LD : 1], mb[MASKED ? K5_DC * K5_LD : 1];
+  __shared__ PairTileSmem<MASKED> ts;
   __shared__ uint32_t smin[K5_T], sflag[K5_T];
-  // linear block index -> (ti, tj) with tj >= ti
-  int ti = 0, rem = blockIdx.x;
-  while (rem >= ntiles - ti) { rem -= ntiles - ti; ti++; }
-  const int tj = ti + rem;
+  int ti, tj;
+  pair_tile_index(blockIdx.x, ntiles, ti, tj);
   const long i0 = (long)ti * K5_T, j0 = (long)tj * K5_T;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   if (tid < K5_T) { smin[tid] = 0x7f800000u; sflag[tid] = 0u; }
 
   float acc[4][4];
   int nmask[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) { acc[r][c] = 0.0f; nmask[r][c] = 0; }
-
-  for (int d0 = 0; d0 < D; d0 += K5_DC) {
-    __syncthreads();
-    // 64 vectors x 32 components per tile; consecutive threads read consecutive components
-    for (int e = tid; e < K5_T * K5_DC; e += 256) {
-      const int v = e >> 5, c = e & 31;
-      const bool cin = d0 + c < D;
-      const long gi = i0 + v, gj = j0 + v;
-      sa[c * K5_LD + v] = (cin && gi < M) ? codes[gi * D + d0 + c] : 0.0f;
-      sb[c * K5_LD + v] = (cin && gj < M) ? codes[gj * D + d0 + c] : 0.0f;
-      if (MASKED) {
-        ma[c * K5_LD + v] = (cin && gi < M) ? mask[gi * D + d0 + c] : 1;
-        mb[c * K5_LD + v] = (cin && gj < M) ? mask[gj * D + d0 + c] : 1;
-      }
-    }
-    __syncthreads();
-    const int dc = (D - d0 < K5_DC) ? D - d0 : K5_DC;
-#pragma unroll 4
-    for (int c = 0; c < dc; c++) {
-      float a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; r++) { a[r] = sa[c * K5_LD + ty * 4 + r]; b[r] = sb[c * K5_LD + tx * 4 + r]; }
-      if (MASKED) {
-        unsigned char xa[4], xb[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) { xa[r] = ma[c * K5_LD + ty * 4 + r]; xb[r] = mb[c * K5_LD + tx * 4 + r]; }
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            if (xa[r] | xb[q]) nmask[r][q]++;
-            else acc[r][q] = sq_acc(acc[r][q], b[q], a[r]);      // later - earlier, lvq_pak.c:306
-          }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) acc[r][q] = sq_acc(acc[r][q], b[q], a[r]);
-      }
-    }
-  }
+  pair_tile_sums<MASKED>(codes, mask, M, D, i0, j0, ts, acc, nmask);   // later - earlier, lvq_pak.c:306
 
 #pragma unroll
   for (int r = 0; r < 4; r++) {

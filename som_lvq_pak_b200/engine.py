@@ -209,6 +209,52 @@ def class_distances(codes, labels, median=True, mask=None):
     return np.array(cls, np.int32), np.array(noe, np.int32), out
 
 
+def identical_pairs(codes, mask=None, cap=1 << 20):
+    """pairs (i < j) of code vectors at vector_dist_euc == 0.0, sorted (remove_identicals, sammon.c:83-127)"""
+    codes = _f32(codes)
+    mask = _opt(mask, np.uint8)
+    M, D = codes.shape
+    pairs = np.empty((cap, 2), np.int32)
+    n = C.c_long(0)
+    _lib.check(_lib.load().bmu_identical_pairs(_ptr(codes), _ptr(mask), M, D, _ptr(pairs), cap, C.byref(n)))
+    return pairs[:n.value].copy()
+
+
+def remove_identicals(codes, mask=None):
+    """indices of the entries remove_identicals (sammon.c:83-127) keeps: walking the list, every later
+    entry still present at distance 0 from the current one is dropped"""
+    M = np.asarray(codes).shape[0]
+    alive = np.ones(M, bool)
+    for i, j in identical_pairs(codes, mask):          # sorted by (i, j): the order of the reference's walk
+        if alive[i] and alive[j]:
+            alive[j] = False
+    return np.nonzero(alive)[0]
+
+
+def sammon_init(M, seed):
+    """initial positions of sammon_iterate (sammon.c:159-162) after init_random(seed)"""
+    state = int(seed)
+    x = np.empty(M, np.float32)
+    for i in range(M):
+        state = (state * 23) % 100000001               # orand, lvq_pak.c:470-473
+        x[i] = np.float32(state % 32767 % M) / np.float32(M)
+    y = np.arange(M, dtype=np.float32) / np.float32(M)
+    return x, y
+
+
+def sammon(codes, length, x, y, mask=None, errors=False):
+    """sammon_iterate (sammon.c:129-262) from the initial positions (x, y); returns the final ones
+    (and the per-sweep mapping errors when errors=True)"""
+    codes = _f32(codes)
+    mask = _opt(mask, np.uint8)
+    M, D = codes.shape
+    x = np.ascontiguousarray(x, np.float32).copy()
+    y = np.ascontiguousarray(y, np.float32).copy()
+    err = np.empty(length, np.float32) if errors else None
+    _lib.check(_lib.load().bmu_sammon(_ptr(codes), _ptr(mask), M, D, length, _ptr(x), _ptr(y), _ptr(err)))
+    return (x, y, err) if errors else (x, y)
+
+
 # ---------------------------------------------------------------------------- host helpers
 def rand_order(n, seed):
     """list order after `-rand seed` (datafile.c:1152-1188 driven by lvq_pak.c:459-473)"""

@@ -1156,6 +1156,115 @@ int mindist_main(int argc, char **argv) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ sammon */
+/* sammon.c:420-490: remove_identicals (83-127) + sammon_iterate (129-262) + save_entries.  The
+ * O(M^2 D) distance loops and the O(M^2) sweeps run on the device (bmu_identical_pairs, bmu_sammon);
+ * the removal walk with its message numbering, the generator for the initial positions and the file
+ * stay here.  The PostScript picture (-eps / -ps) is not produced. */
+int sammon_main(int argc, char **argv) {
+  struct pak_entries *codes, *out;
+  const char *cin_name, *cout_name, *s;
+  long length, i, j, noc, nl = 0, npairs = 0, cap;
+  unsigned long next;
+  int32_t *pairs;
+  unsigned char *alive;
+  float *x, *y, *err = NULL;
+  global_options(argc, argv);
+  cin_name = need(argc, argv, "-cin");
+  cout_name = need(argc, argv, "-cout");
+  length = atol(need(argc, argv, "-rlen"));
+  s = opt(argc, argv, "-rand");
+  next = (unsigned long)(int)(s ? atol(s) : 0);
+  if (!next) next = (unsigned long)(int)time(NULL);                   /* init_random, lvq_pak.c:478-484 */
+  if (flag(argc, argv, "-eps") || flag(argc, argv, "-ps"))
+    fprintf(stderr, "note: the PostScript picture (-eps / -ps) is not provided by the B200 host\n");
+  if (verbose_level >= 2) fprintf(stderr, "Code entries from file %s\n", cin_name);
+  codes = pak_load(cin_name, 0, 1);
+  if (!codes) { fprintf(stderr, "can't open code file %s\n", cin_name); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+
+  /* remove_identicals: for the entry at place ii of the CURRENT list, every later entry still in the
+   * list at distance 0 goes; the counter ij steps by two after a removal (sammon.c:104-118) */
+  cap = 4 * codes->n + 1024;
+  pairs = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)cap);
+  alive = (unsigned char *)malloc((size_t)(codes->n > 0 ? codes->n : 1));
+  if (!pairs || !alive) return 1;
+  if (bmu_identical_pairs(codes->points, codes->mask, codes->n, codes->dim, pairs, cap, &npairs)) {
+    if (npairs <= cap) return engine_failed("bmu_identical_pairs");
+    free(pairs);                                                      /* a codebook full of duplicates */
+    cap = npairs;
+    pairs = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)cap);
+    if (!pairs || bmu_identical_pairs(codes->points, codes->mask, codes->n, codes->dim, pairs, cap, &npairs))
+      return engine_failed("bmu_identical_pairs");
+  }
+  memset(alive, 1, (size_t)(codes->n > 0 ? codes->n : 1));
+  {
+    long p = 0, before = 0, at = 0;                                   /* alive entries in front of `at` */
+    while (p < npairs) {
+      const long cur = pairs[2 * p];
+      long q = p, ij;
+      while (q < npairs && pairs[2 * q] == cur) q++;
+      for (; at < cur; at++) before += alive[at];
+      if (alive[cur]) {
+        const long ii = before + 1;
+        long t = p;
+        ij = ii + 1;
+        for (j = cur + 1; j < codes->n && t < q; j++) {
+          if (!alive[j]) continue;
+          while (t < q && pairs[2 * t + 1] < j) t++;
+          if (t < q && pairs[2 * t + 1] == j) {
+            fprintf(stderr, "Identical entries in codebook ");
+            fprintf(stderr, "(entries %d, %d), removing one.\n", (int)ii, (int)ij);
+            alive[j] = 0;
+            ij += 2;
+          } else {
+            ij++;
+          }
+        }
+      }
+      p = q;
+    }
+  }
+  noc = 0;
+  for (i = 0; i < codes->n; i++) noc += alive[i];
+
+  out = pak_alloc(2, noc);
+  x = (float *)malloc(sizeof(float) * (size_t)(noc > 0 ? noc : 1));
+  y = (float *)malloc(sizeof(float) * (size_t)(noc > 0 ? noc : 1));
+  if (verbose_level >= 2 && length > 0) err = (float *)malloc(sizeof(float) * (size_t)length);
+  if (!out || !x || !y) return 1;
+  out->topol = codes->topol; out->neigh = codes->neigh; out->xdim = codes->xdim; out->ydim = codes->ydim;
+  out->lab_pool = (int *)malloc(sizeof(int) * (size_t)(codes->lab_off[codes->n] > 0 ? codes->lab_off[codes->n] : 1));
+  if (!out->lab_pool) return 1;
+  for (i = 0, j = 0; i < codes->n; i++) {                              /* compact the survivors in place */
+    long l;
+    if (!alive[i]) continue;
+    if (j != i) {
+      memmove(codes->points + (size_t)j * codes->dim, codes->points + (size_t)i * codes->dim, sizeof(float) * codes->dim);
+      if (codes->mask) memmove(codes->mask + (size_t)j * codes->dim, codes->mask + (size_t)i * codes->dim, (size_t)codes->dim);
+    }
+    for (l = codes->lab_off[i]; l < codes->lab_off[i + 1]; l++) out->lab_pool[nl++] = codes->lab_pool[l];
+    j++;
+    out->lab_off[j] = nl;
+  }
+  for (i = 0; i < noc; i++) {                                          /* sammon.c:159-162 */
+    next = (next * 23) % 100000001;                                   /* orand, lvq_pak.c:470-473 */
+    x[i] = (float)((long)(int)(next % 32767L) % noc) / noc;
+    y[i] = (float)(i) / noc;
+  }
+  if (noc > 0 && bmu_sammon(codes->points, codes->mask, noc, codes->dim, length, x, y, err))
+    return engine_failed("bmu_sammon");
+  if (err)
+    for (i = 0; i < length; i++) fprintf(stdout, "Mapping error: %7.3f\n", err[i]);
+  for (i = 0; i < noc; i++) { out->points[2 * i] = x[i]; out->points[2 * i + 1] = y[i]; }
+  if (verbose_level >= 2) fprintf(stderr, "Save code entries to file %s\n", cout_name);
+  if (pak_save(out, cout_name)) return 1;
+  free(pairs); free(alive); free(x); free(y); free(err);
+  pak_free(codes);
+  pak_free(out);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ pakstat */
 /* load only: entries, dimension, a checksum of the values and the time the loader took */
 int pakstat_main(int argc, char **argv) {
