@@ -10,9 +10,10 @@
 //   k6_pair_dist_kernel   the full symmetric M x M distance matrix (row j contiguous, so a warp reads
 //                         its row coalesced) from the shared 64 x 64 pair tile (pairtile.cuh), and the
 //                         list of pairs at distance exactly 0 for remove_identicals;
-//   k6_sweep_kernel       one warp per point j: lanes compute the four terms of 32 consecutive k in
-//                         parallel, park them in shared memory, and the running sums are then advanced
-//                         in k order (a float add is not associative, so this chain cannot be a tree);
+//   k6_sweep_kernel       a CTA per 32 points j: seven warps compute the four terms of every (j, k) pair
+//                         into shared memory, chunk by chunk, while the eighth advances the 32 running
+//                         sums, one per lane, in k order (a float add is not associative, so each chain
+//                         is sequential; giving a chain a lane keeps the conversions it needs fully used);
 //   k6_center_kernel      one CTA: sequential float sums of xu / yu, then the parallel subtraction.
 // FP64-pipe and latency bound; the distance matrix (4 M^2 bytes) stays resident across sweeps.
 #include "common.cuh"
@@ -56,55 +57,71 @@ k6_pair_dist_kernel(const float *__restrict__ codes, const unsigned char *__rest
   }
 }
 
-#define K6_WARPS 8
+#define K6_JT 32          // points per CTA: one lane of the summing warp each
+#define K6_KC 32          // partners per chunk
+#define K6_THREADS 256    // warp 0 sums, warps 1..7 compute terms
 
-__global__ void __launch_bounds__(K6_WARPS * 32)
+struct K6Terms {
+  float t1x[K6_KC][K6_JT], t1y[K6_KC][K6_JT];
+  double t2x[K6_KC][K6_JT], t2y[K6_KC][K6_JT];
+};
+
+// One CTA owns 32 points j.  The running sums of a point are a strictly sequential float/double chain
+// over all partners k, so the chain is given a LANE (32 chains advance per instruction of warp 0)
+// while the other seven warps compute the terms of the next chunk of 32 partners into the second
+// shared-memory buffer ([k][j]: conflict free for both sides).  dd is symmetric, so the producers read
+// dd[k][j0 + lane], contiguous across the lanes.
+__global__ void __launch_bounds__(K6_THREADS)
 k6_sweep_kernel(const float *__restrict__ dd, long M, const float *__restrict__ x, const float *__restrict__ y,
                 float *__restrict__ xu, float *__restrict__ yu) {
-  __shared__ float s1x[K6_WARPS][32], s1y[K6_WARPS][32];
-  __shared__ double s2x[K6_WARPS][32], s2y[K6_WARPS][32];
+  __shared__ K6Terms buf[2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long warp0 = (long)blockIdx.x * K6_WARPS + w, nwarps = (long)gridDim.x * K6_WARPS;
-  for (long j = warp0; j < M; j += nwarps) {
-    const float xj = x[j], yj = y[j];
-    const float *row = dd + j * M;
-    float e1x = 0.0f, e1y = 0.0f, e2x = 0.0f, e2y = 0.0f;
-    for (long k0 = 0; k0 < M; k0 += 32) {
-      const long k = k0 + lane;
-      if (k < M && k != j) {
-        const float xd = __fsub_rn(xj, x[k]), yd = __fsub_rn(yj, y[k]);
-        // (float) sqrt((double) xd * xd + yd * yd): double product + float product, added in double
-        const float dpj = (float)sqrt(__dadd_rn(__dmul_rn((double)xd, (double)xd), (double)__fmul_rn(yd, yd)));
-        const float dt = row[k];
-        const float dq = __fsub_rn(dt, dpj), dr = __fmul_rn(dt, dpj);
-        s1x[w][lane] = __fdiv_rn(__fmul_rn(xd, dq), dr);                       // xd * dq / dr
-        s1y[w][lane] = __fdiv_rn(__fmul_rn(yd, dq), dr);
-        const double u = __dadd_rn(1.0, (double)__fdiv_rn(dq, dpj));           // 1.0 + dq / dpj
-        // (dq - xd * xd * (1.0 + dq / dpj) / dpj) / dr
-        s2x[w][lane] = __ddiv_rn(__dsub_rn((double)dq, __ddiv_rn(__dmul_rn((double)__fmul_rn(xd, xd), u), (double)dpj)),
-                                 (double)dr);
-        s2y[w][lane] = __ddiv_rn(__dsub_rn((double)dq, __ddiv_rn(__dmul_rn((double)__fmul_rn(yd, yd), u), (double)dpj)),
-                                 (double)dr);
+  const long j = (long)blockIdx.x * K6_JT + lane;
+  const long jc = j < M ? j : M - 1;                       // idle lanes of the last CTA repeat the last point
+  const float xj = x[jc], yj = y[jc];
+  float e1x = 0.0f, e1y = 0.0f, e2x = 0.0f, e2y = 0.0f;    // warp 0 only
+  const long nchunks = (M + K6_KC - 1) / K6_KC;
+  for (long c = 0; c <= nchunks; c++) {
+    if (w > 0) {
+      if (c < nchunks) {
+        K6Terms &t = buf[c & 1];
+        const long k0 = c * K6_KC;
+        for (int kl = w - 1; kl < K6_KC; kl += 7) {
+          const long k = k0 + kl;
+          if (k >= M) break;
+          const float xd = __fsub_rn(xj, x[k]), yd = __fsub_rn(yj, y[k]);
+          // (float) sqrt((double) xd * xd + yd * yd): double product + float product, added in double
+          const float dpj = (float)sqrt(__dadd_rn(__dmul_rn((double)xd, (double)xd), (double)__fmul_rn(yd, yd)));
+          const float dt = dd[k * M + jc];
+          const float dq = __fsub_rn(dt, dpj), dr = __fmul_rn(dt, dpj);
+          t.t1x[kl][lane] = __fdiv_rn(__fmul_rn(xd, dq), dr);                     // xd * dq / dr
+          t.t1y[kl][lane] = __fdiv_rn(__fmul_rn(yd, dq), dr);
+          const double u = __dadd_rn(1.0, (double)__fdiv_rn(dq, dpj));           // 1.0 + dq / dpj
+          const double ddq = (double)dq, ddpj = (double)dpj, ddr = (double)dr;
+          // (dq - xd * xd * (1.0 + dq / dpj) / dpj) / dr
+          t.t2x[kl][lane] = __ddiv_rn(__dsub_rn(ddq, __ddiv_rn(__dmul_rn((double)__fmul_rn(xd, xd), u), ddpj)), ddr);
+          t.t2y[kl][lane] = __ddiv_rn(__dsub_rn(ddq, __ddiv_rn(__dmul_rn((double)__fmul_rn(yd, yd), u), ddpj)), ddr);
+        }
       }
-      __syncwarp();
-      const int n = (M - k0 < 32) ? (int)(M - k0) : 32;
-      const int skip = (j >= k0 && j < k0 + 32) ? (int)(j - k0) : -1;
-      // every lane advances the same chain (uniform, broadcast reads); lane 0's copy is stored
-#pragma unroll 8
-      for (int l = 0; l < n; l++) {
-        if (l == skip) continue;
-        e1x = __fadd_rn(e1x, s1x[w][l]);
-        e1y = __fadd_rn(e1y, s1y[w][l]);
-        e2x = (float)__dadd_rn((double)e2x, s2x[w][l]);
-        e2y = (float)__dadd_rn((double)e2y, s2y[w][l]);
+    } else if (c > 0) {
+      const K6Terms &t = buf[(c - 1) & 1];
+      const long k0 = (c - 1) * K6_KC;
+      const int n = (M - k0 < K6_KC) ? (int)(M - k0) : K6_KC;
+#pragma unroll 4
+      for (int kl = 0; kl < n; kl++) {
+        if (k0 + kl == j) continue;                                               // sammon.c:202-203
+        e1x = __fadd_rn(e1x, t.t1x[kl][lane]);
+        e1y = __fadd_rn(e1y, t.t1y[kl][lane]);
+        e2x = (float)__dadd_rn((double)e2x, t.t2x[kl][lane]);
+        e2y = (float)__dadd_rn((double)e2y, t.t2y[kl][lane]);
       }
-      __syncwarp();
     }
-    if (lane == 0) {
-      // x[j] + MAGIC * e1x / fabs(e2x): all in double, rounded on the store (sammon.c:220-221)
-      xu[j] = (float)__dadd_rn((double)xj, __ddiv_rn(__dmul_rn(0.2, (double)e1x), fabs((double)e2x)));
-      yu[j] = (float)__dadd_rn((double)yj, __ddiv_rn(__dmul_rn(0.2, (double)e1y), fabs((double)e2y)));
-    }
+    __syncthreads();
+  }
+  if (w == 0 && j < M) {
+    // x[j] + MAGIC * e1x / fabs(e2x): all in double, rounded on the store (sammon.c:220-221)
+    xu[j] = (float)__dadd_rn((double)xj, __ddiv_rn(__dmul_rn(0.2, (double)e1x), fabs((double)e2x)));
+    yu[j] = (float)__dadd_rn((double)yj, __ddiv_rn(__dmul_rn(0.2, (double)e1y), fabs((double)e2y)));
   }
 }
 
@@ -148,10 +165,9 @@ cudaError_t k6_pair_dist(const float *d_codes, const unsigned char *d_mask, long
 
 cudaError_t k6_sweep(const float *d_dd, long M, float *d_x, float *d_y, float *d_xu, float *d_yu, int num_sms,
                      cudaStream_t st) {
-  long blocks = (M + K6_WARPS - 1) / K6_WARPS;
-  const long cap = (long)num_sms * 8;
-  if (blocks > cap) blocks = cap;
-  k6_sweep_kernel<<<(unsigned)blocks, K6_WARPS * 32, 0, st>>>(d_dd, M, d_x, d_y, d_xu, d_yu);
+  (void)num_sms;
+  const long blocks = (M + K6_JT - 1) / K6_JT;
+  k6_sweep_kernel<<<(unsigned)blocks, K6_THREADS, 0, st>>>(d_dd, M, d_x, d_y, d_xu, d_yu);
   k6_center_kernel<<<1, 1024, 0, st>>>(M, d_xu, d_yu, d_x, d_y);
   return cudaGetLastError();
 }
