@@ -16,6 +16,7 @@
 //   k1_warp_kernel    any k <= 16, masks: one warp per sample, lanes over code vectors
 //   k1_seq_kernel     rows with NaN/Inf: one thread per sample, the reference's loop
 //                     including its early exit (whose side effects are visible with NaN)
+#include <stdlib.h>
 #include "common.cuh"
 #include "k1_search.h"
 
@@ -455,6 +456,7 @@ k1_warp8_kernel(const float *__restrict__ data, const float *__restrict__ cT, lo
         for (int r = 0; r < 8; r++)
 #pragma unroll
           for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+#pragma unroll 4
         for (int i = 0; i < D; i++) {
           const float *cr = cbase + (long)i * K1_TC;
           const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
