@@ -338,7 +338,7 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
           a3 = sq_acc(a3, cr[96], xi);
         }
       } else {
-#pragma unroll 4
+#pragma unroll 16
         for (int i = 0; i < D; i++) {
           const float xi = __ldg(x + i);
           const float *cr = cbase + (long)i * K1_TC;
