@@ -144,3 +144,29 @@ def test_record_kernel_every_k_depth(engine, oracle, D):
     finally:
         engine.set_search_path(0)
     assert bd["k2_certified"] + bd["k2_failed"] == N and bd["k2_certified"] >= 0.9 * N, bd
+
+
+@pytest.mark.parametrize("path", [0, 2])
+@pytest.mark.parametrize("M,D,N,k", [(1500, 2048, 600, 1), (1500, 2048, 300, 5), (65536, 128, 3000, 1),
+                                     (100000, 16, 4000, 1), (100000, 16, 2000, 3), (513, 3000, 257, 2),
+                                     (40000, 8, 5000, 1)])
+def test_search_extreme_shapes(engine, oracle, M, D, N, k, path):
+    """large D (many operand K slices, streaming kernel), large M (C5's 256 x 256 map, more code tiles than
+    one pass holds), very low D with a huge codebook; the oracle checks a subsample of the rows"""
+    rng = np.random.default_rng(M + D + k)
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    data[3] = codes[M - 1]                                  # exact hit on the last code
+    data[4] = codes[0]
+    engine.set_search_path(path)
+    try:
+        idx, diff, nf = engine.find_winner_knn(codes, data, k)
+    finally:
+        engine.set_search_path(0)
+    budget = 1.5e9                                          # element-ops for the oracle
+    sub = np.arange(N)[: max(16, int(budget / (M * D)))]
+    e = oracle.search(codes, data[sub], k)
+    assert_bits_equal(idx[sub], e[0], "idx")
+    assert_bits_equal(diff[sub], e[1], "diff")
+    assert (nf == k).all()
+    assert idx[3, 0] == M - 1 and diff[3, 0] == 0.0 and idx[4, 0] == 0
