@@ -1260,6 +1260,10 @@ static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratc
 // step; that kernel on a second stream beside the GEMM of the next sub-batch 15.7 ms, but the GEMM
 // launches stretched from 12.3 to 13.4 ms (its L2 gathers competed with the code-tile stream and the
 // pipeline needed sub-batch tails); re-rank warps inside the GEMM kernel: see DESIGN.md.
+// Also tried and rejected: the row prep of sub-batches 1.. on a second stream beside the record kernel of
+// the sub-batch before (prep CTAs held to 32 registers so that they fit on an SM next to the record
+// CTA): the record launches stretched by exactly the prep time that was hidden (12.2 -> 13.1 ms at 4
+// sub-batches, step 13.9 ms either way), so prep stays one launch in front.
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   cudaError_t e = k2_launch_prep(c, a, s, 0, a.N, 0, st);
   if (e != cudaSuccess) return e;
