@@ -268,10 +268,15 @@ def main_gpu(args, w):
     ms = e0.elapsed_time(e1)
     launches = lib.bmu_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    # duration of the dominant kernel, measured live with CUDA events on the launching stream
-    # (events bracket every kernel inside the library; read for the last timed step)
-    lib.bmu_last_search_kernel_ms(kms)
-    kernel_ms = [float(x) for x in kms]
+    # duration of the dominant kernel, measured live with CUDA events on the launching stream: events
+    # bracket every kernel inside the library and are kept for the last 32 calls, so the figures below
+    # are the AVERAGE over the timed steps (the board's power cap makes late steps slower than early ones)
+    nhist = min(args.steps, 32)
+    kernel_ms = [0.0] * 8
+    for back in range(nhist):
+        lib.bmu_search_kernel_ms_history(back, kms)
+        for i in range(8):
+            kernel_ms[i] += float(kms[i]) / nhist
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -432,12 +437,16 @@ def c4_extra(bmu, lib, _lib, dev, peaks):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        lib.bmu_last_search_kernel_ms(kms)
+        avg = [0.0] * 8
+        for back in range(steps):                                          # average over the timed steps
+            lib.bmu_search_kernel_ms_history(back, kms)
+            for i in range(8):
+                avg[i] += float(kms[i]) / steps
         bd = bmu.last_search_breakdown()
-        gemm_ms = float(kms[5])
+        gemm_ms = avg[5]
         out["k%d" % k] = {"value": rows / (ms * 1e-3), "unit": "searches/s", "ms_per_step": ms,
-                          "kernel_ms": {"k2_row_prep": float(kms[4]), "k2_gemm": gemm_ms, "k2_rerank": float(kms[6]),
-                                        "k2_lists": float(kms[7])},
+                          "kernel_ms": {"k2_row_prep": avg[4], "k2_gemm": gemm_ms, "k2_rerank": avg[6],
+                                        "k2_lists": avg[7]},
                           "gemm_tflops_algorithmic": 2.0 * M * D * rows / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
                           "gemm_frac_of_sustained_peak": (2.0 * M * D * rows / (gemm_ms * 1e-3) / 1e12 / peak) if gemm_ms > 0 else None,
                           "rows_certified": bd["k2_certified"], "rows_redone_exactly": bd["k2_failed"]}

@@ -80,6 +80,9 @@ int bmu_last_search_breakdown(long out[5]);
  * each family: K1 [0] data_prep, [1] k1_fast, [2] k1_warp, [3] k1_seq; K2 [4] row_prep,
  * [5] gemm + fused top-k, [6] exact re-rank, [7] K1 fallback lists.  Synchronises. */
 int bmu_last_search_kernel_ms(float out[8]);
+/* the same for the search `back` calls ago within each family (0 = the last one; zeros beyond the 32
+ * calls that are kept), so that a timed loop can be read after its closing synchronisation */
+int bmu_search_kernel_ms_history(int back, float out[8]);
 
 /* ---- codebook (replicated on every GPU; reference: struct entries *codes) --------- */
 typedef struct bmu_codebook bmu_codebook;

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "bmu_launch_count": (C.c_long, []),
     "bmu_last_search_breakdown": (C.c_int, [C.POINTER(C.c_long)]),
     "bmu_last_search_kernel_ms": (C.c_int, [c_f]),
+    "bmu_search_kernel_ms_history": (C.c_int, [C.c_int, c_f]),
     "bmu_codebook_create": (vp, [vp, C.c_long, C.c_int]),
     "bmu_codebook_create_dev": (vp, [vp, C.c_long, C.c_int]),
     "bmu_codebook_update": (C.c_int, [vp, vp]),

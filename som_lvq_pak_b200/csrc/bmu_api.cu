@@ -153,6 +153,12 @@ int bmu_last_search_kernel_ms(float out[8]) {
   return BMU_OK;
 }
 
+int bmu_search_kernel_ms_history(int back, float out[8]) {
+  CK(k1_kernel_ms_history(back, out));
+  CK(k2_kernel_ms_history(back, out + 4));
+  return BMU_OK;
+}
+
 int bmu_last_search_breakdown(long out[5]) {
   for (int i = 0; i < 5; i++) out[i] = 0;
   if (!g_last_counters) return BMU_OK;

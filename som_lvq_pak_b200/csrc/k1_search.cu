@@ -577,24 +577,29 @@ cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT
 }
 
 // CUDA events around each kernel of the last k1_search call, on the launching stream
-static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-static bool g_ev_valid = false;
+static cudaEvent_t g_evring[K_EV_RING][5];
+static cudaEvent_t *g_ev = g_evring[0];
+static long g_evcalls = 0;
 
-cudaError_t k1_last_kernel_ms(float out[4]) {
+cudaError_t k1_kernel_ms_history(int back, float out[4]) {
   for (int i = 0; i < 4; i++) out[i] = 0.0f;
-  if (!g_ev_valid) return cudaSuccess;
-  cudaError_t e = cudaEventSynchronize(g_ev[4]);
+  if (back < 0 || back >= K_EV_RING || back >= g_evcalls) return cudaSuccess;
+  cudaEvent_t *ev = g_evring[(g_evcalls - 1 - back) % K_EV_RING];
+  cudaError_t e = cudaEventSynchronize(ev[4]);
   if (e != cudaSuccess) return e;
   for (int i = 0; i < 4; i++) {
-    e = cudaEventElapsedTime(&out[i], g_ev[i], g_ev[i + 1]);
+    e = cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
 
+cudaError_t k1_last_kernel_ms(float out[4]) { return k1_kernel_ms_history(0, out); }
+
 cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   static bool attr_set = false;
   cudaError_t e;
+  g_ev = g_evring[g_evcalls % K_EV_RING];
   if (!g_ev[0])
     for (int i = 0; i < 5; i++)
       if ((e = cudaEventCreate(&g_ev[i])) != cudaSuccess) return e;
@@ -628,7 +633,7 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   cudaEventRecord(g_ev[3], st);
   if ((e = k1_run_seq_list(a, st)) != cudaSuccess) return e;
   cudaEventRecord(g_ev[4], st);
-  g_ev_valid = true;
+  g_evcalls++;
   return cudaSuccess;
 }
 

@@ -41,7 +41,10 @@ cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st);
 cudaError_t k1_run_seq_list(const K1Args &a, cudaStream_t st);
 cudaError_t k1_run_lists(const K1Args &a, cudaStream_t st);
 // device time of [data_prep, k1_fast, k1_warp, k1_seq] of the last k1_search call (ms)
+#define K_EV_RING 32
 cudaError_t k1_last_kernel_ms(float out[4]);
+// the same for the call `back` calls ago (0 = last; zeros beyond the ring of K_EV_RING calls)
+cudaError_t k1_kernel_ms_history(int back, float out[4]);
 long k1_launch_count();
 void k1_count_launch(int n);
 

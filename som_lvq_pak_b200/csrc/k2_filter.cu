@@ -1130,8 +1130,11 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
   return cudaGetLastError();
 }
 
-static cudaEvent_t g_k2ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-static bool g_k2ev_valid = false;
+// CUDA events around the phases of the last K_EV_RING k2_search calls (a ring, so that a benchmark can
+// read every step of its timed region after the closing synchronisation instead of the last one only)
+static cudaEvent_t g_k2ring[K_EV_RING][5];
+static cudaEvent_t *g_k2ev = g_k2ring[0];
+static long g_k2calls = 0;
 
 // Sub-batch pipeline shared by both GEMM kernels: the re-rank of sub-batch i runs on a second stream
 // beside the GEMM kernel of sub-batch i+1 (see k2_run_record).
@@ -1281,18 +1284,22 @@ static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch
   return e;
 }
 
-cudaError_t k2_last_kernel_ms(float out[4]) {
+cudaError_t k2_kernel_ms_history(int back, float out[4]) {
   out[0] = out[1] = out[2] = out[3] = 0.0f;
-  if (!g_k2ev_valid) return cudaSuccess;
-  cudaError_t e = cudaEventSynchronize(g_k2ev[4]);
+  if (back < 0 || back >= K_EV_RING || back >= g_k2calls) return cudaSuccess;
+  cudaEvent_t *ev = g_k2ring[(g_k2calls - 1 - back) % K_EV_RING];
+  cudaError_t e = cudaEventSynchronize(ev[4]);
   if (e != cudaSuccess) return e;
   for (int i = 0; i < 4; i++)
-    if ((e = cudaEventElapsedTime(&out[i], g_k2ev[i], g_k2ev[i + 1])) != cudaSuccess) return e;
+    if ((e = cudaEventElapsedTime(&out[i], ev[i], ev[i + 1])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
+cudaError_t k2_last_kernel_ms(float out[4]) { return k2_kernel_ms_history(0, out); }
+
 cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *scratch_bytes, cudaStream_t st) {
   cudaError_t e;
+  g_k2ev = g_k2ring[g_k2calls % K_EV_RING];
   if (!g_k2ev[0])
     for (int i = 0; i < 5; i++)
       if ((e = cudaEventCreate(&g_k2ev[i])) != cudaSuccess) return e;
@@ -1339,7 +1346,7 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   // rows that failed the certificate + masked / tiny rows, then the non-finite rows
   if ((e = k1_run_lists(a, st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[4], st);
-  g_k2ev_valid = true;
+  g_k2calls++;
   return cudaSuccess;
 }
 

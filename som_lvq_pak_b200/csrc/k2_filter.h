@@ -22,6 +22,8 @@ void k2_codebook_free(K2Codebook *c);
 // scratch: grow-only device buffer owned by the caller
 // device time of [row_prep, gemm, rerank, fallback lists] of the last k2_search call (ms)
 cudaError_t k2_last_kernel_ms(float out[4]);
+// the same for the call `back` calls ago (0 = last; zeros beyond the ring of K_EV_RING calls)
+cudaError_t k2_kernel_ms_history(int back, float out[4]);
 cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *scratch_bytes,
                       cudaStream_t st);
 
