@@ -79,20 +79,48 @@ k6_sweep_kernel(const float *__restrict__ dd, long M, const float *__restrict__ 
   const long j = (long)blockIdx.x * K6_JT + lane;
   const long jc = j < M ? j : M - 1;                       // idle lanes of the last CTA repeat the last point
   const float xj = x[jc], yj = y[jc];
-  float e1x = 0.0f, e1y = 0.0f, e2x = 0.0f, e2y = 0.0f;    // warp 0 only
+  float e1x = 0.0f, e1y = 0.0f;                            // warp 0 only
+  double e2x = 0.0, e2y = 0.0;                             // float-valued: rounded to float after every add
+  // (rounding the significand in integer arithmetic instead of the two conversions was measured: slower)
   const long nchunks = (M + K6_KC - 1) / K6_KC;
+  constexpr int NP = (K6_KC + 6) / 7;                      // partners per producer warp and chunk
+  // a producer's inputs for the NEXT chunk are loaded while it computes the current one (the dd row
+  // segments come from HBM: 4 M^2 bytes per sweep)
+  float nxt_x[NP], nxt_y[NP], nxt_d[NP];
+#pragma unroll
+  for (int it = 0; it < NP; it++) {
+    const int kl = w - 1 + 7 * it;
+    const bool ok = w > 0 && kl < K6_KC && kl < M;
+    nxt_x[it] = ok ? x[kl] : 0.0f;
+    nxt_y[it] = ok ? y[kl] : 0.0f;
+    nxt_d[it] = ok ? dd[(long)kl * M + jc] : 0.0f;
+  }
   for (long c = 0; c <= nchunks; c++) {
     if (w > 0) {
       if (c < nchunks) {
         K6Terms &t = buf[c & 1];
         const long k0 = c * K6_KC;
-        for (int kl = w - 1; kl < K6_KC; kl += 7) {
+        float cur_x[NP], cur_y[NP], cur_d[NP];
+#pragma unroll
+        for (int it = 0; it < NP; it++) {
+          cur_x[it] = nxt_x[it]; cur_y[it] = nxt_y[it]; cur_d[it] = nxt_d[it];
+          const int kl = w - 1 + 7 * it;
+          const long kn = k0 + K6_KC + kl;
+          const bool ok = kl < K6_KC && kn < M;
+          nxt_x[it] = ok ? x[kn] : 0.0f;
+          nxt_y[it] = ok ? y[kn] : 0.0f;
+          nxt_d[it] = ok ? dd[kn * M + jc] : 0.0f;
+        }
+        // five partners per producer warp, unrolled: their square-root / division chains are independent
+#pragma unroll
+        for (int it = 0; it < NP; it++) {
+          const int kl = w - 1 + 7 * it;
           const long k = k0 + kl;
-          if (k >= M) break;
-          const float xd = __fsub_rn(xj, x[k]), yd = __fsub_rn(yj, y[k]);
+          if (kl >= K6_KC || k >= M) continue;
+          const float xd = __fsub_rn(xj, cur_x[it]), yd = __fsub_rn(yj, cur_y[it]);
           // (float) sqrt((double) xd * xd + yd * yd): double product + float product, added in double
           const float dpj = (float)sqrt(__dadd_rn(__dmul_rn((double)xd, (double)xd), (double)__fmul_rn(yd, yd)));
-          const float dt = dd[k * M + jc];
+          const float dt = cur_d[it];
           const float dq = __fsub_rn(dt, dpj), dr = __fmul_rn(dt, dpj);
           t.t1x[kl][lane] = __fdiv_rn(__fmul_rn(xd, dq), dr);                     // xd * dq / dr
           t.t1y[kl][lane] = __fdiv_rn(__fmul_rn(yd, dq), dr);
@@ -112,16 +140,16 @@ k6_sweep_kernel(const float *__restrict__ dd, long M, const float *__restrict__ 
         if (k0 + kl == j) continue;                                               // sammon.c:202-203
         e1x = __fadd_rn(e1x, t.t1x[kl][lane]);
         e1y = __fadd_rn(e1y, t.t1y[kl][lane]);
-        e2x = (float)__dadd_rn((double)e2x, t.t2x[kl][lane]);
-        e2y = (float)__dadd_rn((double)e2y, t.t2y[kl][lane]);
+        e2x = (double)(float)__dadd_rn(e2x, t.t2x[kl][lane]);                 // e2x += <double>: float result
+        e2y = (double)(float)__dadd_rn(e2y, t.t2y[kl][lane]);
       }
     }
     __syncthreads();
   }
   if (w == 0 && j < M) {
     // x[j] + MAGIC * e1x / fabs(e2x): all in double, rounded on the store (sammon.c:220-221)
-    xu[j] = (float)__dadd_rn((double)xj, __ddiv_rn(__dmul_rn(0.2, (double)e1x), fabs((double)e2x)));
-    yu[j] = (float)__dadd_rn((double)yj, __ddiv_rn(__dmul_rn(0.2, (double)e1y), fabs((double)e2y)));
+    xu[j] = (float)__dadd_rn((double)xj, __ddiv_rn(__dmul_rn(0.2, (double)e1x), fabs(e2x)));
+    yu[j] = (float)__dadd_rn((double)yj, __ddiv_rn(__dmul_rn(0.2, (double)e1y), fabs(e2y)));
   }
 }
 
