@@ -19,6 +19,7 @@ static int dispatch(const char *prog, int argc, char **argv) {
   if (strcmp(prog, "eveninit") == 0 || strcmp(prog, "propinit") == 0) return eveninit_main(argc, argv, prog);
   if (strcmp(prog, "mindist") == 0) return mindist_main(argc, argv);
   if (strcmp(prog, "sammon") == 0) return sammon_main(argc, argv);
+  if (strcmp(prog, "balance") == 0) return balance_main(argc, argv);
   if (strcmp(prog, "cmatr") == 0) return cmatr_main(argc, argv);
   if (strcmp(prog, "setlabel") == 0) return setlabel_main(argc, argv);
   if (strcmp(prog, "elimin") == 0) return elimin_main(argc, argv);
@@ -37,7 +38,7 @@ int main(int argc, char **argv) {
   rc = dispatch(base, argc, argv);
   if (rc == -2 && argc > 1) rc = dispatch(argv[1], argc - 1, argv + 1);
   if (rc == -2) {
-    fprintf(stderr, "usage: bmu_pak <randinit|eveninit|propinit|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n");
+    fprintf(stderr, "usage: bmu_pak <randinit|eveninit|propinit|balance|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n");
     return 2;
   }
   return rc;

@@ -1156,6 +1156,196 @@ int mindist_main(int argc, char **argv) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ balance */
+/* balance.c:45-226: med_distances per class (K5), classes whose median is far below / above the mean
+ * lose / gain one codebook vector, new vectors are picked among the data entries their own knn
+ * neighbours classify correctly (pick_inside_codes, one batched self-search), then one pass of OLVQ1
+ * (length = number of data entries, alpha 0.3) and the medians again.
+ *
+ * Reference quirk, reproduced on purpose: balance.c:160-190 appends the new vectors without counting
+ * them (its comment there says so, in Finnish), so olvq1_training (lvq_rout.c:607-627) sizes its per-unit rate
+ * array by the count BEFORE the additions and the appended units read their rate from beyond the array.
+ * With glibc's allocator those bytes are zero / a denormal chunk header, i.e. the appended units are
+ * never adapted (the reference's ex1b.cod holds them as untouched data vectors) and the .lra file has
+ * one line per counted unit only.  Here: rate 0 for the appended units, .lra of the counted length. */
+static int class_medians(const struct pak_entries *codes, const int32_t *label, struct pak_hitlist *classes,
+                         float *dists) {
+  const size_t n = (size_t)(codes->n > 0 ? codes->n : 1);
+  float *near = (float *)malloc(sizeof(float) * n), *meds = (float *)malloc(sizeof(float) * n);
+  int32_t *found = (int32_t *)malloc(sizeof(int32_t) * n);
+  long c, i;
+  if (!near || !meds || !found) return 1;
+  hit_clear(classes);
+  for (i = 0; i < codes->n; i++) hit_add(classes, label[i]);
+  if (bmu_class_nearest(codes->points, codes->mask, label, codes->n, codes->dim, near, found))
+    return engine_failed("bmu_class_nearest");
+  for (c = 0; c < classes->n; c++) {                                   /* lvq_rout.c:430-470 */
+    long not = 0;
+    dists[c] = 0.0f;
+    for (i = 0; i < codes->n; i++)
+      if (label[i] == classes->label[c] && found[i]) meds[not++] = near[i];
+    if (not > 0) {
+      qsort(meds, (size_t)not, sizeof(float), cmp_float);
+      dists[c] = meds[not / 2];
+    }
+  }
+  free(near); free(meds); free(found);
+  return 0;
+}
+
+int balance_main(int argc, char **argv) {
+  const double BAL = 1.3;                                              /* balance.c:30 */
+  struct pak_entries *data, *codes, *out;
+  struct pak_hitlist classes, more, hits;
+  struct winners w;
+  const char *din, *cin_name, *cout_name, *s;
+  int32_t *label, *data_label, *out_label, *sample;
+  unsigned char *inside;
+  float *dists, *unit_alpha, aver;
+  long *picked, npicked = 0, i, c, nol, kept = 0, counted, nl = 0, total;
+  int *diff, note, knn, t;
+  char lra[2048];
+  global_options(argc, argv);
+  din = need(argc, argv, "-din");
+  cin_name = need(argc, argv, "-cin");
+  cout_name = need(argc, argv, "-cout");
+  s = opt(argc, argv, "-knn");
+  knn = s ? atoi(s) : 5;
+  if (knn < 1) knn = 1;
+  if (knn > BMU_KMAX) { fprintf(stderr, "-knn %d is larger than the engine's limit %d\n", knn, BMU_KMAX); return 1; }
+  if (verbose_level >= 2) fprintf(stderr, "Input entries are read from file %s\n", din);
+  data = pak_load(din, 1, 1);
+  if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  if (verbose_level >= 2) fprintf(stderr, "Codebook entries are read from file %s\n", cin_name);
+  codes = pak_load(cin_name, 1, 1);
+  if (!codes) { fprintf(stderr, "Can't open code file '%s'\n", cin_name); return 1; }
+  if (data->dim != codes->dim) { fprintf(stderr, "Data and codes have different dimensions\n"); return 1; }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+
+  label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(codes->n > 0 ? codes->n : 1));
+  dists = (float *)malloc(sizeof(float) * (size_t)(codes->n + data->n + 1));
+  if (!label || !dists) return 1;
+  for (i = 0; i < codes->n; i++) label[i] = pak_label(codes, i);
+  hit_init(&classes);
+  if (verbose_level >= 2) fprintf(stderr, "Medians of the shortest distances are computed\n");
+  if (class_medians(codes, label, &classes, dists)) return 1;
+  nol = classes.n;
+  diff = (int *)calloc((size_t)(nol > 0 ? nol : 1), sizeof(int));
+  if (!diff) return 1;
+  aver = 0.0f;
+  note = 0;
+  for (c = 0; c < nol; c++)
+    if (classes.freq[c] > 1) { aver += dists[c]; note++; }
+  aver /= note;                                                        /* balance.c:82-90 */
+  note = 0;
+  if (verbose_level >= 2) fprintf(stderr, "Medians of different classes are compared\n");
+  for (c = 0; c < nol; c++) {                                          /* balance.c:95-104 */
+    if ((aver > BAL * dists[c]) && (classes.freq[c] > 1)) { diff[c]--; note++; }
+    if (BAL * aver < dists[c]) { diff[c]++; note--; }
+  }
+  for (c = 0; c < nol; c++) {                                          /* balance.c:121-134 */
+    if ((aver > BAL * dists[c]) && ((classes.freq[c] + diff[c]) > 1))
+      if (note < 0) { diff[c]--; note++; }
+    if (BAL * aver < dists[c])
+      if (note > 0) { diff[c]++; note--; }
+  }
+
+  /* new vectors: diff[c] more for the classes with diff > 0, picked in data order */
+  hit_init(&more);
+  total = 0;
+  for (c = 0; c < nol; c++)
+    for (t = 0; t < diff[c]; t++) { hit_add(&more, classes.label[c]); total++; }
+  inside = (unsigned char *)calloc((size_t)(data->n > 0 ? data->n : 1), 1);
+  picked = (long *)malloc(sizeof(long) * (size_t)(data->n > 0 ? data->n : 1));
+  data_label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(data->n > 0 ? data->n : 1));
+  if (!inside || !picked || !data_label) return 1;
+  for (i = 0; i < data->n; i++) data_label[i] = pak_label(data, i);
+  if (verbose_level >= 1) fprintf(stderr, "Some codebook vectors are removed\n");
+  if (verbose_level >= 1) fprintf(stderr, "Some new codebook vectors are picked\n");
+  if (total > 0) {
+    if (find_winners(data, data, knn, &w)) return 1;
+    hit_init(&hits);
+    for (i = 0; i < data->n; i++) {
+      if (w.nfound[i] != knn) { inside[i] = 1; continue; }            /* lvq_rout.c:173 */
+      hit_clear(&hits);
+      for (t = 0; t < knn; t++) hit_add(&hits, pak_label(data, w.idx[i * knn + t]));
+      inside[i] = hits.n > 0 && hits.label[0] == data_label[i];
+    }
+    pick_inside(data, inside, &more, picked, &npicked);
+    hit_free(&hits);
+    winners_free(&w);
+  }
+
+  /* the balanced codebook: survivors in list order (the first -diff entries of a class go,
+   * balance.c:141-163), then the picked data entries */
+  out = pak_alloc(codes->dim, codes->n + npicked);
+  out_label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(codes->n + npicked + 1));
+  unit_alpha = (float *)malloc(sizeof(float) * (size_t)(codes->n + npicked + 1));
+  if (!out || !out_label || !unit_alpha) return 1;
+  out->topol = codes->topol; out->neigh = codes->neigh; out->xdim = codes->xdim; out->ydim = codes->ydim;
+  if (codes->mask || data->mask) out->mask = (unsigned char *)calloc((size_t)(codes->n + npicked + 1) * codes->dim, 1);
+  out->lab_pool = (int *)malloc(sizeof(int) * (size_t)(codes->lab_off[codes->n] + data->lab_off[data->n] + 1));
+  if (!out->lab_pool || ((codes->mask || data->mask) && !out->mask)) return 1;
+  for (i = 0; i < codes->n; i++) {
+    long l;
+    for (c = 0; c < nol; c++)
+      if (classes.label[c] == label[i]) break;
+    if (c < nol && diff[c] < 0) { diff[c]++; continue; }
+    memcpy(out->points + (size_t)kept * codes->dim, codes->points + (size_t)i * codes->dim, sizeof(float) * codes->dim);
+    if (codes->mask) memcpy(out->mask + (size_t)kept * codes->dim, codes->mask + (size_t)i * codes->dim, (size_t)codes->dim);
+    for (l = codes->lab_off[i]; l < codes->lab_off[i + 1]; l++) out->lab_pool[nl++] = codes->lab_pool[l];
+    out_label[kept] = label[i];
+    unit_alpha[kept] = 0.3f;
+    kept++;
+    out->lab_off[kept] = nl;
+  }
+  counted = kept;                                                      /* what the reference's num_entries says */
+  for (i = 0; i < npicked; i++) {
+    const long j = picked[i];
+    long l;
+    memcpy(out->points + (size_t)kept * codes->dim, data->points + (size_t)j * codes->dim, sizeof(float) * codes->dim);
+    if (data->mask) memcpy(out->mask + (size_t)kept * codes->dim, data->mask + (size_t)j * codes->dim, (size_t)codes->dim);
+    for (l = data->lab_off[j]; l < data->lab_off[j + 1]; l++) out->lab_pool[nl++] = data->lab_pool[l];
+    out_label[kept] = data_label[j];
+    unit_alpha[kept] = 0.0f;                                           /* read from beyond the rate array: see above */
+    kept++;
+    out->lab_off[kept] = nl;
+  }
+  out->n = kept;
+
+  if (verbose_level >= 1) fprintf(stderr, "Codebook vectors are redistributed\n");
+  if (data->n > 0 && out->n > 0) {                                     /* balance.c:196-202: one pass of OLVQ1 */
+    sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)data->n);
+    if (!sample) return 1;
+    bmu_lvq_schedule(0, data->n, data->n, 0.3f, BMU_ALPHA_LINEAR, data->n, NULL, sample, dists + codes->n);
+    if (bmu_lvq_train(BMU_OLVQ1, out->points, out_label, out->n, out->dim, data->points, data->mask, data_label,
+                      data->n, sample, NULL, data->n, 0.0f, 0.0f, 0.3f, unit_alpha))
+      return engine_failed("bmu_lvq_train");
+    free(sample);
+  }
+  lra_name(cout_name, lra, sizeof lra);                                /* alpha_write, datafile.c:1061-1086 */
+  {
+    FILE *fp = fopen(lra, "w+");
+    if (!fp) fprintf(stderr, "Can't open alpha file %s for writing", lra);
+    else {
+      for (i = 0; i < counted; i++) fprintf(fp, "%g\n", unit_alpha[i]);
+      fclose(fp);
+    }
+  }
+  if (verbose_level >= 2) fprintf(stderr, "Medians of the shortest distances are computed\n");
+  if (class_medians(out, out_label, &classes, dists)) return 1;
+  if (verbose_level > 0)
+    for (c = 0; c < classes.n; c++)
+      fprintf(stdout, "In class %9s %3d units, min dist.: %.3f\n", label_string((int)classes.label[c]),
+              (int)classes.freq[c], dists[c]);
+  if (verbose_level >= 2) fprintf(stderr, "Codebook entries are saved to file %s\n", cout_name);
+  if (pak_save(out, cout_name)) return 1;
+  free(label); free(dists); free(diff); free(inside); free(picked); free(data_label); free(out_label); free(unit_alpha);
+  hit_free(&classes); hit_free(&more);
+  pak_free(data); pak_free(codes); pak_free(out);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ sammon */
 /* sammon.c:420-490: remove_identicals (83-127) + sammon_iterate (129-262) + save_entries.  The
  * O(M^2 D) distance loops and the O(M^2) sweeps run on the device (bmu_identical_pairs, bmu_sammon);

@@ -82,6 +82,7 @@ int randinit_main(int argc, char **argv, const char *progname);
 int eveninit_main(int argc, char **argv, const char *progname);
 int mindist_main(int argc, char **argv);
 int sammon_main(int argc, char **argv);
+int balance_main(int argc, char **argv);
 int pakcat_main(int argc, char **argv);   /* load + save: exercises the file layer alone */
 int pakstat_main(int argc, char **argv);  /* load only, prints counts and the load time */
 

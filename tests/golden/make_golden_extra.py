@@ -52,6 +52,14 @@ def main():
     out["propinit_cod"] = np.array(open(os.path.join(td, "p.cod")).read())
     run([b("eveninit"), "-din", "ex2.dat", "-cout", "e2.cod", "-noc", "317"], td)
     out["eveninit2_cod"] = np.array(open(os.path.join(td, "e2.cod")).read())
+    # balance (config 2 of BASELINE.json): the demo step, and a second codebook / neighbour count
+    open(os.path.join(td, "ex1e.cod"), "w").write(str(demo["lvq_e_cod"]))
+    out["balance_stdout"] = np.array(run([b("balance"), "-din", "ex1.dat", "-cin", "ex1e.cod", "-cout", "bal.cod"], td))
+    assert open(os.path.join(td, "bal.cod")).read() == str(demo["lvq_b_cod"])
+    out["balance_lra"] = np.array(open(os.path.join(td, "bal.lra")).read())
+    out["balance2_stdout"] = np.array(run([b("balance"), "-din", "ex2.dat", "-cin", "e2.cod", "-cout", "bal2.cod", "-knn", "3"], td))
+    out["balance2_cod"] = np.array(open(os.path.join(td, "bal2.cod")).read())
+    out["balance2_lra"] = np.array(open(os.path.join(td, "bal2.lra")).read())
     # snapshots (som_rout.c:650-658, lvq_pak.c:663-764): one file per snapshot, and -snaptype keepopen
     open(os.path.join(td, "ex.dat"), "w").write(str(demo["in_ex.dat"]))
     open(os.path.join(td, "ex.cod"), "w").write(str(demo["som_init_cod"]))
