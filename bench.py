@@ -83,11 +83,29 @@ def synth_rows_torch(seed, row0, rows, D, device):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (the timed
+    region of the search is tens of milliseconds, shorter than one nvidia-smi call); nvidia-smi -lms as
+    the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu):
+        self.sm, self.mx, self.mask, self.p, self.thread = [], None, 0, None, None
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
@@ -96,8 +114,31 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _poll(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if reasons:
+                    self.mask |= int(reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out["sm_mhz"] = float(np.median(self.sm))
+                out["sm_max_mhz"] = self.mx
+                out["samples"] = len(self.sm)
+                out["source"] = "nvml"
+            out["reasons"] = sorted(n for n, b in self.BITS.items() if self.mask & b)
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -126,6 +167,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(mx))
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi"
         out["reasons"] = sorted(reasons)
         return out
 
