@@ -2,7 +2,7 @@
 units with k = 5, C5 256x256x128 map) checked through size-independent properties, plus direct
 oracle comparison on samples the CPU finishes in seconds:
   * every row gets a winner, the BMU histogram sums to N;
-  * the tensor-core filter path (K2) and the exact FP32 path (K1) agree bit for bit on a sample;
+  * the tensor-core filter path (K2) and the exact FP32 path (K1) agree bit for bit on every row (C3) / a sample;
   * a sample agrees bit for bit with the oracle;
   * searching the codebook against itself returns the identity with distance 0;
   * k-NN lists are sorted by the reference's rule and hold distinct codes;
@@ -43,12 +43,16 @@ def test_c3_full_size(engine, oracle):
     assert bool((nf == 1).all())
     hist = torch.bincount(idx[:, 0].long(), minlength=M)
     assert int(hist.sum()) == N and int(idx.min()) >= 0 and int(idx.max()) < M
-    # exact FP32 path on a random sample of rows: identical winners and distances
+    # the exact FP32 path (K1) on ALL 10 M rows: identical winners and distance bits, row for row
+    eidx, ediff, _ = dev_search(engine, cb, data, 1, 1)
+    assert bool((eidx == idx).all()) and bool((ediff.view(torch.int32) == diff.view(torch.int32)).all())
+    del eidx, ediff
+    # a second run of the filter path gives the same bits (no order dependence in the fused kernel)
+    idx2, diff2, _ = dev_search(engine, cb, data, 1, 2)
+    assert bool((idx2 == idx).all()) and bool((diff2.view(torch.int32) == diff.view(torch.int32)).all())
+    del idx2, diff2
     g = torch.Generator(device="cpu").manual_seed(5)
     rows = torch.randperm(N, generator=g)[:200_000].to(dev)
-    sub = data[rows].contiguous()
-    eidx, ediff, _ = dev_search(engine, cb, sub, 1, 1)
-    assert bool((eidx == idx[rows]).all()) and bool((ediff.view(torch.int32) == diff[rows].view(torch.int32)).all())
     # oracle on a smaller sample
     h = rows[:1500]
     o = oracle.search(codes.cpu().numpy(), data[h].cpu().numpy(), 1)
@@ -74,7 +78,7 @@ def test_c4_full_size_knn(engine, oracle):
     d0, d1 = diff[:, :-1], diff[:, 1:]
     i0, i1 = idx[:, :-1], idx[:, 1:]
     assert bool(((d0 < d1) | ((d0 == d1) & (i0 > i1))).all())
-    rows = torch.arange(0, N, 337, device=dev)[:3000]
+    rows = torch.arange(0, N, 10, device=dev)                               # 100 000 rows through the exact k-NN kernel
     sub = data[rows].contiguous()
     eidx, ediff, _ = dev_search(engine, cb, sub, k, 1)                       # exact path
     assert bool((eidx == idx[rows]).all()) and bool((ediff.view(torch.int32) == diff[rows].view(torch.int32)).all())
@@ -84,6 +88,9 @@ def test_c4_full_size_knn(engine, oracle):
     # k = 1 (accuracy / classify): first neighbour of the k-NN list unless a tie changes the rule
     idx1, diff1, _ = dev_search(engine, cb, data, 1, 0)
     assert bool((diff1[:, 0] == diff[:, 0]).all())
+    # ... and equal, on every one of the 1 M rows, to the exact FP32 kernel's winner and distance bits
+    eidx1, ediff1, _ = dev_search(engine, cb, data, 1, 1)
+    assert bool((eidx1 == idx1).all()) and bool((ediff1.view(torch.int32) == diff1.view(torch.int32)).all())
     cb.close()
 
 
