@@ -134,3 +134,36 @@ def test_vfind_python_orchestration(engine, golden):
     assert n == 4
     assert "%f" % (q / np.float32(data.points.shape[0])) == "9.632525"
     assert [["%g" % v for v in row] for row in codes] == [["%g" % v for v in row] for row in ref.points]
+
+
+@pytest.mark.parametrize("xdim,ydim,D,neigh", [(30, 20, 700, 1), (12, 9, 2100, 2), (300, 300, 8, 1), (64, 48, 130, 2),
+                                               (3, 2, 1, 1), (1, 1, 5, 2)])
+def test_som_extreme_shapes(engine, oracle, xdim, ydim, D, neigh):
+    """codebooks far from the benchmark shapes: very long vectors (the unit does not fit one register /
+    shared-memory slice), 90 000 units, and degenerate 1-component / 1-unit maps"""
+    rng = np.random.default_rng(xdim * 31 + D)
+    M, N = xdim * ydim, 300
+    rlen = 120 if M * D > 2_000_000 else 250
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    out = engine.som_training(codes, data, xdim, ydim, 3, neigh, rlen, 0.05, 5.0, 1, rand_seed=4)
+    exp = oracle.som_train(codes, data, xdim, ydim, 3, neigh, rlen, 0.05, 5.0, 1, order=oracle.shuffle_order(N, 4))
+    close_or_equal(out, exp, neigh, "som %dx%d D=%d n%d" % (xdim, ydim, D, neigh))
+
+
+@pytest.mark.parametrize("M,D", [(3000, 600), (20, 2500), (30000, 12), (1, 4), (2, 1)])
+def test_lvq_extreme_shapes(engine, oracle, M, D):
+    rng = np.random.default_rng(M + D)
+    N, L = 400, 5
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    cl = rng.integers(1, L + 1, M).astype(np.int32)
+    dl = rng.integers(1, L + 1, N).astype(np.int32)
+    for algo in ((1, 4) if M < 2 else (1, 2, 3, 4)):                # lvq2 / lvq3 need two neighbours
+        alpha = 0.3 if algo == 4 else 0.05
+        out = engine.lvq_training(algo, codes, cl, data, dl, 500, alpha, 1, 0.3, 0.1, rand_seed=2)
+        exp, eua = oracle.lvq_train(algo, codes, cl, data, dl, 500, alpha, 1, 0.3, 0.1, order=oracle.shuffle_order(N, 2))
+        if algo == 4:
+            out, ua = out
+            assert_bits_equal(ua, eua, "unit alpha")
+        assert_bits_equal(out, exp, "lvq algo %d M=%d D=%d" % (algo, M, D))
