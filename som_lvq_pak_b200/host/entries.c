@@ -313,8 +313,34 @@ static char *slurp(FILE *fp, size_t *len) {
   return buf;
 }
 
+/* open_file (fileio.c:60-190): "-" is stdin / stdout, a name ending in .gz / .z / .Z goes through gzip
+ * ("gzip -d -c %s" / "gzip -9 -c >%s", fileio.h:33-38), a name starting with '|' is a command. */
+static FILE *pak_open(const char *name, int writing, int *piped) {
+  char cmd[4200];
+  const char *dot;
+  *piped = 0;
+  if (strcmp(name, "-") == 0) return writing ? stdout : stdin;
+  if (name[0] == '|') {
+    *piped = 1;
+    return popen(name + 1, writing ? "w" : "r");
+  }
+  dot = strrchr(name, '.');
+  if (dot && (strcmp(dot, ".gz") == 0 || strcmp(dot, ".z") == 0 || strcmp(dot, ".Z") == 0)) {
+    if (strlen(name) > 4000) return NULL;
+    sprintf(cmd, writing ? "gzip -9 -c >%s" : "gzip -d -c %s", name);
+    *piped = 1;
+    return popen(cmd, writing ? "w" : "r");
+  }
+  return fopen(name, writing ? "w" : "r");
+}
+static void pak_close(FILE *fp, int piped) {
+  if (fp == stdin || fp == stdout) return;
+  if (piped) pclose(fp); else fclose(fp);
+}
+
 struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
-  FILE *fp = strcmp(name, "-") == 0 ? stdin : fopen(name, "r");
+  int piped = 0;
+  FILE *fp = pak_open(name, 0, &piped);
   char *buf, *p, *endbuf, tokbuf[64];
   size_t len = 0;
   long header_lines = 0, total = 0, totlab = 0, i;
@@ -325,7 +351,7 @@ struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty
   const char *env = getenv("BMU_PAK_THREADS");
   if (!fp) return NULL;
   buf = slurp(fp, &len);
-  if (fp != stdin) fclose(fp);
+  pak_close(fp, piped);
   if (!buf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
   endbuf = buf + len;
   /* header: first line that is not a comment (datafile.c:112-148) */
@@ -450,7 +476,8 @@ void pak_write_header(FILE *fp, const struct pak_entries *e) {     /* datafile.c
 }
 
 int pak_save(const struct pak_entries *e, const char *name) {
-  FILE *fp = strcmp(name, "-") == 0 ? stdout : fopen(name, "w");
+  int piped = 0;
+  FILE *fp = pak_open(name, 1, &piped);
   long i, l;
   int c;
   if (!fp) { fprintf(stderr, "save_entries: Can't open file '%s'\n", name); return 1; }
@@ -465,7 +492,7 @@ int pak_save(const struct pak_entries *e, const char *name) {
     for (l = e->lab_off[i]; l < e->lab_off[i + 1]; l++) fprintf(fp, "%s ", label_string(e->lab_pool[l]));
     fprintf(fp, "\n");
   }
-  if (fp != stdout) fclose(fp);
+  pak_close(fp, piped);
   return 0;
 }
 

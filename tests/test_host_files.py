@@ -155,3 +155,18 @@ def test_randinit_program(tmp_path, demo):
                     "-topol", "rect", "-neigh", "gaussian", "-rand", "7"], check=True, cwd=tmp_path)
     assert (tmp_path / "g.cod").read_text() == str(demo["som_g_init_cod"])
 
+
+
+def test_compressed_and_piped_names(tmp_path, demo):
+    """open_file (fileio.c:60-190): names ending in .gz go through gzip, names starting with '|' are commands"""
+    import shutil
+    if not shutil.which("gzip"):
+        pytest.skip("no gzip here")
+    text = str(demo["in_ex_fts.dat"])
+    (tmp_path / "a.dat").write_text(text)
+    subprocess.run([PAK, "pakcat", "-din", "a.dat", "-dout", "plain.dat"], check=True, cwd=tmp_path)
+    subprocess.run([PAK, "pakcat", "-din", "a.dat", "-dout", "b.dat.gz"], check=True, cwd=tmp_path)
+    subprocess.run([PAK, "pakcat", "-din", "b.dat.gz", "-dout", "c.dat"], check=True, cwd=tmp_path)
+    assert (tmp_path / "c.dat").read_text() == (tmp_path / "plain.dat").read_text()
+    subprocess.run([PAK, "pakcat", "-din", "|cat a.dat", "-dout", "|cat > d.dat"], check=True, cwd=tmp_path)
+    assert (tmp_path / "d.dat").read_text() == (tmp_path / "plain.dat").read_text()
