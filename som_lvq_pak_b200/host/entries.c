@@ -30,6 +30,12 @@ int label_index(const char *str) {
   return ++g_nlabels;
 }
 
+void label_reset(void) {                   /* a fresh table per program of `bmu_pak batch` */
+  int i;
+  for (i = 0; i < g_nlabels; i++) free(g_labels[i]);
+  g_nlabels = 0;
+}
+
 const char *label_string(int ind) {
   if (ind <= 0 || ind > g_nlabels) return NULL;
   return g_labels[ind - 1];

@@ -2,6 +2,7 @@
  * link named after the program (vsom, qerror, visual, vcal, accuracy, classify, knntest, cmatr,
  * setlabel, elimin, lvq1, olvq1, lvq2, lvq3), as the reference installs one binary per program (reference Makefile). */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "somhost.h"
@@ -31,14 +32,54 @@ static int dispatch(const char *prog, int argc, char **argv) {
   return -2;
 }
 
+/* `bmu_pak batch [file]`: one program per line ("vsom -din ex.dat ..."; '#' starts a comment; "..." or
+ * '...' keep blanks in a word), run one after the other in THIS process.  Creating the CUDA context costs
+ * about a second, far more than a demo-size program needs; a recipe of several programs pays it once.
+ * Every line starts from a fresh label table; the first failing program ends the batch with its code. */
+static int batch_main(int argc, char **argv) {
+  FILE *fp = argc > 1 && strcmp(argv[1], "-") != 0 ? fopen(argv[1], "r") : stdin;
+  char line[8192];
+  int rc = 0;
+  if (!fp) { fprintf(stderr, "batch: can't open %s\n", argv[1]); return 1; }
+  while (rc == 0 && fgets(line, sizeof line, fp)) {
+    char *words[512], *p = line;
+    int n = 0;
+    while (*p && n < 511) {
+      while (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n') p++;
+      if (!*p || *p == '#') break;
+      if (*p == '"' || *p == '\'') {
+        const char q = *p++;
+        words[n++] = p;
+        while (*p && *p != q) p++;
+      } else {
+        words[n++] = p;
+        while (*p && *p != ' ' && *p != '\t' && *p != '\r' && *p != '\n') p++;
+      }
+      if (*p) *p++ = '\0';
+    }
+    if (n == 0) continue;
+    words[n] = NULL;
+    label_reset();
+    rc = dispatch(words[0], n, words);
+    fflush(stdout);
+    if (rc == -2) { fprintf(stderr, "batch: unknown program '%s'\n", words[0]); rc = 2; }
+  }
+  if (fp != stdin) fclose(fp);
+  return rc;
+}
+
 int main(int argc, char **argv) {
   const char *base = strrchr(argv[0], '/');
   int rc;
   base = base ? base + 1 : argv[0];
   rc = dispatch(base, argc, argv);
-  if (rc == -2 && argc > 1) rc = dispatch(argv[1], argc - 1, argv + 1);
+  if (rc == -2 && argc > 1) {
+    if (strcmp(argv[1], "batch") == 0) return batch_main(argc - 1, argv + 1);
+    rc = dispatch(argv[1], argc - 1, argv + 1);
+  }
   if (rc == -2) {
-    fprintf(stderr, "usage: bmu_pak <randinit|eveninit|propinit|balance|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n");
+    fprintf(stderr, "usage: bmu_pak <randinit|eveninit|propinit|balance|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n"
+                    "       bmu_pak batch [file]     one program per line, run in one process\n");
     return 2;
   }
   return rc;

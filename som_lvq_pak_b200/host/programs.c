@@ -51,6 +51,7 @@ static int flag(int argc, char **argv, const char *name) {              /* OPTIO
 static int verbose_level = 1;
 static void global_options(int argc, char **argv) {                     /* lvq_pak.c:618-661 */
   const char *s = getenv("LVQSOM_MASK_STR");
+  pak_mask_string = "x";                                             /* `bmu_pak batch` runs several programs */
   if (s) pak_mask_string = s;
   s = opt(argc, argv, "-mask_str");
   if (s) pak_mask_string = s;

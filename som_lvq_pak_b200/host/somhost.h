@@ -27,6 +27,7 @@
 /* ---- label table (reference labels.c:36-128): index 0 is the empty label ---------- */
 int label_index(const char *str);        /* adds the label when it is new */
 const char *label_string(int ind);       /* NULL for LABEL_EMPTY / unknown */
+void label_reset(void);                   /* forget every label (between programs of one process) */
 
 /* ---- entries: one .dat / .cod file in flat arrays ------------------------------------- */
 struct pak_entries {

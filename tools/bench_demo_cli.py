@@ -58,6 +58,12 @@ def main():
             steps = run_chain(chain, ours, td)
             res["%s_%s" % (name, "bmu_pak_b200" if ours else "reference_cpu")] = {
                 "total_s": round(sum(t for _, t in steps), 3), "steps": steps}
+            if ours:                                            # the same recipe as ONE process
+                recipe = "".join("%s %s\n" % (p, a) for p, a in chain)
+                t0 = time.perf_counter()
+                subprocess.run([PAK, "batch"], input=recipe.encode(), cwd=td, stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, check=True)
+                res["%s_bmu_pak_b200_batch" % name] = {"total_s": round(time.perf_counter() - t0, 3)}
     print(json.dumps(res))
 
 
