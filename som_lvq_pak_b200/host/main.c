@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "somhost.h"
 
@@ -60,7 +61,15 @@ static int batch_main(int argc, char **argv) {
     if (n == 0) continue;
     words[n] = NULL;
     label_reset();
-    rc = dispatch(words[0], n, words);
+    {
+      struct timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      rc = dispatch(words[0], n, words);
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if (getenv("BMU_PAK_BATCH_TIMING"))
+        fprintf(stderr, "[batch] %-10s %.3f s\n", words[0],
+                (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+    }
     fflush(stdout);
     if (rc == -2) { fprintf(stderr, "batch: unknown program '%s'\n", words[0]); rc = 2; }
   }
