@@ -903,6 +903,12 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 #pragma unroll 1
         for (int c0 = 0; c0 < K2R_TNH; c0 += 32) {
           tmem_ld_wait32(v);
+          if (c0 + 32 >= K2R_TNH) {
+            // the last 32 columns are in registers: the accumulator can be refilled while they are processed
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[g]);
+          }
           // minima of the eight 4-column groups (FMNMX3 + FMNMX), then of the chunk: 20 ALU ops
           float gm[8];
 #pragma unroll
@@ -936,9 +942,6 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
             r.lost = (ins && s2 < r.thr) ? fminf(r.lost, s2) : r.lost;
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[g]);
       }
       {
         // hand the row over to the re-rank warps (the buffer of two passes ago must have been drained)
