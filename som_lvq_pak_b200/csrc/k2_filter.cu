@@ -49,7 +49,11 @@ constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to th
 constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel = epilogue groups = accumulators
 constexpr int K2R_BST = 2;        // staged code tiles (3 measured no faster; 2 leave 60 KB of the SM's shared memory
                                   // to the prep / re-rank blocks that run beside the GEMM CTA)
-constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM)
+constexpr int K2R_TNH = 128;      // accumulator width: half a code tile (4 x 128 columns fill TMEM).  Measured and rejected:
+                                  // two 64-column accumulators per row tile (the MMAs fill one while the epilogue drains
+                                  // the other): 13.5 instead of 11.7 ms, a 128 x 64 x 16 MMA takes about as long as a
+                                  // 128 x 128 x 16 one; and an issuer in which one elected lane also does the barrier
+                                  // waits while the other lanes park: 12.3 instead of 12.0 ms on the same box.
 constexpr int K2R_THREADS = 704;  // warps 0-15 epilogue (group g = warp / 4 owns row tile g), warp 16 producer, warp 17 MMA,
                                   // warps 18-21 exact re-rank of the pass the epilogue finished before
 constexpr int K2R_GW = 4;         // candidate granularity: groups of 4 consecutive codes
