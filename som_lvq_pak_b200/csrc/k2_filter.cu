@@ -651,7 +651,7 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 // smallest group minima seen so far with the first code of their group, and `lost` = lower
 // bound of every group minimum that was looked at but is not (or no longer) one of the two
 struct K2RRow {
-  float best, thr, lost, k0, k1;
+  float thr, lost, k0, k1;      // thr = k0 + delta (rounded up): k0 is also the running minimum
   int i0, i1;
 };
 
@@ -898,7 +898,7 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
     for (long st = blockIdx.x; st < nsuper; st += gridDim.x, cnt++) {
       const long n = (st * R + g) * K2_TM + row;
       const float delta = n < N ? rs[n].delta : 0.0f;
-      K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
+      K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
       for (int q = 0; q < nacc; q++, use++) {               // q = 2 * code tile + half
         mbar_wait(&tfull[g], use & 1);
         tc_fence_after();
@@ -938,15 +938,14 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
             const int qs = (inA ? 0 : (inB ? 3 : 6)) + (e0 ? 0 : (e1 ? 1 : 2));
             const float s2 = fminf(fminf(fminf(inA ? b3 : a3, (inA || inB) ? c2 : b3), e0 ? t1 : t0), (e0 || e1) ? t2 : t1);
             const int gi = q * K2R_TNH + c0 + K2R_GW * qs;     // first code of that group
-            const bool first = ins && m < r.k0, second = ins && !first && m < r.k1;
+            const bool first = m < r.k0, second = ins && !first && m < r.k1;     // m < k0 <= thr implies ins
             // the minimum that leaves the pair (or m itself when it does not enter) bounds what is dropped
             r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? m : INFINITY));
             r.k1 = first ? r.k0 : (second ? m : r.k1);
             r.i1 = first ? r.i0 : (second ? gi : r.i1);
             r.k0 = first ? m : r.k0;
             r.i0 = first ? gi : r.i0;
-            r.best = ins ? fminf(r.best, m) : r.best;
-            r.thr = ins ? __fadd_ru(r.best, delta) : r.thr;
+            r.thr = first ? __fadd_ru(m, delta) : r.thr;           // a new running minimum tightens the threshold
             // only one group of this chunk is recorded; the others are >= s2
             r.lost = (ins && s2 < r.thr) ? fminf(r.lost, s2) : r.lost;
           }
