@@ -907,20 +907,22 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
 #pragma unroll 1
         for (int c0 = 0; c0 < K2R_TNH; c0 += 32) {
           tmem_ld_wait32(v);
-          if (c0 + 32 >= K2R_TNH) {
-            // the last 32 columns are in registers: the accumulator can be refilled while they are processed
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[g]);
-          }
           // minima of the eight 4-column groups (FMNMX3 + FMNMX), then of the chunk: 20 ALU ops
           float gm[8];
 #pragma unroll
           for (int t = 0; t < 8; t++)
             gm[t] = fminf(fminf(fminf(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), __uint_as_float(v[4 * t + 2])),
                           __uint_as_float(v[4 * t + 3]));
-          // the scores are dead now: the next chunk streams into the same registers
-          if (c0 + 32 < K2R_TNH) tmem_ld32_nowait(tbase + c0 + 32, v);
+          if (c0 + 32 < K2R_TNH) {
+            // the scores are dead now: the next chunk streams into the same registers
+            tmem_ld32_nowait(tbase + c0 + 32, v);
+          } else {
+            // the last 32 columns have been consumed: the accumulator can be refilled while the rest of this
+            // chunk is processed
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[g]);
+          }
           const float a3 = fminf(fminf(gm[0], gm[1]), gm[2]), b3 = fminf(fminf(gm[3], gm[4]), gm[5]), c2 = fminf(gm[6], gm[7]);
           const float m = fminf(fminf(a3, b3), c2);
           const bool ins = m < r.thr;
