@@ -414,9 +414,9 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                : "memory");
 }
 struct K2Smem {
-  static size_t bytes(int Kp, bool a_res) {
+  static size_t bytes(int Kp, bool a_res, int nst) {
     size_t stage = (size_t)K2_TN * K2_KS * 2 + (a_res ? 0 : (size_t)K2_TM * K2_KS * 2);
-    return (a_res ? (size_t)K2_TM * Kp * 2 : 0) + K2_NSTAGE * stage + 256;
+    return (a_res ? (size_t)K2_TM * Kp * 2 : 0) + nst * stage + 256;
   }
 };
 
@@ -448,7 +448,7 @@ __device__ __forceinline__ uint32_t k2_idesc() {
 template <int TG, int TT>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
-               const RowStats *__restrict__ rs, long N, long M, int Kp, int a_res, int k,
+               const RowStats *__restrict__ rs, long N, long M, int Kp, int a_res, int nst, int k,
                int32_t *__restrict__ cand, float *__restrict__ thr) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const size_t a_res_bytes = a_res ? (size_t)K2_TM * Kp * 2 : 0;
@@ -457,7 +457,7 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
   const size_t stage_bytes = b_stage_bytes + a_stage_bytes;
   unsigned char *sAres = smem;
   unsigned char *sStage = smem + a_res_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + K2_NSTAGE * stage_bytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + nst * stage_bytes);   // nst <= K2_NSTAGE slab stages
   uint64_t *full = bars, *empty = bars + K2_NSTAGE;
   uint64_t *tfull = bars + 2 * K2_NSTAGE, *tempty = tfull + 2;
   uint64_t *afull = tempty + 2, *aempty = afull + 1;
@@ -498,9 +498,9 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         for (int ct = 0; ct < nct; ct++) {
           const unsigned char *gB = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)ct * K2_TN * Kp * 2;
           for (int sl = 0; sl < nslab; sl++, seq++) {
-            const int st = seq % K2_NSTAGE;
+            const int st = seq % nst;
             const int kc = min(K2_KS, Kp - sl * K2_KS);               // K elements in this slab
-            mbar_wait(&empty[st], ((seq / K2_NSTAGE) & 1) ^ 1);
+            mbar_wait(&empty[st], ((seq / nst) & 1) ^ 1);
             const uint32_t bB = (uint32_t)K2_TN * kc * 2, bA = a_res ? 0u : (uint32_t)K2_TM * kc * 2;
             mbar_arrive_expect_tx(&full[st], bB + bA);
             unsigned char *dst = sStage + (size_t)st * stage_bytes;
@@ -523,9 +523,9 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * K2_TN;
           for (int sl = 0; sl < nslab; sl++, seq++) {
-            const int st = seq % K2_NSTAGE;
+            const int st = seq % nst;
             const int kc = min(K2_KS, Kp - sl * K2_KS);
-            mbar_wait(&full[st], (seq / K2_NSTAGE) & 1);
+            mbar_wait(&full[st], (seq / nst) & 1);
             tc_fence_after();
             const uint32_t bBase = smem_u32(sStage + (size_t)st * stage_bytes);
             const uint32_t aBase = a_res ? smem_u32(sAres) + (uint32_t)sl * K2_KS * K2_TM * 2
@@ -576,6 +576,21 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
               b[0] = fminf(b[0], lo);
               b[1] = fminf(fminf(b[1], hi), t);
             }
+          } else if constexpr (TT == 4) {
+            // pairs merged into the sorted four by rank selection (the k-th smallest of two sorted lists is
+            // min over i of max(b[i-1], p[k-i])): 2 LOP3 + 2 (sort the pair) + 1 + 2 + 3 + 3 = 6.5 ALU ops per
+            // score instead of the 9 of two insertions, which made the k = 5 epilogue slower than its MMAs
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float k0 = __uint_as_float((v[c] & 0xFFFFFF00u) | (uint32_t)(c0 + c));
+              const float k1 = __uint_as_float((v[c + 1] & 0xFFFFFF00u) | (uint32_t)(c0 + c + 1));
+              const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+              const float r0 = fminf(b[0], lo);
+              const float r1 = fminf(fminf(hi, fmaxf(b[0], lo)), b[1]);
+              const float r2 = fminf(fminf(fmaxf(b[0], hi), fmaxf(b[1], lo)), b[2]);
+              const float r3 = fminf(fminf(fmaxf(b[1], hi), fmaxf(b[2], lo)), b[3]);
+              b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
+            }
           } else {
 #pragma unroll
             for (int c = 0; c < 32; c++) {
@@ -590,24 +605,59 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
             }
           }
         };
-        tmem_ld32_nowait(tbase, va);
+        // TT == 4: a second, independent chain of four (the upper 32 columns of every 64): one warp per
+        // SM partition runs this epilogue, and a single chain of dependent min/max leaves its issue slots idle
+        float b2[TT];
+#pragma unroll
+        for (int t = 0; t < TT; t++) b2[t] = INFINITY;
+        if constexpr (TT == 4) {
+          tmem_ld32_nowait(tbase, va);
+          tmem_ld32_nowait(tbase + 32, vb);
 #pragma unroll 1
-        for (int c0 = 0; c0 < K2_TN; c0 += 64) {
-          tmem_ld_wait32(va);
-          tmem_ld32_nowait(tbase + c0 + 32, vb);
-          fold(va, c0);
-          tmem_ld_wait32(vb);
-          if (c0 + 64 < K2_TN) tmem_ld32_nowait(tbase + c0 + 64, va);
-          fold(vb, c0 + 32);
+          for (int c0 = 0; c0 < K2_TN; c0 += 64) {
+            tmem_ld_wait32(va);
+            tmem_ld_wait32(vb);
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float k0 = __uint_as_float((va[c] & 0xFFFFFF00u) | (uint32_t)(c0 + c));
+              const float k1 = __uint_as_float((va[c + 1] & 0xFFFFFF00u) | (uint32_t)(c0 + c + 1));
+              const float q0 = __uint_as_float((vb[c] & 0xFFFFFF00u) | (uint32_t)(c0 + 32 + c));
+              const float q1 = __uint_as_float((vb[c + 1] & 0xFFFFFF00u) | (uint32_t)(c0 + 32 + c + 1));
+              const float lo = fminf(k0, k1), hi = fmaxf(k0, k1), lo2 = fminf(q0, q1), hi2 = fmaxf(q0, q1);
+              const float r0 = fminf(b[0], lo), s0 = fminf(b2[0], lo2);
+              const float r1 = fminf(fminf(hi, fmaxf(b[0], lo)), b[1]), s1 = fminf(fminf(hi2, fmaxf(b2[0], lo2)), b2[1]);
+              const float r2 = fminf(fminf(fmaxf(b[0], hi), fmaxf(b[1], lo)), b[2]);
+              const float s2 = fminf(fminf(fmaxf(b2[0], hi2), fmaxf(b2[1], lo2)), b2[2]);
+              const float r3 = fminf(fminf(fmaxf(b[1], hi), fmaxf(b[2], lo)), b[3]);
+              const float s3 = fminf(fminf(fmaxf(b2[1], hi2), fmaxf(b2[2], lo2)), b2[3]);
+              b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
+              b2[0] = s0; b2[1] = s1; b2[2] = s2; b2[3] = s3;
+            }
+            if (c0 + 64 < K2_TN) {
+              tmem_ld32_nowait(tbase + c0 + 64, va);
+              tmem_ld32_nowait(tbase + c0 + 96, vb);
+            }
+          }
+        } else {
+          tmem_ld32_nowait(tbase, va);
+#pragma unroll 1
+          for (int c0 = 0; c0 < K2_TN; c0 += 64) {
+            tmem_ld_wait32(va);
+            tmem_ld32_nowait(tbase + c0 + 32, vb);
+            fold(va, c0);
+            tmem_ld_wait32(vb);
+            if (c0 + 64 < K2_TN) tmem_ld32_nowait(tbase + c0 + 64, va);
+            fold(vb, c0 + 32);
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
-        // everything of this tile that is not kept is >= the tile's TT-th smallest key
-        tmin = fminf(tmin, b[TT - 1]);
+        // everything of this tile that is not kept is >= the TT-th smallest key of its chain
+        tmin = fminf(tmin, fminf(b[TT - 1], b2[TT - 1]));
 #pragma unroll
-        for (int t = 0; t < TT; t++) {
-          float key = b[t];
+        for (int t = 0; t < (TT == 4 ? 2 * TT : TT); t++) {
+          float key = t < TT ? b[t < TT ? t : 0] : b2[t >= TT ? t - TT : 0];
           int j = ct * K2_TN + (int)(__float_as_uint(key) & 0xFFu);
           if (key < gk[TG - 1]) {
             // sorted insertion with static indexing: once placed, everything below shifts down
@@ -1187,8 +1237,11 @@ static cudaError_t k2_run_rerank(K2Codebook *c, const K1Args &a, const K2Scratch
 template <int TG, int TT>
 static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
   const int Kp = c->Kp;
+  // (A resident beyond K2_ARES_MAX_KP with the two slab stages that then fit was measured at K = 528:
+  // slower, 4.08 -> 4.23 ms for k = 1; the slab ring needs its depth.)
   const bool a_res = Kp <= K2_ARES_MAX_KP;
-  const size_t smem = K2Smem::bytes(Kp, a_res);
+  const int nst = K2_NSTAGE;
+  const size_t smem = K2Smem::bytes(Kp, a_res, nst);
   cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long ntiles_all = (a.N + K2_TM - 1) / K2_TM;
@@ -1206,7 +1259,7 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
     const long ntiles = (n + K2_TM - 1) / K2_TM;
     const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
     k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg + (size_t)row0 * Kp, (const __half *)c->d_ops,
-                                                          s.rs + row0, n, a.M, Kp, a_res ? 1 : 0, a.k,
+                                                          s.rs + row0, n, a.M, Kp, a_res ? 1 : 0, nst, a.k,
                                                           s.cand + row0 * TG, s.thr + row0);
     k1_count_launch(1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
