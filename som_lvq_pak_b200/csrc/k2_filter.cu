@@ -605,12 +605,12 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
             }
           }
         };
-        // TT == 4: a second, independent chain of four (the upper 32 columns of every 64): one warp per
+        // TT == 3, 4: a second, independent chain (the upper 32 columns of every 64): one warp per
         // SM partition runs this epilogue, and a single chain of dependent min/max leaves its issue slots idle
         float b2[TT];
 #pragma unroll
         for (int t = 0; t < TT; t++) b2[t] = INFINITY;
-        if constexpr (TT == 4) {
+        if constexpr (TT == 4 || TT == 3) {
           tmem_ld32_nowait(tbase, va);
           tmem_ld32_nowait(tbase + 32, vb);
 #pragma unroll 1
@@ -628,10 +628,13 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
               const float r1 = fminf(fminf(hi, fmaxf(b[0], lo)), b[1]), s1 = fminf(fminf(hi2, fmaxf(b2[0], lo2)), b2[1]);
               const float r2 = fminf(fminf(fmaxf(b[0], hi), fmaxf(b[1], lo)), b[2]);
               const float s2 = fminf(fminf(fmaxf(b2[0], hi2), fmaxf(b2[1], lo2)), b2[2]);
-              const float r3 = fminf(fminf(fmaxf(b[1], hi), fmaxf(b[2], lo)), b[3]);
-              const float s3 = fminf(fminf(fmaxf(b2[1], hi2), fmaxf(b2[2], lo2)), b2[3]);
-              b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
-              b2[0] = s0; b2[1] = s1; b2[2] = s2; b2[3] = s3;
+              if constexpr (TT == 4) {
+                const float r3 = fminf(fminf(fmaxf(b[1], hi), fmaxf(b[2], lo)), b[3]);
+                const float s3 = fminf(fminf(fmaxf(b2[1], hi2), fmaxf(b2[2], lo2)), b2[3]);
+                b[3] = r3; b2[3] = s3;
+              }
+              b[0] = r0; b[1] = r1; b[2] = r2;
+              b2[0] = s0; b2[1] = s1; b2[2] = s2;
             }
             if (c0 + 64 < K2_TN) {
               tmem_ld32_nowait(tbase + c0 + 64, va);
@@ -656,7 +659,7 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
         // everything of this tile that is not kept is >= the TT-th smallest key of its chain
         tmin = fminf(tmin, fminf(b[TT - 1], b2[TT - 1]));
 #pragma unroll
-        for (int t = 0; t < (TT == 4 ? 2 * TT : TT); t++) {
+        for (int t = 0; t < ((TT == 4 || TT == 3) ? 2 * TT : TT); t++) {
           float key = t < TT ? b[t < TT ? t : 0] : b2[t >= TT ? t - TT : 0];
           int j = ct * K2_TN + (int)(__float_as_uint(key) & 0xFFu);
           if (key < gk[TG - 1]) {
