@@ -720,15 +720,15 @@ __device__ __forceinline__ uint32_t k2r_idesc() {
   return (1u << 4) | ((uint32_t)(K2R_TNH >> 3) << 17) | ((uint32_t)(K2_TM >> 4) << 24);
 }
 
-// Record kernel.  CTA = 4 row tiles (A resident) x all code tiles (staged whole, 3-deep ring).
+// Record kernel.  CTA = 4 row tiles (A resident) x all code tiles (staged whole, K2R_BST-deep ring).
 // MMA order per code tile: (half h, row tile r) -> accumulator r (128 TMEM columns each), so an
 // accumulator is rewritten every 4th MMA group and its epilogue group has 3 MMA groups of time.
-// Epilogue per 32 columns of a row: minima of the four 8-column groups and of the chunk
-// (18 FMNMX3/FMNMX, 0.56 ALU op per score).  Only if some lane's chunk minimum is below its
-// running threshold thr = best + delta (vote) does the warp run the short predicated update that
-// records the GROUP holding the minimum; the exact distances of the <= 2 x 8 codes of the
-// recorded groups are computed by the re-rank warps (k2r_rerank_row).  Invariant for the certificate: a
-// group that is not recorded has a minimum >= min(final best + delta, lost).
+// Epilogue per 32 columns of a row: minima of the eight 4-column groups and of the chunk
+// (20 FMNMX3/FMNMX, 0.63 ALU-pipe op per score).  Only if some lane's chunk minimum is below its
+// running threshold thr = k0 + delta (vote) does the warp run the short predicated update (41
+// instructions) that records the GROUP holding the minimum; the exact distances of the <= 2 x 4 codes
+// of the recorded groups are computed by the re-rank warps (k2r_rerank_row).  Invariant for the
+// certificate: a group that is not recorded has a minimum >= min(final k0 + delta, lost).
 // Exact re-rank of ONE row inside the record kernel (one thread): the reference's sum (lvq_pak.c:63-73)
 // over the <= 2 x K2R_GW codes of the recorded groups, first-minimum rule (lvq_pak.c:79), then the
 // certificate.  Returns false when the row has to be answered by the exact kernel K1.
