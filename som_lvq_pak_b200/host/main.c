@@ -17,7 +17,8 @@ static int dispatch(const char *prog, int argc, char **argv) {
   if (strcmp(prog, "classify") == 0) return classify_main(argc, argv);
   if (strcmp(prog, "knntest") == 0) return knntest_main(argc, argv);
   if (strcmp(prog, "vfind") == 0) return vfind_main(argc, argv);
-  if (strcmp(prog, "randinit") == 0 || strcmp(prog, "mapinit") == 0) return randinit_main(argc, argv, prog);
+  if (strcmp(prog, "randinit") == 0 || strcmp(prog, "lininit") == 0 || strcmp(prog, "mapinit") == 0)
+    return randinit_main(argc, argv, prog);
   if (strcmp(prog, "eveninit") == 0 || strcmp(prog, "propinit") == 0) return eveninit_main(argc, argv, prog);
   if (strcmp(prog, "mindist") == 0) return mindist_main(argc, argv);
   if (strcmp(prog, "sammon") == 0) return sammon_main(argc, argv);
@@ -87,7 +88,7 @@ int main(int argc, char **argv) {
     rc = dispatch(argv[1], argc - 1, argv + 1);
   }
   if (rc == -2) {
-    fprintf(stderr, "usage: bmu_pak <randinit|eveninit|propinit|balance|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n"
+    fprintf(stderr, "usage: bmu_pak <randinit|lininit|eveninit|propinit|balance|mindist|sammon|vsom|vfind|qerror|visual|vcal|accuracy|classify|knntest|cmatr|setlabel|elimin|lvq1|olvq1|lvq2|lvq3|pakcat> <options>\n"
                     "       bmu_pak batch [file]     one program per line, run in one process\n");
     return 2;
   }

@@ -935,6 +935,120 @@ int vfind_main(int argc, char **argv) {
 /* ------------------------------------------------------------------ randinit */
 /* mapinit.c:52-181 with the random initialisation (randinit / mapinit -init rand); the linear
  * initialisation (eigenvectors of the data) is not on the BMU path and is not carried over */
+/* ------------------------------------------------------------------ lininit */
+/* lininit_codes / find_eigenvectors (som_rout.c:166-429): the map is laid out on the plane of the two
+ * largest eigenvectors of the data's autocorrelation matrix, found by ten power iterations from a start
+ * drawn with the reference's generator.  Host arithmetic (every sum is a sequential float sum over the
+ * data, so its order is part of the result); each operation keeps the reference's operand types. */
+static void lin_normalize(float *v, int n) {                         /* som_rout.c:166-174 */
+  float sum = 0.0;
+  int j;
+  for (j = 0; j < n; j++) sum += v[j] * v[j];
+  sum = sqrt(sum);
+  for (j = 0; j < n; j++) v[j] /= sum;
+}
+static float lin_dotprod(const float *v, const float *w, int n) {    /* som_rout.c:177-184 */
+  float sum = 0.0;
+  int j;
+  for (j = 0; j < n; j++) sum += v[j] * w[j];
+  return sum;
+}
+static int lin_gram_schmidt(float *v, int n, int e) {                /* som_rout.c:187-208 */
+  int i, j, p, t;
+  float sum, *w = (float *)malloc(sizeof(float) * (size_t)n * e);
+  if (!w) return 1;
+  for (i = 0; i < e; i++) {
+    for (t = 0; t < n; t++) {
+      sum = v[i * n + t];
+      for (j = 0; j < i; j++)
+        for (p = 0; p < n; p++) sum -= w[j * n + t] * w[j * n + p] * v[i * n + p];
+      w[i * n + t] = sum;
+    }
+    lin_normalize(w + i * n, n);
+  }
+  memcpy(v, w, sizeof(float) * (size_t)n * e);
+  free(w);
+  return 0;
+}
+/* mean[n], eigen1[n], eigen2[n]; returns non-zero when the reference would fail (fewer than three
+ * entries, a zero eigenvalue estimate) */
+static int lin_eigenvectors(const struct pak_entries *data, unsigned long *next, float *mean, float *eigen1, float *eigen2) {
+  const int n = data->dim;
+  float *r = (float *)calloc((size_t)n * n, sizeof(float)), *m = mean;
+  float *u = (float *)malloc(sizeof(float) * 2 * (size_t)n), *v = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+  long *k2 = (long *)calloc((size_t)n, sizeof(long)), i, j, k, e;
+  float mu[2], sum;
+  if (!r || !u || !v || !k2) return 1;
+  for (i = 0; i < n; i++) m[i] = 0.0;
+  for (e = 0; e < data->n; e++) {                                     /* som_rout.c:244-254 */
+    const float *pt = data->points + (size_t)e * n;
+    const unsigned char *mk = data->mask ? data->mask + (size_t)e * n : NULL;
+    for (i = 0; i < n; i++)
+      if (!mk || mk[i] == 0) { m[i] += pt[i]; k2[i]++; }
+  }
+  k = data->n;
+  if (k < 3) return 1;
+  for (i = 0; i < n; i++) m[i] /= k2[i];
+  for (e = 0; e < data->n; e++) {                                     /* som_rout.c:269-283 */
+    const float *pt = data->points + (size_t)e * n;
+    const unsigned char *mk = data->mask ? data->mask + (size_t)e * n : NULL;
+    for (i = 0; i < n; i++) {
+      if (mk && mk[i] != 0) continue;
+      for (j = i; j < n; j++) {
+        if (mk && mk[j] != 0) continue;
+        r[i * n + j] += (pt[i] - m[i]) * (pt[j] - m[j]);
+      }
+    }
+  }
+  for (i = 0; i < n; i++)
+    for (j = i; j < n; j++) r[j * n + i] = r[i * n + j] /= k;
+  for (i = 0; i < 2; i++) {                                           /* som_rout.c:289-293 */
+    for (j = 0; j < n; j++) {
+      *next = (*next * 23) % 100000001;                               /* orand, lvq_pak.c:470-473 */
+      u[i * n + j] = (long)(int)(*next % 32767L) / 16384.0 - 1.0;
+    }
+    lin_normalize(u + i * n, n);
+    mu[i] = 1.0;
+  }
+  for (k = 0; k < 10; k++) {                                          /* som_rout.c:295-311 */
+    for (i = 0; i < 2; i++)
+      for (j = 0; j < n; j++) v[i * n + j] = mu[i] * lin_dotprod(r + j * n, u + i * n, n) + u[i * n + j];
+    if (lin_gram_schmidt(v, n, 2)) return 1;
+    sum = 0.0;                                                        /* NOT reset between the two vectors */
+    for (i = 0; i < 2; i++) {
+      for (j = 0; j < n; j++) sum += fabs(v[i * n + j] / lin_dotprod(r + j * n, v + i * n, n));
+      mu[i] = sum / n;
+    }
+    memcpy(u, v, sizeof(float) * 2 * (size_t)n);
+  }
+  if (mu[0] == 0.0 || mu[1] == 0.0) return 1;
+  for (j = 0; j < n; j++) { eigen1[j] = u[j]; eigen1[j] /= sqrt(mu[0]); }
+  for (j = 0; j < n; j++) { eigen2[j] = u[n + j]; eigen2[j] /= sqrt(mu[1]); }
+  free(r); free(u); free(v); free(k2);
+  return 0;
+}
+static int lininit_codes(const struct pak_entries *data, int xdim, int ydim, long seed, float *codes) {
+  const int dim = data->dim;
+  unsigned long next = (unsigned long)(int)seed;
+  float *mean = (float *)malloc(sizeof(float) * 3 * (size_t)dim), *eigen1, *eigen2, xf, yf;
+  long index, i;
+  if (!mean) return 1;
+  eigen1 = mean + dim;
+  eigen2 = eigen1 + dim;
+  if (lin_eigenvectors(data, &next, mean, eigen1, eigen2)) {
+    fprintf(stderr, "lininit_codes: Can't find eigenvectors\n");
+    free(mean);
+    return 1;
+  }
+  for (index = 0; index < (long)xdim * ydim; index++) {               /* som_rout.c:412-419 */
+    xf = 4.0 * (float)(index % xdim) / (xdim - 1.0) - 2.0;
+    yf = 4.0 * (float)(index / xdim) / (ydim - 1.0) - 2.0;
+    for (i = 0; i < dim; i++) codes[(size_t)index * dim + i] = mean[i] + xf * eigen1[i] + yf * eigen2[i];
+  }
+  free(mean);
+  return 0;
+}
+
 int randinit_main(int argc, char **argv, const char *progname) {
   struct pak_entries *data, *codes;
   const char *din, *cout_name, *s;
@@ -942,7 +1056,7 @@ int randinit_main(int argc, char **argv, const char *progname) {
   long seed;
   FILE *fp;
   long i;
-  int c;
+  int c, lin = -1;
   global_options(argc, argv);
   din = need(argc, argv, "-din");
   cout_name = need(argc, argv, "-cout");
@@ -957,18 +1071,25 @@ int randinit_main(int argc, char **argv, const char *progname) {
   xdim = atoi(need(argc, argv, "-xdim"));
   ydim = atoi(need(argc, argv, "-ydim"));
   s = opt(argc, argv, "-init");
-  if ((s && strcmp(s, "rand") != 0) || (!s && strcasecmp(progname, "randinit") != 0)) {
-    fprintf(stderr, "Unknown initialization type %s (only the random initialisation is provided)\n", s ? s : progname);
-    return 1;
-  }
+  if (strcasecmp(progname, "lininit") == 0) lin = 1;                  /* mapinit.c:72-75, 104-119 */
+  else if (strcasecmp(progname, "randinit") == 0) lin = 0;
+  if (s) lin = strcmp(s, "lin") == 0 ? 1 : (strcmp(s, "rand") == 0 ? 0 : -1);
+  if (lin < 0) { fprintf(stderr, "Unknown initialization type %s\n", s ? s : progname); return 1; }
   if ((long)xdim * ydim <= 0 || xdim < 0) { fprintf(stderr, "Dimensions of map (%d %d) are incorrect\n", xdim, ydim); return 1; }
   data = pak_load(din, 0, 1);
   if (!data) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
   codes = pak_alloc(data->dim, (long)xdim * ydim);
   if (!codes) return 1;
   codes->topol = topol; codes->neigh = neigh; codes->xdim = xdim; codes->ydim = ydim;
-  bmu_randinit_codes(data->points, data->mask, data->n, data->dim, codes->n,
-                     (int)(seed ? seed : (long)time(NULL)), codes->points);       /* init_random, lvq_pak.c:478-484 */
+  if (lin) {
+    if (lininit_codes(data, xdim, ydim, seed ? seed : (long)time(NULL), codes->points)) {
+      fprintf(stderr, "initialization failure\n");
+      return 1;
+    }
+  } else {
+    bmu_randinit_codes(data->points, data->mask, data->n, data->dim, codes->n,
+                       (int)(seed ? seed : (long)time(NULL)), codes->points);     /* init_random, lvq_pak.c:478-484 */
+  }
   fp = fopen(cout_name, "w");
   if (!fp) { fprintf(stderr, "save_entries: Can't open file '%s'\n", cout_name); return 1; }
   pak_write_header(fp, codes);

@@ -52,6 +52,25 @@ def main():
     out["propinit_cod"] = np.array(open(os.path.join(td, "p.cod")).read())
     run([b("eveninit"), "-din", "ex2.dat", "-cout", "e2.cod", "-noc", "317"], td)
     out["eveninit2_cod"] = np.array(open(os.path.join(td, "e2.cod")).read())
+    # lininit (mapinit -init lin): map on the plane of the two largest eigenvectors (som_rout.c:211-429)
+    for f in ("ex.dat", "ex_fts.dat", "ex_ndy.dat"):
+        open(os.path.join(td, f), "w").write(str(demo["in_" + f]))
+    run([b("lininit"), "-din", "ex.dat", "-cout", "lin.cod", "-xdim", "12", "-ydim", "8", "-topol", "hexa", "-neigh", "bubble",
+         "-rand", "123"], td)
+    out["lininit_cod"] = np.array(open(os.path.join(td, "lin.cod")).read())
+    run([b("mapinit"), "-init", "lin", "-din", "ex_fts.dat", "-cout", "lin2.cod", "-xdim", "5", "-ydim", "9", "-topol", "rect",
+         "-neigh", "gaussian", "-rand", "7"], td)
+    out["lininit2_cod"] = np.array(open(os.path.join(td, "lin2.cod")).read())
+    lines = str(demo["in_ex_fts.dat"]).splitlines()
+    for r, c in ((3, 0), (3, 2), (10, 4), (57, 1), (100, 3), (101, 3), (200, 0)):    # a few masked components
+        t = lines[r].split()
+        t[c] = "x"
+        lines[r] = " ".join(t)
+    open(os.path.join(td, "masked.dat"), "w").write("\n".join(lines) + "\n")
+    run([b("lininit"), "-din", "masked.dat", "-cout", "lin3.cod", "-xdim", "4", "-ydim", "3", "-topol", "hexa", "-neigh", "bubble",
+         "-rand", "11"], td)
+    out["lininit3_in"] = np.array(open(os.path.join(td, "masked.dat")).read())
+    out["lininit3_cod"] = np.array(open(os.path.join(td, "lin3.cod")).read())
     # balance (config 2 of BASELINE.json): the demo step, and a second codebook / neighbour count
     open(os.path.join(td, "ex1e.cod"), "w").write(str(demo["lvq_e_cod"]))
     out["balance_stdout"] = np.array(run([b("balance"), "-din", "ex1.dat", "-cin", "ex1e.cod", "-cout", "bal.cod"], td))

@@ -170,3 +170,21 @@ def test_compressed_and_piped_names(tmp_path, demo):
     assert (tmp_path / "c.dat").read_text() == (tmp_path / "plain.dat").read_text()
     subprocess.run([PAK, "pakcat", "-din", "|cat a.dat", "-dout", "|cat > d.dat"], check=True, cwd=tmp_path)
     assert (tmp_path / "d.dat").read_text() == (tmp_path / "plain.dat").read_text()
+
+
+def test_lininit_program(tmp_path, demo, golden):
+    """lininit / mapinit -init lin (som_rout.c:211-429) is host arithmetic: byte-identical maps, also from
+    data with masked components"""
+    x = golden.demo_extra
+    (tmp_path / "ex.dat").write_text(str(demo["in_ex.dat"]))
+    (tmp_path / "ex_fts.dat").write_text(str(demo["in_ex_fts.dat"]))
+    (tmp_path / "masked.dat").write_text(str(x["lininit3_in"]))
+    subprocess.run([PAK, "lininit", "-din", "ex.dat", "-cout", "lin.cod", "-xdim", "12", "-ydim", "8", "-topol", "hexa",
+                    "-neigh", "bubble", "-rand", "123"], check=True, cwd=tmp_path)
+    assert (tmp_path / "lin.cod").read_text() == str(x["lininit_cod"])
+    subprocess.run([PAK, "mapinit", "-init", "lin", "-din", "ex_fts.dat", "-cout", "lin2.cod", "-xdim", "5", "-ydim", "9",
+                    "-topol", "rect", "-neigh", "gaussian", "-rand", "7"], check=True, cwd=tmp_path)
+    assert (tmp_path / "lin2.cod").read_text() == str(x["lininit2_cod"])
+    subprocess.run([PAK, "lininit", "-din", "masked.dat", "-cout", "lin3.cod", "-xdim", "4", "-ydim", "3", "-topol", "hexa",
+                    "-neigh", "bubble", "-rand", "11"], check=True, cwd=tmp_path)
+    assert (tmp_path / "lin3.cod").read_text() == str(x["lininit3_cod"])
