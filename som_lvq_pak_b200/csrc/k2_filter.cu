@@ -43,7 +43,9 @@ constexpr int K2_TM = 128;   // rows per sample tile (UMMA M)
 constexpr int K2_TN = 256;   // codes per code tile (UMMA N)
 constexpr int K2_KS = 64;    // K elements per pipeline stage (4 MMAs), streaming kernel
 constexpr int K2_NSTAGE = 4;
-constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.  (Eight epilogue warps, two per
+                                  // row splitting the 256 columns, were measured on C4: GEMM 4.0 -> 4.5 ms (k = 1), 4.95 -> 5.85
+                                  // (k = 5), and the re-rank blocks that run beside the GEMM CTA got fewer registers.)
 constexpr int K2_ARES_MAX_KP = 320;   // A image stays resident in smem up to this Kp (streaming kernel)
 
 constexpr int K2R_R = 4;          // row tiles per CTA pass of the record kernel = epilogue groups = accumulators
