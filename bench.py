@@ -5,13 +5,16 @@ configs[2]: 10 M vectors x 64-dim vs a 100x100 map, qerror + visual style consum
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference's C code on host cores
 
-One "step" = one pass of the hot path over one batch: every rank searches its own shard of
-`rows` vectors against the replicated codebook (no data-path collective), reduces its
-qerror sum / found count / BMU histogram on the device, and the small statistics vector is
-combined by ONE NCCL all-reduce.  Weak scaling: rows per GPU is fixed.
+One "step" = one pass of the hot path over the batch: the 10 M rows are cut into contiguous
+shards, one per GPU (STRONG scaling: the total is fixed); every rank searches its shard against
+the replicated codebook (no data-path collective), reduces its qerror sum / found count / BMU
+histogram on the device, and the small statistics vector is combined by ONE grouped NCCL
+all-reduce issued by the library.  For N > 1 a weak-scaling figure (10 M rows on
+every GPU) is reported beside it under "weak".
 
 JSON keys follow the driver contract; `value` is device-resident (inputs already in HBM),
-`e2e` goes through bmu_search() with pinned HOST buffers (H2D + D2H inside the timed region).
+`e2e` goes through bmu_search() with plain pageable HOST buffers (H2D + D2H inside the timed
+region; the library stages them through its pinned ring).
 The oracle/ directory is only used for the cpu_baseline leg and for --impl reference.
 """
 import argparse
@@ -29,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: rows per GPU, D, M, xdim, k
+    # name: rows IN TOTAL (sharded over the GPUs), D, M, xdim, k
     "c3": dict(rows=10_000_000, D=64, M=10_000, xdim=100, k=1,
                desc="synthetic batch winner search: 10M x 64-dim vs 100x100 map (BASELINE.json configs[2])"),
     "c4": dict(rows=1_000_000, D=512, M=4096, xdim=64, k=1,
@@ -226,7 +229,7 @@ def main_reference(args, w):
         "impl": "reference", "metric": "BMU searches/s", "value": value, "unit": "searches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * rows_per_core * cores / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "rows_per_step": rows_per_core * cores, "D": w["D"],
                    "M": w["M"], "k": w["k"]},
         "cpu_baseline": {"value": value, "unit": "searches/s", "cores": cores, "kind": kind,
@@ -245,6 +248,7 @@ def main_gpu(args, w):
     import torch.distributed as dist
     import som_lvq_pak_b200 as bmu
     from som_lvq_pak_b200 import _lib
+    from som_lvq_pak_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,58 +260,53 @@ def main_gpu(args, w):
     bmu.init(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        D.comm_init()                 # the library's own NCCL communicator (id moved by torch.distributed)
     lib = _lib.load()
     _lib.check(lib.bmu_set_search_path({"auto": 0, "exact": 1, "filter": 2}[args.path]))
 
-    rows, D, M, k = args.rows or w["rows"], w["D"], w["M"], w["k"]
-    # codebook: generated on rank 0, replicated by one broadcast
-    codes = synth_rows_torch(2, 0, M, D, dev) if rank == 0 else torch.empty((M, D), device=dev)
-    if world > 1:
-        dist.broadcast(codes, 0)
+    # STRONG scaling (the named config): `total` rows in all, rank r searches the contiguous shard
+    # [lo, hi) the library's own rule gives it (bmu_multi_shard_bounds)
+    total, D_, M, k = args.rows or w["rows"], w["D"], w["M"], w["k"]
+    Dm = D_
+    lo, hi = D.shard_bounds(total, rank, world)
+    rows = hi - lo
+    stream = torch.cuda.current_stream().cuda_stream
+    # codebook: generated on rank 0, replicated by ONE ncclBroadcast inside the library
+    codes = synth_rows_torch(2, 0, M, Dm, dev) if rank == 0 else torch.empty((M, Dm), device=dev)
+    _lib.check(lib.bmu_comm_broadcast_dev(codes.data_ptr(), M * Dm * 4, 0, stream))
     torch.cuda.synchronize()
-    cb = lib.bmu_codebook_create_dev(codes.data_ptr(), M, D)
+    cb = lib.bmu_codebook_create_dev(codes.data_ptr(), M, Dm)
     if not cb:
         raise SystemExit("bmu_codebook_create_dev: " + lib.bmu_last_error().decode())
-    data = synth_rows_torch(1, rank * rows, rows, D, dev)
-    idx = torch.empty((rows, k), dtype=torch.int32, device=dev)
-    diff = torch.empty((rows, k), dtype=torch.float32, device=dev)
-    nf = torch.empty(rows, dtype=torch.int32, device=dev)
-    stats = torch.zeros(2 + M, dtype=torch.float64, device=dev)      # [sum sqrt, n_found, hist...]
-    hist = torch.zeros(M, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        hist.zero_()
-        stats.zero_()
-        _lib.check(lib.bmu_search_dev(cb, data.data_ptr(), None, rows, k, idx.data_ptr(),
-                                      diff.data_ptr(), nf.data_ptr(), stream))
-        _lib.check(lib.bmu_search_stats_dev(idx.data_ptr(), diff.data_ptr(), nf.data_ptr(), rows, k,
-                                            M, stats.data_ptr(), hist.data_ptr(), None, None, 0,
-                                            None, stream))
-        if world > 1:
-            stats[2:] = hist.to(torch.float64)      # counts < 2^53: exact in float64
-            dist.all_reduce(stats)
+    data = synth_rows_torch(1, lo, rows, Dm, dev)
+    ss = D.ShardedSearch(cb, M, rows, k, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
+        return float(t[0])
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        ss.step(data.data_ptr())
     barrier()
     kms = (ctypes.c_float * 8)()
-
     launches0 = lib.bmu_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(lambda: ss.step(data.data_ptr()), args.steps)
     launches = lib.bmu_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     # duration of the dominant kernel, measured live with CUDA events on the launching stream: events
@@ -319,44 +318,71 @@ def main_gpu(args, w):
         lib.bmu_search_kernel_ms_history(back, kms)
         for i in range(8):
             kernel_ms[i] += float(kms[i]) / nhist
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum)
-        ms, launches = float(tmax[0]), int(tsum[1])
-    else:
-        launches = int(launches)
-    value = world * rows * args.steps / (ms * 1e-3)
-    qsum, nfound = float(stats[0]), int(stats[1])
+        dist.all_reduce(t)
+    launches = int(t[0])
+    value = total * args.steps / (ms * 1e-3)
+    qsum, nfound, hist = ss.totals()
     bd = bmu.last_search_breakdown()
+    idx, diff = ss.idx, ss.diff
 
-    # ---- e2e: the reference-facing C-ABI call with HOST buffers (pinned), copies in the timed region
-    h_data = torch.empty((rows, D), dtype=torch.float32, pin_memory=True)
-    h_data.copy_(data)
-    h_idx = torch.empty((rows, k), dtype=torch.int32, pin_memory=True)
-    h_diff = torch.empty((rows, k), dtype=torch.float32, pin_memory=True)
-    h_nf = torch.empty(rows, dtype=torch.int32, pin_memory=True)
-    torch.cuda.synchronize()
+    # ---- e2e: the reference-facing C-ABI call with plain HOST buffers (pageable numpy arrays, what a C
+    # host's calloc gives, datafile.c:472), host<->device copies inside the timed region
+    h_data = np.empty((rows, Dm), np.float32)
+    step_rows = 1 << 20
+    for r in range(0, rows, step_rows):
+        h_data[r:r + step_rows] = data[r:r + step_rows].cpu().numpy()
+    h_idx = np.empty((rows, k), np.int32)
+    h_diff = np.empty((rows, k), np.float32)
+    h_nf = np.empty(rows, np.int32)
 
     def e2e_step():
-        _lib.check(lib.bmu_search(cb, h_data.data_ptr(), None, rows, k, h_idx.data_ptr(),
-                                  h_diff.data_ptr(), h_nf.data_ptr()))
+        _lib.check(lib.bmu_search(cb, h_data.ctypes.data, None, rows, k, h_idx.ctypes.data,
+                                  h_diff.ctypes.data, h_nf.ctypes.data))
+
+    def wall(fn, steps):
+        fn()                                                   # warm-up (allocates the pinned ring)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
 
     e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * rows * e2e_steps / float(te[0])
-    same = bool((h_idx.to(dev) == idx).all()) and bool((h_diff.to(dev) == diff).all())
+    e2e_s = wall(e2e_step, e2e_steps)
+    e2e_value = total * e2e_steps / e2e_s
+    same = bool((torch.from_numpy(h_idx).to(dev) == idx).all()) and bool((torch.from_numpy(h_diff).to(dev) == diff).all())
+    # the same call on page-locked buffers (bmu_host_register): the DMA reads the caller's arrays directly
+    e2e_pinned = None
+    if not args.no_pinned:
+        regs = [(h_data.ctypes.data, h_data.nbytes), (h_idx.ctypes.data, h_idx.nbytes),
+                (h_diff.ctypes.data, h_diff.nbytes), (h_nf.ctypes.data, h_nf.nbytes)]
+        ok = all(lib.bmu_host_register(p_, n_) == 0 for p_, n_ in regs)
+        if ok:
+            e2e_pinned = total * e2e_steps / wall(e2e_step, e2e_steps)
+        for p_, _ in regs:
+            lib.bmu_host_unregister(p_)
+    del h_data
+
+    # ---- weak scaling beside the strong headline (N > 1): `total` rows on EVERY GPU
+    weak = None
+    if world > 1 and not args.no_weak:
+        del data, ss
+        torch.cuda.empty_cache()
+        wdata = synth_rows_torch(1, rank * total, total, Dm, dev)
+        ws = D.ShardedSearch(cb, M, total, k, dev)
+        for _ in range(2):
+            ws.step(wdata.data_ptr())
+        wsteps = max(1, min(args.steps, 3))
+        wms = timed(lambda: ws.step(wdata.data_ptr()), wsteps)
+        weak = {"value": world * total * wsteps / (wms * 1e-3), "unit": "searches/s", "ms_per_step": wms / wsteps,
+                "rows_per_gpu": total, "steps": wsteps}
+        del wdata, ws
 
     if rank == 0:
         peaks = {}
@@ -371,35 +397,36 @@ def main_gpu(args, w):
         used_k2 = bd["k2_certified"] + bd["k2_failed"] > 0
         names = ("k1_data_prep", "k1_fast", "k1_warp", "k1_seq", "k2_row_prep", "k2_gemm", "k2_rerank", "k2_lists")
         step_ms = {n: v for n, v in zip(names, kernel_ms) if (n.startswith("k2") == used_k2)}
-        hbm_bytes = rows * (4.0 * D + 12.0 * k)
+        hbm_bytes = rows * (4.0 * Dm + 12.0 * k)
         if used_k2:
-            kp = ((D + 7) // 8 * 8 + 3 + 15) // 16 * 16                   # fp16 operand K: D + 3 norm columns
+            kp = ((Dm + 7) // 8 * 8 + 3 + 15) // 16 * 16                   # fp16 operand K: D + 3 norm columns
             k_ms = kernel_ms[5]
             kname = "k2_rec_kernel" if (k == 1 and kp <= 96) else "k2_gemm_kernel"
-            flop = 2.0 * M * D * rows                                      # 2*M*D per search
+            flop = 2.0 * M * Dm * rows                                     # 2*M*D per search
             achieved = flop / (k_ms * 1e-3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             m_pad = (M + 255) // 256 * 256
-            issued = achieved * (kp / D) * (m_pad / M)
+            issued = achieved * (kp / Dm) * (m_pad / M)
+            traffic = NCU_TRAFFIC.get((kname, rows, Dm, M))
             roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((kname, rows, D, M)),
+                    "frac": achieved / peak, "traffic": traffic,
                     "kernel_ms": k_ms, "step_kernels_ms": step_ms,
-                    "note": "algorithmic 2*M*D flop per search over the live CUDA-event duration of %s vs the "
-                            "sustained fp16/bf16 cuBLAS peak (%s); the kernel issues %.2fx that many MMA flops "
+                    "note": "algorithmic 2*M*D flop per search over the live CUDA-event duration of %s (rank 0's shard) "
+                            "vs the sustained fp16/bf16 cuBLAS peak (%s); the kernel issues %.2fx that many MMA flops "
                             "(K %d -> %d: 3 norm columns + padding to 16; M %d -> %d), so the tensor pipe itself "
                             "runs at %.3f of that peak.  For k = 1 the timed kernel also contains the exact re-rank "
                             "(4 extra warps; FMA-pipe work that replaced a separate 2.3 ms kernel), which the flop "
                             "count above does not credit.  traffic = ncu dram bytes of one launch (profiles/), null "
                             "when no capture exists for this shape"
                             % (kname, "measured" if "bf16_tflops_sustained" in peaks else "fallback",
-                               (kp / D) * (m_pad / M), D, kp, M, m_pad, issued / peak),
+                               (kp / Dm) * (m_pad / M), Dm, kp, M, m_pad, issued / peak),
                     "mma_issued_tflops": issued,
                     "rows_certified": bd["k2_certified"], "rows_redone_exactly": bd["k2_failed"]}
             search_path = "filter (K2 tcgen05 GEMM + exact re-rank, K1 for uncertified rows)"
         else:
             k_ms = kernel_ms[1] if kernel_ms[1] > 0 else kernel_ms[2]
             kname = "k1_fast_kernel" if kernel_ms[1] > 0 else "k1_warp_kernel"
-            flop = 3.0 * M * D * rows                                      # 3*M*D per search
+            flop = 3.0 * M * Dm * rows                                     # 3*M*D per search
             achieved = flop / (k_ms * 1e-3) / 1e12
             roof = {"bound": "fp32_issue", "kernel": kname, "achieved": achieved, "peak": fp32_peak,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None, "kernel_ms": k_ms,
@@ -413,39 +440,50 @@ def main_gpu(args, w):
                        "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}
         line = {
             "metric": "BMU searches/s", "value": value, "unit": "searches/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": w["desc"], "rows_per_gpu": rows, "D": D, "M": M, "k": k,
-                       "parallelism": "data-sharded x%d, codebook replicated, 1 all-reduce of %d doubles per step"
-                                      % (world, 2 + M),
-                       "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB)" % (rows * D * 4 / 1e9),
+            "config": {"workload": w["desc"], "rows_total": total, "rows_per_gpu": rows, "D": Dm, "M": M, "k": k,
+                       "parallelism": "rows sharded x%d inside libbmu_b200 (contiguous slices), codebook replicated by "
+                                      "one ncclBroadcast, ONE grouped ncclAllReduce per step of 1 double + %d int64 "
+                                      "(sum sqrt(diff); n_found, BMU histogram)" % (world, 1 + M),
+                       "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB)" % (rows * Dm * 4 / 1e9),
                        "search_path": search_path},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "searches/s", "h2d_bytes_per_step": rows * D * 4,
-                    "d2h_bytes_per_step": rows * k * 8 + rows * 4, "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": "searches/s", "h2d_bytes_per_step": total * Dm * 4,
+                    "d2h_bytes_per_step": total * k * 8 + total * 4, "steps": e2e_steps,
+                    "host_buffers": "pageable (numpy), staged through the library's pinned ring by its copy threads",
+                    "value_page_locked_buffers": e2e_pinned,
                     "matches_device_resident_run": same},
             "gpu_launches": launches,
             "roofline": roof,
-            "result_check": {"mean_qerror": qsum / max(nfound, 1), "n_found": nfound},
+            "result_check": {"mean_qerror": qsum / max(nfound, 1), "n_found": nfound,
+                             "hist_total": int(hist.sum())},
         }
+        if weak:
+            line["weak"] = weak
         if world == 1 and not args.no_vsom:
             line["vsom"] = vsom_c5(bmu, args)
         if world == 1 and not args.no_c4 and args.workload == "c3":
-            del data, idx, diff, nf, h_data, h_idx, h_diff, h_nf
+            try:
+                del data, ss
+            except NameError:
+                pass
+            del idx, diff
             torch.cuda.empty_cache()
             line["c4"] = c4_extra(bmu, lib, _lib, dev, peaks)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            rpc = args.ref_rows or max(64, int(10.0 * 1600 * (10_000 * 64) / (M * D)))
-            v, kind, wall = cpu_searches_per_s(w, rpc, cores, k)
+            rpc = args.ref_rows or max(64, int(10.0 * 1600 * (10_000 * 64) / (M * Dm)))
+            v, kind, wall_s = cpu_searches_per_s(w, rpc, cores, k)
             line["cpu_baseline"] = {"value": v, "unit": "searches/s", "cores": cores, "kind": kind,
                                     "sample": "first %d rows per core x %d forked processes, same codebook "
                                               "(reference find_winner_euc, gcc -O3), %.1f s wall"
-                                              % (rpc, cores, wall)}
+                                              % (rpc, cores, wall_s)}
         print(json.dumps(line))
     lib.bmu_codebook_destroy(cb)
     if world > 1:
+        lib.bmu_comm_destroy()
         dist.destroy_process_group()
     return 0
 
@@ -520,11 +558,25 @@ def vsom_c5(bmu, args):
     ms = t.last_ms()
     t.close()
     M = xdim * ydim
+    info = bmu.device_info()
+    try:
+        sm_max = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0)
+    except Exception:
+        sm_max = 1965.0
+    fp32_peak = info["sm_count"] * 128 * sm_max * 1e6 / 1e12
+    ach = 6.0 * M * D * steps / (ms * 1e-3) / 1e12
     out = {"metric": "vsom steps/s", "value": steps / (ms * 1e-3), "unit": "steps/s",
            "e2e_value": steps / wall, "steps": steps, "us_per_step": 1e3 * ms / steps,
-           "config": "256x256 hexa gaussian map, 128-dim, rlen 1e6 schedule (first %d steps), alpha 0.05 "
-                     "linear, radius 100, -rand 3 order, 100000 x 128 synthetic data" % steps,
-           "lane_ops_per_step": 6.0 * M * D, "achieved_tflops": 6.0 * M * D * steps / (ms * 1e-3) / 1e12}
+           "config": "256x256 hexa gaussian map, 128-dim, rlen 1e6 schedule (%s), alpha 0.05 "
+                     "linear, radius 100, -rand 3 order, 100000 x 128 synthetic data"
+                     % ("all 1e6 steps" if steps == length else "first %d steps" % steps),
+           "lane_ops_per_step": 6.0 * M * D,
+           "roofline": {"bound": "fp32_issue", "kernel": "k3_som_fused_kernel", "achieved": ach, "peak": fp32_peak,
+                        "unit": "T lane-ops/s", "frac": ach / fp32_peak,
+                        "note": "6*M*D non-FMA FP32 lane-ops per gaussian step (search 3*M*D + update 3*M*D, SURVEY 8d) "
+                                "over the CUDA-event duration of the one persistent launch, vs SMs*128*sm_max_clock; the "
+                                "step is a latency chain (grid-wide winner exchange -> lattice weights -> one pass), so "
+                                "this fraction is what the chain leaves, not a pipe limit"}}
     if not args.no_cpu:
         from oracle.pyoracle import Reference, Oracle
         nref = 30
@@ -556,12 +608,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
+    ap.add_argument("--rows", type=int, default=0, help="override the total number of rows (debug)")
     ap.add_argument("--ref-rows", type=int, default=0, help="override CPU sample rows per core")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vsom", action="store_true", help="skip the vsom (configs[4]) extra metric")
     ap.add_argument("--no-c4", action="store_true", help="skip the high-dim (configs[3]) extra metric")
-    ap.add_argument("--vsom-steps", type=int, default=50000)
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra (N > 1)")
+    ap.add_argument("--no-pinned", action="store_true", help="skip the page-locked variant of the e2e leg")
+    ap.add_argument("--vsom-steps", type=int, default=1_000_000)
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "filter"],
                     help="search kernels: auto (default), exact = K1 only, filter = K2 forced")
     args = ap.parse_args()

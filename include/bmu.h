@@ -84,7 +84,9 @@ int bmu_last_search_kernel_ms(float out[8]);
  * calls that are kept), so that a timed loop can be read after its closing synchronisation */
 int bmu_search_kernel_ms_history(int back, float out[8]);
 
-/* ---- codebook (replicated on every GPU; reference: struct entries *codes) --------- */
+/* ---- codebook (replicated on every GPU; reference: struct entries *codes) ---------
+ * All kernel-side images (K1 tiles, the fp16 operands of the K2 filter) are built synchronously
+ * inside create / update. */
 typedef struct bmu_codebook bmu_codebook;
 bmu_codebook *bmu_codebook_create(const float *codes, long M, int D);        /* host ptr  */
 bmu_codebook *bmu_codebook_create_dev(const float *d_codes, long M, int D);  /* device ptr */
@@ -99,20 +101,87 @@ void bmu_codebook_destroy(bmu_codebook *cb);
  * Host-pointer version: copies in chunks overlapped with compute (this is bench.py's e2e). */
 int bmu_search(bmu_codebook *cb, const float *data, const unsigned char *mask, long N, int k,
                int32_t *idx, float *diff, int32_t *nfound);
-/* device-pointer version, asynchronous on `stream` (a cudaStream_t, NULL = default) */
+/* device-pointer version, asynchronous on `stream` (a cudaStream_t, NULL = default).  All searches
+ * of one device share one scratch set (work lists, counters, operand images): the library orders
+ * every search after the one before it with an event, whatever streams they were launched on, so
+ * calls from several streams are safe but do not overlap each other. */
 int bmu_search_dev(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask, long N,
                    int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound, void *stream);
 
 /* per-shard partial statistics of a finished search, to be summed over GPUs by ONE small
- * all-reduce.  d_stats[0] = sum sqrt(diff[:,0]) over found rows (double; the
- * byte-exact float sum of som_rout.c:715 is replayed on the host in data order),
- * d_stats[1] = number of found rows; d_hist (nullable): M int64 BMU hit counts;
- * d_confusion (nullable): n_labels x n_labels int64, [sample label][winner label], labels
- * from d_sample_label[N] / d_code_label[M] in 0..n_labels-1.  Accumulates (+=). */
+ * all-reduce (reference accumulators: find_qerror som_rout.c:710-721, find_labels
+ * vcal.c:109-131, compute_accuracy accuracy.c:82-118, compute_cmatr cmatr.c:84-109).
+ * *d_sum += sum of sqrt(diff[:,0]) over found rows -- a double, reduced on the device in a fixed
+ * order (bit-identical from run to run for a given N; NOT the reference's sequential float sum:
+ * the byte-exact qerror is bmu_replay_qerror over the gathered diffs in data order);
+ * *d_nfound_total += number of found rows; d_hist (nullable): M int64 BMU hit counts;
+ * d_confusion (nullable): n_labels x n_labels int64, [sample label][winner's label], labels from
+ * d_sample_label[N] / d_code_label[M] in 0..n_labels-1.  All counters are int64 and accumulate (+=):
+ * zero them before the first shard/chunk.  Asynchronous on `stream`. */
 int bmu_search_stats_dev(const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound,
-                         long N, int k, long M, double *d_stats, long long *d_hist,
-                         const int32_t *d_sample_label, const int32_t *d_code_label,
-                         int n_labels, long long *d_confusion, void *stream);
+                         long N, int k, long M, double *d_sum, long long *d_nfound_total,
+                         long long *d_hist, const int32_t *d_sample_label,
+                         const int32_t *d_code_label, int n_labels, long long *d_confusion,
+                         void *stream);
+
+/* ---- the data-parallel split: rows sharded over GPUs, codebook replicated ---- */
+/* Host-side view of the combined statistics (bmu_multi_search).  hist / confusion: NULL = not wanted,
+ * else caller arrays of M / n_labels*n_labels int64 that receive the totals over ALL shards. */
+typedef struct bmu_stats {
+  double sum_sqrt;              /* out: sum of sqrt(diff[:,0]) over found rows                 */
+  long long n_found;            /* out: rows with a winner                                     */
+  long long *hist;              /* out (nullable): BMU hits per code vector                    */
+  long long *confusion;         /* out (nullable): [sample label][winner's label]              */
+  const int32_t *sample_label;  /* in: N labels in 0..n_labels-1 (only with confusion)         */
+  int n_labels;
+} bmu_stats;
+
+/* (A) one process, all GPUs -- what the C hosts use.  nshards = 0: $SOMLVQ_GPUS if set, else every
+ * visible device.  One shard per device; asking for more shards than devices places the extra
+ * (logical) shards round-robin on the devices, each with its own streams and scratch (used by the
+ * tests to run the sharded path on one GPU; statistics of shards that share a device are added on
+ * the device, devices are combined by NCCL).  Needs libnccl.so.2 at run time when > 1 device. */
+int bmu_multi_init(int nshards);
+int bmu_multi_shards(void);
+int bmu_multi_devices(void);
+/* rows [lo, hi) of shard `shard`: contiguous, balanced, cut at multiples of 512 rows */
+void bmu_multi_shard_bounds(long N, int nshards, int shard, long *lo, long *hi);
+typedef struct bmu_mcodebook bmu_mcodebook;
+/* codes (host) -> device 0 -> ONE ncclBroadcast to the other devices */
+bmu_mcodebook *bmu_mcodebook_create(const float *codes, long M, int D);
+int bmu_mcodebook_update(bmu_mcodebook *cb, const float *codes);
+int bmu_mcodebook_set_labels(bmu_mcodebook *cb, const int32_t *code_label);   /* M, for confusion */
+void bmu_mcodebook_destroy(bmu_mcodebook *cb);
+/* bmu_search over all shards: every shard streams its contiguous slice of the caller's rows through
+ * its own GPU and writes idx/diff/nfound straight into the caller's arrays (data order kept, no
+ * gather); stats (nullable) = totals over all shards after ONE grouped NCCL all-reduce of
+ * {double sum} + {int64 n_found, hist[M], confusion[L*L]}.  Results are identical to bmu_search. */
+int bmu_multi_search(bmu_mcodebook *cb, const float *data, const unsigned char *mask, long N, int k,
+                     int32_t *idx, float *diff, int32_t *nfound, bmu_stats *stats);
+
+/* (B) one process per GPU (torchrun / MPI style launchers): rank 0 makes the id, the launcher hands
+ * the 128 bytes to every rank, every rank binds its bmu_init device.  The collectives run on device
+ * buffers, asynchronously on `stream`; with no communicator (a single rank) they are no-ops. */
+int bmu_comm_unique_id(unsigned char id[128]);
+int bmu_comm_init_rank(int nranks, int rank, const unsigned char id[128]);
+int bmu_comm_destroy(void);
+int bmu_comm_broadcast_dev(void *d_buf, size_t bytes, int root, void *stream);   /* codebook replicate */
+/* ONE grouped all-reduce (sum) of a double vector and an int64 vector, in place */
+int bmu_comm_allreduce_stats_dev(double *d_sum, long nsum, long long *d_counts, long ncounts,
+                                 void *stream);
+
+/* ---- page-locked host memory -------------------------------------------------------- */
+/* bmu_search / bmu_multi_search accept ANY host memory.  Pageable buffers (malloc/calloc, what the
+ * reference's hosts have, datafile.c:472) are staged through a pinned ring by a few copy threads,
+ * chunk by chunk, overlapped with the DMA and the kernels; buffers that are already page-locked are
+ * read by the DMA engine directly.  A host that owns its allocation can skip the staging hop: */
+void *bmu_host_alloc(size_t bytes);            /* page-locked; NULL on failure */
+void bmu_host_free(void *p);
+int bmu_host_register(void *p, size_t bytes);  /* pin an existing allocation in place */
+int bmu_host_unregister(void *p);
+/* threads that stage pageable memory (0 = default: min(8, cores / ranks on this box), or
+ * $SOMLVQ_COPY_THREADS) */
+int bmu_set_copy_threads(int n);
 
 /* ---- online training (sequential; one GPU) ---------------------------------------- */
 /* Schedules are produced on the host with the reference's own formulas (bmu_som_schedule /

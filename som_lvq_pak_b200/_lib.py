@@ -35,8 +35,27 @@ PROTOTYPES = {
     "bmu_codebook_destroy": (None, [vp]),
     "bmu_search": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, vp, vp, vp]),
     "bmu_search_dev": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, vp, vp, vp, vp]),
-    "bmu_search_stats_dev": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, C.c_long, vp, vp, vp, vp,
+    "bmu_search_stats_dev": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, C.c_long, vp, vp, vp, vp, vp,
                                        C.c_int, vp, vp]),
+    "bmu_multi_init": (C.c_int, [C.c_int]),
+    "bmu_multi_shards": (C.c_int, []),
+    "bmu_multi_devices": (C.c_int, []),
+    "bmu_multi_shard_bounds": (None, [C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+    "bmu_mcodebook_create": (vp, [vp, C.c_long, C.c_int]),
+    "bmu_mcodebook_update": (C.c_int, [vp, vp]),
+    "bmu_mcodebook_set_labels": (C.c_int, [vp, vp]),
+    "bmu_mcodebook_destroy": (None, [vp]),
+    "bmu_multi_search": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, vp, vp, vp, vp]),
+    "bmu_comm_unique_id": (C.c_int, [vp]),
+    "bmu_comm_init_rank": (C.c_int, [C.c_int, C.c_int, vp]),
+    "bmu_comm_destroy": (C.c_int, []),
+    "bmu_comm_broadcast_dev": (C.c_int, [vp, C.c_size_t, C.c_int, vp]),
+    "bmu_comm_allreduce_stats_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp]),
+    "bmu_host_alloc": (vp, [C.c_size_t]),
+    "bmu_host_free": (None, [vp]),
+    "bmu_host_register": (C.c_int, [vp, C.c_size_t]),
+    "bmu_host_unregister": (C.c_int, [vp]),
+    "bmu_set_copy_threads": (C.c_int, [C.c_int]),
     "bmu_som_train": (C.c_int, [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                 C.c_long, vp, vp, vp, vp, C.c_long]),
     "bmu_lvq_train": (C.c_int, [C.c_int, vp, vp, C.c_long, C.c_int, vp, vp, vp, C.c_long, vp, vp,
@@ -61,6 +80,14 @@ PROTOTYPES = {
     "bmu_lvq_schedule": (None, [C.c_long, C.c_long, C.c_long, C.c_float, C.c_int, C.c_long, vp,
                                 vp, vp]),
 }
+
+
+
+class Stats(C.Structure):
+    """struct bmu_stats of include/bmu.h"""
+    _fields_ = [("sum_sqrt", C.c_double), ("n_found", C.c_longlong), ("hist", vp), ("confusion", vp),
+                ("sample_label", vp), ("n_labels", C.c_int)]
+
 
 _lib = None
 

@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/bmu.h"
 #include "common.cuh"
 #include "k1_search.h"
@@ -23,11 +25,18 @@ using namespace bmu;
 
 // ------------------------------------------------------------------ context
 namespace bmu {
-char g_err[512] = "";
-int g_dev = -1;
-int g_sms = 0;
-size_t g_smem_optin = 0;
-cudaStream_t g_compute = nullptr, g_copy = nullptr, g_out = nullptr;
+thread_local char g_err[512] = "";
+static DevCtx g_primary_ctx;                 // the device of bmu_init (single-GPU entry points)
+static thread_local DevCtx *t_ctx = nullptr; // worker threads of the multi-GPU path bind their own
+static std::atomic<long> g_launches{0};
+
+DevCtx *ctx() { return t_ctx ? t_ctx : &g_primary_ctx; }
+void bind_ctx(DevCtx *c) {
+  t_ctx = c;
+  if (c && c->dev >= 0) cudaSetDevice(c->dev);
+}
+long k1_launch_count() { return g_launches.load(); }
+void k1_count_launch(int n) { g_launches += n; }
 
 int fail(int code, const char *fmt, ...) {
   va_list ap;
@@ -37,7 +46,7 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 int ensure_init() {
-  if (g_dev >= 0) return BMU_OK;
+  if (ctx()->dev >= 0) return BMU_OK;
   return bmu_init(0);
 }
 int Scratch::ensure(size_t need) {
@@ -62,28 +71,8 @@ void Scratch::release() {
   p = nullptr;
   bytes = 0;
 }
-}  // namespace bmu
 
-namespace {
-
-int g_path = BMU_PATH_AUTO;
-const int *g_last_counters = nullptr;     // device counters of the last search call
-long g_last_rows = 0;
-int g_last_used_k2 = 0;
-
-struct SearchScratch {
-  Scratch xT, flags, listW, listS, counters, k2;
-};
-SearchScratch g_ss[2];          // two sets so that chunked host searches can overlap
-Scratch g_stage_in[2], g_stage_mask[2], g_stage_idx[2], g_stage_diff[2], g_stage_nf[2];
-Scratch g_q2_out;                // per-sample values of bmu_qerror2
-
-}  // namespace
-
-extern "C" {
-
-int bmu_init(int device) {
-  if (g_dev == device && g_compute) return BMU_OK;
+int ctx_open(DevCtx *c, int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -98,31 +87,77 @@ int bmu_init(int device) {
   if (p.major != 10)
     return fail(BMU_ERR_NODEV, "device %d is sm_%d%d; this library is built for sm_100a only",
                 device, p.major, p.minor);
-  if (g_compute) bmu_shutdown();
-  g_dev = device;
-  g_sms = p.multiProcessorCount;
-  g_smem_optin = p.sharedMemPerBlockOptin;
-  CK(cudaStreamCreateWithFlags(&g_compute, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&g_out, cudaStreamNonBlocking));
+  if (c->compute) ctx_close(c);
+  c->dev = device;
+  c->sms = p.multiProcessorCount;
+  c->smem_optin = p.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->out, cudaStreamNonBlocking));
+  // every event the entry points use is created once here (not per call)
+  CK(cudaEventCreateWithFlags(&c->ss_done, cudaEventDisableTiming));
+  for (int b = 0; b < BMU_NSLOT; b++) {
+    CK(cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_work[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming));
+  }
+  c->ss_used = 0;
   return BMU_OK;
 }
 
-void bmu_shutdown(void) {
-  if (g_dev < 0) return;
+void ctx_close(DevCtx *c) {
+  if (c->dev < 0) return;
+  cudaSetDevice(c->dev);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 2; i++) {
-    g_ss[i].xT.release(); g_ss[i].flags.release(); g_ss[i].listW.release();
-    g_ss[i].listS.release(); g_ss[i].counters.release(); g_ss[i].k2.release();
-    g_stage_in[i].release(); g_stage_mask[i].release(); g_stage_idx[i].release();
-    g_stage_diff[i].release(); g_stage_nf[i].release();
+  host_ring_free(c);
+  c->ss.xT.release(); c->ss.flags.release(); c->ss.listW.release();
+  c->ss.listS.release(); c->ss.counters.release(); c->ss.k2.release();
+  for (int i = 0; i < BMU_NSLOT; i++) {
+    c->stage_in[i].release(); c->stage_mask[i].release(); c->stage_idx[i].release();
+    c->stage_diff[i].release(); c->stage_nf[i].release(); c->stage_lab[i].release();
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_work[i]) cudaEventDestroy(c->ev_work[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    c->ev_in[i] = c->ev_work[i] = c->ev_out[i] = nullptr;
   }
-  g_q2_out.release();
-  if (g_compute) cudaStreamDestroy(g_compute);
-  if (g_copy) cudaStreamDestroy(g_copy);
-  if (g_out) cudaStreamDestroy(g_out);
-  g_compute = g_copy = g_out = nullptr;
-  g_dev = -1;
+  c->q2_out.release(); c->stat_f64.release(); c->stat_i64.release(); c->stat_part.release();
+  if (c->ss_done) cudaEventDestroy(c->ss_done);
+  c->ss_done = nullptr;
+  for (int r = 0; r < K_EV_RING; r++)
+    for (int i = 0; i < 5; i++) {
+      if (c->k1ring[r][i]) cudaEventDestroy(c->k1ring[r][i]);
+      if (c->k2ring[r][i]) cudaEventDestroy(c->k2ring[r][i]);
+      c->k1ring[r][i] = c->k2ring[r][i] = nullptr;
+    }
+  c->k1calls = c->k2calls = 0;
+  for (int i = 0; i < 8; i++) { if (c->k2sub[i]) cudaEventDestroy(c->k2sub[i]); c->k2sub[i] = nullptr; }
+  if (c->k2join) cudaEventDestroy(c->k2join);
+  c->k2join = nullptr;
+  if (c->k2aux) cudaStreamDestroy(c->k2aux);
+  if (c->compute) cudaStreamDestroy(c->compute);
+  if (c->copy) cudaStreamDestroy(c->copy);
+  if (c->out) cudaStreamDestroy(c->out);
+  c->k2aux = c->compute = c->copy = c->out = nullptr;
+  c->last_counters = nullptr;
+  c->dev = -1;
+}
+}  // namespace bmu
+
+namespace {
+int g_path = BMU_PATH_AUTO;
+}  // namespace
+
+extern "C" {
+
+int bmu_init(int device) {
+  DevCtx *c = &g_primary_ctx;
+  if (c->dev == device && c->compute) return cudaSetDevice(device) == cudaSuccess ? BMU_OK : fail(BMU_ERR_CUDA, "cudaSetDevice");
+  return ctx_open(c, device);
+}
+
+void bmu_shutdown(void) {
+  multi_shutdown();
+  ctx_close(&g_primary_ctx);
 }
 
 const char *bmu_last_error(void) { return g_err; }
@@ -160,20 +195,44 @@ int bmu_search_kernel_ms_history(int back, float out[8]) {
 }
 
 int bmu_last_search_breakdown(long out[5]) {
+  DevCtx *c = ctx();
   for (int i = 0; i < 5; i++) out[i] = 0;
-  if (!g_last_counters) return BMU_OK;
+  if (!c->last_counters) return BMU_OK;
   int h[4];
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(h, g_last_counters, sizeof(h), cudaMemcpyDeviceToHost));
-  out[0] = g_last_rows;
+  CK(cudaMemcpy(h, c->last_counters, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = c->last_rows;
   out[1] = h[0];
   out[2] = h[1];
-  out[3] = g_last_used_k2 ? h[2] : 0;
-  out[4] = g_last_used_k2 ? h[3] : 0;
+  out[3] = c->last_used_k2 ? h[2] : 0;
+  out[4] = c->last_used_k2 ? h[3] : 0;
   return BMU_OK;
 }
 
 // ------------------------------------------------------------------ codebook
+static bool k2_worth_building(long M, int D, unsigned cb_flags) {
+  // the operands of the tensor-core filter are built WITH the codebook (synchronously, on the
+  // context's stream) whenever a later search could pick the filter on its own; a search that is
+  // forced onto the filter afterwards (bmu_set_search_path) builds them inside the search, ordered
+  // like every search by the context's ss_done event
+  return k2_eligible(g_path, M, D, 1L << 30, 1, cb_flags);
+}
+
+static int codebook_finish(bmu_codebook *cb) {       // after d_codes is written on g_compute
+  cudaError_t e = k1_prepare_codebook(cb->d_codes, cb->M, cb->D, cb->d_cT, cb->d_flags, g_compute);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+  if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "codebook upload failed: %s", cudaGetErrorString(e));
+  k2_codebook_invalidate(&cb->k2);
+  if (k2_worth_building(cb->M, cb->D, cb->h_flags)) {
+    e = k2_prepare_codebook(&cb->k2, cb->d_codes, cb->M, cb->D, g_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+    if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k2_prepare_codebook: %s", cudaGetErrorString(e));
+  }
+  return BMU_OK;
+}
+
 static bmu_codebook *codebook_from_dev(const float *d_src, const float *h_src, long M, int D) {
   if (ensure_init()) return nullptr;
   if (M <= 0 || D <= 0 || M > 0x7fffff00L) {
@@ -184,6 +243,7 @@ static bmu_codebook *codebook_from_dev(const float *d_src, const float *h_src, l
   if (!cb) { fail(BMU_ERR_NOMEM, "calloc"); return nullptr; }
   cb->M = M;
   cb->D = D;
+  cb->owner = ctx();
   size_t bytes = (size_t)M * D * sizeof(float);
   bool ok = cudaMalloc(&cb->d_codes, bytes) == cudaSuccess &&
             cudaMalloc(&cb->d_cT, k1_cT_floats(M, D) * sizeof(float)) == cudaSuccess &&
@@ -194,19 +254,39 @@ static bmu_codebook *codebook_from_dev(const float *d_src, const float *h_src, l
     bmu_codebook_destroy(cb);
     return nullptr;
   }
-  cudaError_t e = h_src ? cudaMemcpyAsync(cb->d_codes, h_src, bytes, cudaMemcpyHostToDevice, g_compute)
-                        : cudaMemcpyAsync(cb->d_codes, d_src, bytes, cudaMemcpyDeviceToDevice, g_compute);
-  if (e == cudaSuccess) e = k1_prepare_codebook(cb->d_codes, M, D, cb->d_cT, cb->d_flags, g_compute);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
+  cudaError_t e = cudaSuccess;
+  if (h_src) e = cudaMemcpyAsync(cb->d_codes, h_src, bytes, cudaMemcpyHostToDevice, g_compute);
+  else if (d_src) e = cudaMemcpyAsync(cb->d_codes, d_src, bytes, cudaMemcpyDeviceToDevice, g_compute);
   if (e != cudaSuccess) {
     fail(BMU_ERR_CUDA, "codebook upload failed: %s", cudaGetErrorString(e));
     bmu_codebook_destroy(cb);
     return nullptr;
   }
+  if ((h_src || d_src) && codebook_finish(cb)) {
+    bmu_codebook_destroy(cb);
+    return nullptr;
+  }
   return cb;
 }
+
+}  // extern "C"
+namespace bmu {
+// multi-GPU path: an empty replica whose d_codes the caller fills (ncclBroadcast) before codebook_ready
+bmu_codebook *codebook_alloc(long M, int D) { return codebook_from_dev(nullptr, nullptr, M, D); }
+int codebook_ready(bmu_codebook *cb) { return codebook_finish(cb); }
+int codebook_set_labels(bmu_codebook *cb, const int32_t *label) {
+  if (cb->d_label) { cudaFree(cb->d_label); cb->d_label = nullptr; }
+  if (!label) return BMU_OK;
+  if (cudaMalloc((void **)&cb->d_label, (size_t)cb->M * 4) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BMU_ERR_NOMEM, "cudaMalloc of the code labels failed");
+  }
+  CK(cudaMemcpyAsync(cb->d_label, label, (size_t)cb->M * 4, cudaMemcpyHostToDevice, g_compute));
+  CK(cudaStreamSynchronize(g_compute));
+  return BMU_OK;
+}
+}  // namespace bmu
+extern "C" {
 
 bmu_codebook *bmu_codebook_create(const float *codes, long M, int D) {
   if (!codes) { fail(BMU_ERR_ARG, "codes is NULL"); return nullptr; }
@@ -220,14 +300,13 @@ bmu_codebook *bmu_codebook_create_dev(const float *d_codes, long M, int D) {
 
 int bmu_codebook_update(bmu_codebook *cb, const float *codes) {
   if (!cb || !codes) return fail(BMU_ERR_ARG, "NULL argument");
+  DevCtx *c = ctx();
+  // a search still in flight on another stream reads the images that are rewritten here
+  if (c->ss_used) CK(cudaStreamWaitEvent(g_compute, c->ss_done, 0));
   CK(cudaMemcpyAsync(cb->d_codes, codes, (size_t)cb->M * cb->D * sizeof(float),
                      cudaMemcpyHostToDevice, g_compute));
-  CK(k1_prepare_codebook(cb->d_codes, cb->M, cb->D, cb->d_cT, cb->d_flags, g_compute));
-  CK(cudaMemcpyAsync(&cb->h_flags, cb->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, g_compute));
-  CK(cudaStreamSynchronize(g_compute));
-  k2_codebook_invalidate(&cb->k2);
   if (cb->d_cq) { cudaFree(cb->d_cq); cb->d_cq = nullptr; }
-  return BMU_OK;
+  return codebook_finish(cb);
 }
 
 void bmu_codebook_destroy(bmu_codebook *cb) {
@@ -236,22 +315,31 @@ void bmu_codebook_destroy(bmu_codebook *cb) {
   if (cb->d_cT) cudaFree(cb->d_cT);
   if (cb->d_flags) cudaFree(cb->d_flags);
   if (cb->d_cq) cudaFree(cb->d_cq);
+  if (cb->d_label) cudaFree(cb->d_label);
   k2_codebook_free(&cb->k2);
   free(cb);
 }
 
 // ------------------------------------------------------------------ search
-static int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask,
-                           long N, int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound,
-                           cudaStream_t st, SearchScratch &ss) {
+}  // extern "C"
+namespace bmu {
+int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask, long N, int k,
+                    int32_t *d_idx, float *d_diff, int32_t *d_nfound, cudaStream_t st) {
   if (!cb || !d_data || !d_idx || !d_diff || !d_nfound) return fail(BMU_ERR_ARG, "NULL argument");
   if (k < 1 || k > BMU_KMAX) return fail(BMU_ERR_ARG, "k=%d outside 1..%d", k, BMU_KMAX);
   if (N < 0 || N > 0x7fffff00L) return fail(BMU_ERR_ARG, "bad N=%ld", N);
   if (N == 0) return BMU_OK;
+  DevCtx *c = ctx();
+  if (cb->owner != c) return fail(BMU_ERR_ARG, "codebook belongs to another device context");
+  SearchScratch &ss = c->ss;
   const int D = cb->D;
   int rc;
   const bool use_k2 = k2_eligible(g_path, cb->M, D, N, k, cb->h_flags);
   const bool need_tiles = (k == 1) && !cb->h_flags && !use_k2;
+  // the scratch (and the K2 operands of the codebook) are shared by every search of this context:
+  // wait for the search before, whatever stream it ran on.  Growing a buffer frees the old one, which
+  // the CUDA runtime orders after all work already queued on the device.
+  if (c->ss_used) CK(cudaStreamWaitEvent(st, c->ss_done, 0));
   if (need_tiles && (rc = ss.xT.ensure(k1_xT_floats(N, D) * sizeof(float)))) return rc;
   if ((rc = ss.flags.ensure((size_t)N))) return rc;
   if ((rc = ss.listW.ensure((size_t)N * sizeof(int)))) return rc;
@@ -262,103 +350,35 @@ static int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned
   a.data = d_data; a.mask = d_mask; a.codes = cb->d_codes; a.cT = cb->d_cT;
   a.cb_flags = cb->d_flags; a.N = N; a.M = cb->M; a.D = D; a.k = k;
   a.skip_fast = need_tiles ? 0 : 1;
-  a.num_sms = g_sms;
+  a.num_sms = c->sms;
   a.short_list = use_k2 ? 1 : 0;
   a.xT = (float *)ss.xT.p; a.flags = (unsigned char *)ss.flags.p;
   a.listW = (int *)ss.listW.p; a.listS = (int *)ss.listS.p; a.counters = (int *)ss.counters.p;
   a.idx = d_idx; a.diff = d_diff; a.nfound = d_nfound;
-  g_last_counters = a.counters;
-  g_last_rows = N;
-  g_last_used_k2 = use_k2 ? 1 : 0;
-  if (use_k2) {
-    cudaError_t e = k2_search(&cb->k2, a, &ss.k2.p, &ss.k2.bytes, st);
-    if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k2_search: %s", cudaGetErrorString(e));
-    return BMU_OK;
-  }
-  cudaError_t e = k1_search(a, st);
-  if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "k1_search: %s", cudaGetErrorString(e));
+  c->last_counters = a.counters;
+  c->last_rows = N;
+  c->last_used_k2 = use_k2 ? 1 : 0;
+  cudaError_t e = use_k2 ? k2_search(&cb->k2, a, &ss.k2.p, &ss.k2.bytes, st) : k1_search(a, st);
+  if (e != cudaSuccess) return fail(BMU_ERR_CUDA, "%s: %s", use_k2 ? "k2_search" : "k1_search", cudaGetErrorString(e));
+  CK(cudaEventRecord(c->ss_done, st));
+  c->ss_used = 1;
   return BMU_OK;
 }
+}  // namespace bmu
+extern "C" {
 
 int bmu_search_dev(bmu_codebook *cb, const float *d_data, const unsigned char *d_mask, long N,
                    int k, int32_t *d_idx, float *d_diff, int32_t *d_nfound, void *stream) {
   int rc = ensure_init();
   if (rc) return rc;
-  return search_dev_impl(cb, d_data, d_mask, N, k, d_idx, d_diff, d_nfound, (cudaStream_t)stream,
-                         g_ss[0]);
-}
-
-// Host-pointer search: rows are processed in chunks on three streams; chunk c+1 is copied in
-// (g_copy) while chunk c is searched (g_compute) and chunk c-1's results drain (g_out).
-int bmu_search(bmu_codebook *cb, const float *data, const unsigned char *mask, long N, int k,
-               int32_t *idx, float *diff, int32_t *nfound) {
-  int rc = ensure_init();
-  if (rc) return rc;
-  if (!cb || !data || !idx || !diff || !nfound) return fail(BMU_ERR_ARG, "NULL argument");
-  if (k < 1 || k > BMU_KMAX) return fail(BMU_ERR_ARG, "k=%d outside 1..%d", k, BMU_KMAX);
-  if (N <= 0) return N == 0 ? BMU_OK : fail(BMU_ERR_ARG, "bad N");
-  const int D = cb->D;
-  // chunk: about 256 MB of input, a multiple of the 128-row tile
-  long chunk = (256L << 20) / ((long)D * 4);
-  chunk = (chunk / K1_TS) * K1_TS;
-  if (chunk < K1_TS) chunk = K1_TS;
-  if (chunk > N) chunk = N;
-  for (int b = 0; b < 2; b++) {
-    if ((rc = g_stage_in[b].ensure((size_t)chunk * D * 4))) return rc;
-    if (mask && (rc = g_stage_mask[b].ensure((size_t)chunk * D))) return rc;
-    if ((rc = g_stage_idx[b].ensure((size_t)chunk * k * 4))) return rc;
-    if ((rc = g_stage_diff[b].ensure((size_t)chunk * k * 4))) return rc;
-    if ((rc = g_stage_nf[b].ensure((size_t)chunk * 4))) return rc;
-  }
-  cudaEvent_t in_done[2], work_done[2], out_done[2];
-  for (int b = 0; b < 2; b++) {
-    CK(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&work_done[b], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
-  }
-  const long nchunks = (N + chunk - 1) / chunk;
-  int status = BMU_OK;
-  for (long c = 0; c < nchunks && status == BMU_OK; c++) {
-    const int b = (int)(c & 1);
-    const long n0 = c * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
-    // the staging buffers of slot b are free once chunk c-2 has been searched and drained
-    if (c >= 2) CK(cudaStreamWaitEvent(g_copy, work_done[b], 0));
-    CK(cudaMemcpyAsync(g_stage_in[b].p, data + n0 * (long)D, (size_t)n * D * 4,
-                       cudaMemcpyHostToDevice, g_copy));
-    if (mask)
-      CK(cudaMemcpyAsync(g_stage_mask[b].p, mask + n0 * (long)D, (size_t)n * D,
-                         cudaMemcpyHostToDevice, g_copy));
-    CK(cudaEventRecord(in_done[b], g_copy));
-    CK(cudaStreamWaitEvent(g_compute, in_done[b], 0));
-    if (c >= 2) CK(cudaStreamWaitEvent(g_compute, out_done[b], 0));
-    status = search_dev_impl(cb, (const float *)g_stage_in[b].p,
-                             mask ? (const unsigned char *)g_stage_mask[b].p : nullptr, n, k,
-                             (int32_t *)g_stage_idx[b].p, (float *)g_stage_diff[b].p,
-                             (int32_t *)g_stage_nf[b].p, g_compute, g_ss[b]);
-    if (status) break;
-    CK(cudaEventRecord(work_done[b], g_compute));
-    CK(cudaStreamWaitEvent(g_out, work_done[b], 0));
-    CK(cudaMemcpyAsync(idx + n0 * (long)k, g_stage_idx[b].p, (size_t)n * k * 4,
-                       cudaMemcpyDeviceToHost, g_out));
-    CK(cudaMemcpyAsync(diff + n0 * (long)k, g_stage_diff[b].p, (size_t)n * k * 4,
-                       cudaMemcpyDeviceToHost, g_out));
-    CK(cudaMemcpyAsync(nfound + n0, g_stage_nf[b].p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_out));
-    CK(cudaEventRecord(out_done[b], g_out));
-  }
-  cudaError_t e1 = cudaStreamSynchronize(g_compute), e2 = cudaStreamSynchronize(g_out);
-  cudaStreamSynchronize(g_copy);
-  for (int b = 0; b < 2; b++) {
-    cudaEventDestroy(in_done[b]); cudaEventDestroy(work_done[b]); cudaEventDestroy(out_done[b]);
-  }
-  if (status) return status;
-  if (e1 != cudaSuccess) return fail(BMU_ERR_CUDA, "search failed: %s", cudaGetErrorString(e1));
-  if (e2 != cudaSuccess) return fail(BMU_ERR_CUDA, "search copy failed: %s", cudaGetErrorString(e2));
-  return BMU_OK;
+  return search_dev_impl(cb, d_data, d_mask, N, k, d_idx, d_diff, d_nfound, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ qerror -qetype 1
 // find_qerror2 (som_rout.c:823-891): winner search (k = 1) followed by the neighbourhood-weighted
 // pass K4 over the same resident chunk; the host adds out[] in data order (one float, som_rout.c:872).
+// Chunks are double buffered: the rows of chunk c+1 are copied in (copy stream) and the values of
+// chunk c-1 drain (out stream) while chunk c is searched and weighted (compute stream).
 int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, float radius,
                 const float *data, const unsigned char *mask, long N, float *out) {
   int rc = ensure_init();
@@ -369,6 +389,8 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
   if (topol != BMU_TOPOL_HEXA && topol != BMU_TOPOL_RECT) return fail(BMU_ERR_ARG, "bad topology %d", topol);
   if (neigh != BMU_NEIGH_BUBBLE && neigh != BMU_NEIGH_GAUSSIAN) return fail(BMU_ERR_ARG, "bad neighbourhood %d", neigh);
   if (N <= 0) return N == 0 ? BMU_OK : fail(BMU_ERR_ARG, "bad N");
+  DevCtx *c = ctx();
+  if (cb->owner != c) return fail(BMU_ERR_ARG, "codebook belongs to another device context");
   const int D = cb->D;
   if (!cb->d_cq) {
     if (cudaMalloc((void **)&cb->d_cq, (size_t)k4_mp(cb->M) * D * sizeof(float)) != cudaSuccess) {
@@ -378,31 +400,53 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
     CK(k4_transpose_codebook(cb->d_codes, cb->M, D, cb->d_cq, g_compute));
     k1_count_launch(1);
   }
-  long chunk = (256L << 20) / ((long)D * 4);
+  long chunk = (64L << 20) / ((long)D * 4);
   if (chunk < 1) chunk = 1;
   if (chunk > N) chunk = N;
-  if ((rc = g_stage_in[0].ensure((size_t)chunk * D * 4))) return rc;
-  if (mask && (rc = g_stage_mask[0].ensure((size_t)chunk * D))) return rc;
-  if ((rc = g_stage_idx[0].ensure((size_t)chunk * 4))) return rc;
-  if ((rc = g_stage_diff[0].ensure((size_t)chunk * 4))) return rc;
-  if ((rc = g_stage_nf[0].ensure((size_t)chunk * 4))) return rc;
-  if ((rc = g_q2_out.ensure((size_t)chunk * 4))) return rc;
-  for (long n0 = 0; n0 < N; n0 += chunk) {
-    const long n = (N - n0 < chunk) ? N - n0 : chunk;
-    CK(cudaMemcpyAsync(g_stage_in[0].p, data + n0 * (long)D, (size_t)n * D * 4, cudaMemcpyHostToDevice, g_compute));
-    if (mask)
-      CK(cudaMemcpyAsync(g_stage_mask[0].p, mask + n0 * (long)D, (size_t)n * D, cudaMemcpyHostToDevice, g_compute));
-    const unsigned char *d_mask = mask ? (const unsigned char *)g_stage_mask[0].p : nullptr;
-    if ((rc = search_dev_impl(cb, (const float *)g_stage_in[0].p, d_mask, n, 1, (int32_t *)g_stage_idx[0].p,
-                              (float *)g_stage_diff[0].p, (int32_t *)g_stage_nf[0].p, g_compute, g_ss[0])))
-      return rc;
-    CK(k4_qerror2(cb->d_cq, cb->M, D, xdim, topol, neigh, radius, (const float *)g_stage_in[0].p, d_mask, n,
-                  (const int32_t *)g_stage_idx[0].p, (const int32_t *)g_stage_nf[0].p, (float *)g_q2_out.p,
-                  g_sms, g_compute));
-    k1_count_launch(1);
-    CK(cudaMemcpyAsync(out + n0, g_q2_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_compute));
-    CK(cudaStreamSynchronize(g_compute));
+  Scratch *q2[2] = {&c->q2_out, &c->stage_lab[0]};          // per-sample values of the two slots
+  for (int b = 0; b < 2; b++) {
+    if ((rc = c->stage_in[b].ensure((size_t)chunk * D * 4))) return rc;
+    if (mask && (rc = c->stage_mask[b].ensure((size_t)chunk * D))) return rc;
+    if ((rc = c->stage_idx[b].ensure((size_t)chunk * 4))) return rc;
+    if ((rc = c->stage_diff[b].ensure((size_t)chunk * 4))) return rc;
+    if ((rc = c->stage_nf[b].ensure((size_t)chunk * 4))) return rc;
+    if ((rc = q2[b]->ensure((size_t)chunk * 4))) return rc;
   }
+  int status = BMU_OK;
+  long cidx = 0;
+  for (long n0 = 0; n0 < N && status == BMU_OK; n0 += chunk, cidx++) {
+    const int b = (int)(cidx & 1);
+    const long n = (N - n0 < chunk) ? N - n0 : chunk;
+    cudaError_t e = cudaSuccess;
+    // slot b is free once chunk c-2 has been computed (inputs) and drained (values)
+    if (cidx >= 2) e = cudaStreamWaitEvent(g_copy, c->ev_work[b], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(c->stage_in[b].p, data + n0 * (long)D, (size_t)n * D * 4, cudaMemcpyHostToDevice, g_copy);
+    if (e == cudaSuccess && mask)
+      e = cudaMemcpyAsync(c->stage_mask[b].p, mask + n0 * (long)D, (size_t)n * D, cudaMemcpyHostToDevice, g_copy);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_in[b], g_copy);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_compute, c->ev_in[b], 0);
+    if (e == cudaSuccess && cidx >= 2) e = cudaStreamWaitEvent(g_compute, c->ev_out[b], 0);
+    if (e != cudaSuccess) { status = fail(BMU_ERR_CUDA, "bmu_qerror2: %s", cudaGetErrorString(e)); break; }
+    const unsigned char *d_mask = mask ? (const unsigned char *)c->stage_mask[b].p : nullptr;
+    if ((status = search_dev_impl(cb, (const float *)c->stage_in[b].p, d_mask, n, 1, (int32_t *)c->stage_idx[b].p,
+                                  (float *)c->stage_diff[b].p, (int32_t *)c->stage_nf[b].p, g_compute)))
+      break;
+    e = k4_qerror2(cb->d_cq, cb->M, D, xdim, topol, neigh, radius, (const float *)c->stage_in[b].p, d_mask, n,
+                   (const int32_t *)c->stage_idx[b].p, (const int32_t *)c->stage_nf[b].p, (float *)q2[b]->p, c->sms,
+                   g_compute);
+    k1_count_launch(1);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_work[b], g_compute);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_out, c->ev_work[b], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out + n0, q2[b]->p, (size_t)n * 4, cudaMemcpyDeviceToHost, g_out);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_out[b], g_out);
+    if (e != cudaSuccess) status = fail(BMU_ERR_CUDA, "bmu_qerror2: %s", cudaGetErrorString(e));
+  }
+  // single exit: nothing that references the caller's buffers is left queued, error or not
+  cudaError_t e0 = cudaStreamSynchronize(g_copy), e1 = cudaStreamSynchronize(g_compute), e2 = cudaStreamSynchronize(g_out);
+  if (status) return status;
+  if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
+    return fail(BMU_ERR_CUDA, "bmu_qerror2: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
   return BMU_OK;
 }
 
@@ -563,11 +607,22 @@ int bmu_sammon(const float *codes, const unsigned char *mask, long M, int D, lon
 }
 
 // ------------------------------------------------------------------ statistics
-__global__ void stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
-                             const int32_t *__restrict__ nfound, long N, int k, long M,
-                             double *__restrict__ stats, unsigned long long *__restrict__ hist,
-                             const int32_t *__restrict__ slabel, const int32_t *__restrict__ clabel,
-                             int L, unsigned long long *__restrict__ conf) {
+// Per-shard sums of a finished search (find_qerror's accumulator som_rout.c:710-721, the hit counts of
+// vcal.c:109-131 / accuracy.c:82-118 / cmatr.c:84-109), in the form ONE all-reduce can combine:
+// counts are int64 (exact whatever the order), the sum of sqrt(diff) is a double that is reduced in a
+// FIXED order -- per-thread grid-stride partial, xor-shuffle tree, warp partials in warp order, block
+// partials in block order by the last block to finish -- so it is bit-identical from run to run for a
+// given (N, grid).  It is NOT the reference's sequential float sum; bmu_replay_qerror is.
+#define STATS_THREADS 256
+__global__ void __launch_bounds__(STATS_THREADS)
+stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
+             const int32_t *__restrict__ nfound, long N, int k, long M, double *__restrict__ sum_out,
+             unsigned long long *__restrict__ nfound_out, unsigned long long *__restrict__ hist,
+             const int32_t *__restrict__ slabel, const int32_t *__restrict__ clabel, int L,
+             unsigned long long *__restrict__ conf, double *__restrict__ part, unsigned *__restrict__ ticket) {
+  __shared__ double ws[STATS_THREADS / 32];
+  __shared__ unsigned long long wc[STATS_THREADS / 32];
+  __shared__ bool last;
   double s = 0.0;
   unsigned long long cnt = 0;
   for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < N; n += (long)gridDim.x * blockDim.x) {
@@ -585,29 +640,62 @@ __global__ void stats_kernel(const int32_t *__restrict__ idx, const float *__res
     s += __shfl_xor_sync(0xffffffffu, s, off);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&stats[0], s);
-    atomicAdd(&stats[1], (double)cnt);
+  if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wc[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bs = 0.0;
+    unsigned long long bc = 0;
+    for (int w = 0; w < STATS_THREADS / 32; w++) { bs += ws[w]; bc += wc[w]; }
+    part[blockIdx.x] = bs;
+    if (bc) atomicAdd(nfound_out, bc);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b2 = 0; b2 < gridDim.x; b2++) t += ((volatile double *)part)[b2];
+    *sum_out += t;                       // accumulates over the chunks of a call, in chunk order
+    *ticket = 0;
   }
 }
 
+}  // extern "C"
+namespace bmu {
+int stats_accumulate(DevCtx *c, const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound, long N, int k,
+                     long M, double *d_sum, long long *d_nfound_total, long long *d_hist, const int32_t *d_slabel,
+                     const int32_t *d_clabel, int L, long long *d_conf, cudaStream_t st) {
+  if (N <= 0) return BMU_OK;
+  const int grid = c->sms * 4;
+  if (c->stat_part.bytes < (size_t)(grid + 2) * 8) {
+    int rc = c->stat_part.ensure((size_t)(grid + 2) * 8);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->stat_part.p, 0, c->stat_part.bytes, st));
+  }
+  double *part = (double *)c->stat_part.p;
+  stats_kernel<<<grid, STATS_THREADS, 0, st>>>(d_idx, d_diff, d_nfound, N, k, M, d_sum,
+                                               (unsigned long long *)d_nfound_total, (unsigned long long *)d_hist,
+                                               d_slabel, d_clabel, L, (unsigned long long *)d_conf, part + 1,
+                                               (unsigned *)part);
+  k1_count_launch(1);
+  CK(cudaGetLastError());
+  return BMU_OK;
+}
+}  // namespace bmu
+extern "C" {
+
 int bmu_search_stats_dev(const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound,
-                         long N, int k, long M, double *d_stats, long long *d_hist,
+                         long N, int k, long M, double *d_sum, long long *d_nfound_total, long long *d_hist,
                          const int32_t *d_sample_label, const int32_t *d_code_label,
                          int n_labels, long long *d_confusion, void *stream) {
   int rc = ensure_init();
   if (rc) return rc;
-  if (!d_idx || !d_diff || !d_nfound || !d_stats) return fail(BMU_ERR_ARG, "NULL argument");
+  if (!d_idx || !d_diff || !d_nfound || !d_sum || !d_nfound_total) return fail(BMU_ERR_ARG, "NULL argument");
   if (d_confusion && (!d_sample_label || !d_code_label || n_labels <= 0))
     return fail(BMU_ERR_ARG, "confusion counts need labels");
-  if (N <= 0) return BMU_OK;
-  int grid = g_sms * 4;
-  stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      d_idx, d_diff, d_nfound, N, k, M, d_stats, (unsigned long long *)d_hist, d_sample_label,
-      d_code_label, n_labels, (unsigned long long *)d_confusion);
-  k1_count_launch(1);
-  CK(cudaGetLastError());
-  return BMU_OK;
+  return stats_accumulate(ctx(), d_idx, d_diff, d_nfound, N, k, M, d_sum, d_nfound_total, d_hist, d_sample_label,
+                          d_code_label, n_labels, d_confusion, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ host helpers

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "k1_search.h"
+#include "api_internal.h"
 
 namespace bmu {
 
@@ -556,9 +557,7 @@ k1_seq_kernel(const float *__restrict__ data, const unsigned char *__restrict__ 
 }
 
 // ---------------------------------------------------------------- launchers
-static long g_launches = 0;
-long k1_launch_count() { return g_launches; }
-void k1_count_launch(int n) { g_launches += n; }
+// (launch counter: bmu_api.cu, one atomic for all device contexts)
 
 size_t k1_cT_floats(long M, int D) { return (size_t)((M + K1_TC - 1) / K1_TC) * D * K1_TC; }
 size_t k1_xT_floats(long N, int D) { return (size_t)((N + K1_TS - 1) / K1_TS) * D * K1_TS * 2; }
@@ -572,19 +571,18 @@ cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   cb_prep_kernel<<<blocks, 256, 0, st>>>(d_codes, M, D, d_cT, d_cb_flags);
-  g_launches++;
+  k1_count_launch(1);
   return cudaGetLastError();
 }
 
 // CUDA events around each kernel of the last k1_search call, on the launching stream
-static cudaEvent_t g_evring[K_EV_RING][5];
-static cudaEvent_t *g_ev = g_evring[0];
-static long g_evcalls = 0;
+// (the ring lives in the device context of the calling thread, api_internal.h)
 
 cudaError_t k1_kernel_ms_history(int back, float out[4]) {
   for (int i = 0; i < 4; i++) out[i] = 0.0f;
-  if (back < 0 || back >= K_EV_RING || back >= g_evcalls) return cudaSuccess;
-  cudaEvent_t *ev = g_evring[(g_evcalls - 1 - back) % K_EV_RING];
+  DevCtx *c = ctx();
+  if (back < 0 || back >= K_EV_RING || back >= c->k1calls) return cudaSuccess;
+  cudaEvent_t *ev = c->k1ring[(c->k1calls - 1 - back) % K_EV_RING];
   cudaError_t e = cudaEventSynchronize(ev[4]);
   if (e != cudaSuccess) return e;
   for (int i = 0; i < 4; i++) {
@@ -597,18 +595,15 @@ cudaError_t k1_kernel_ms_history(int back, float out[4]) {
 cudaError_t k1_last_kernel_ms(float out[4]) { return k1_kernel_ms_history(0, out); }
 
 cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
-  static bool attr_set = false;
   cudaError_t e;
-  g_ev = g_evring[g_evcalls % K_EV_RING];
+  DevCtx *c = ctx();
+  cudaEvent_t *g_ev = c->k1ring[c->k1calls % K_EV_RING];
   if (!g_ev[0])
     for (int i = 0; i < 5; i++)
       if ((e = cudaEventCreate(&g_ev[i])) != cudaSuccess) return e;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(k1_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)FastSmem::BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // (function attributes are per device: set on every call, it is a cheap host-side table update)
+  e = cudaFuncSetAttribute(k1_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastSmem::BYTES);
+  if (e != cudaSuccess) return e;
   if (a.N <= 0) return cudaSuccess;
   const long ntiles = (a.N + K1_TS - 1) / K1_TS;
   e = cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), st);
@@ -618,14 +613,14 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   data_prep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a.data, a.mask, a.N, a.D, a.k, a.cb_flags,
                                                      a.xT, a.flags, a.listW, a.listS, a.counters,
                                                      a.idx, a.diff, a.nfound, want_tiles);
-  g_launches++;
+  k1_count_launch(1);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(g_ev[1], st);
   if (want_tiles) {
     int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
     k1_fast_kernel<<<grid, 288, FastSmem::BYTES, st>>>(a.xT, a.cT, a.N, a.M, a.D, a.flags, a.idx,
                                                        a.diff, a.nfound);
-    g_launches++;
+    k1_count_launch(1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   cudaEventRecord(g_ev[2], st);
@@ -633,7 +628,7 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
   cudaEventRecord(g_ev[3], st);
   if ((e = k1_run_seq_list(a, st)) != cudaSuccess) return e;
   cudaEventRecord(g_ev[4], st);
-  g_evcalls++;
+  c->k1calls++;
   return cudaSuccess;
 }
 
@@ -651,11 +646,11 @@ cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
     split = 16 * a.num_sms;
     k1_warp8_kernel<<<grid, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, split, a.idx, a.diff,
                                           a.nfound);
-    g_launches++;
+    k1_count_launch(1);
   }
   k1_warp_kernel<<<grid, 256, 0, st>>>(a.data, a.mask, a.cT, a.M, a.D, a.k, a.listW,
                                        a.counters + 0, split, a.idx, a.diff, a.nfound);
-  g_launches++;
+  k1_count_launch(1);
   return cudaGetLastError();
 }
 
@@ -663,7 +658,7 @@ cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
 cudaError_t k1_run_seq_list(const K1Args &a, cudaStream_t st) {
   k1_seq_kernel<<<a.num_sms * 2, 128, 0, st>>>(a.data, a.mask, a.codes, a.M, a.D, a.k, a.listS,
                                                a.counters + 1, a.idx, a.diff, a.nfound);
-  g_launches++;
+  k1_count_launch(1);
   return cudaGetLastError();
 }
 

@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "k2_filter.h"
+#include "api_internal.h"
 
 namespace bmu {
 
@@ -1161,7 +1162,8 @@ void k2_codebook_free(K2Codebook *c) {
   c->valid = 0;
 }
 
-static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_t st) {
+struct K2CbArgs { const float *codes; long M; int D; };
+static cudaError_t k2_build_codebook(K2Codebook *c, const K2CbArgs &a, cudaStream_t st) {
   const int Kp = k2_kp(a.D);
   const long nct = (a.M + K2_TN - 1) / K2_TN;
   const size_t need = (size_t)nct * K2_TN * Kp * 2;
@@ -1200,14 +1202,19 @@ static cudaError_t k2_build_codebook(K2Codebook *c, const K1Args &a, cudaStream_
 
 // CUDA events around the phases of the last K_EV_RING k2_search calls (a ring, so that a benchmark can
 // read every step of its timed region after the closing synchronisation instead of the last one only)
-static cudaEvent_t g_k2ring[K_EV_RING][5];
-static cudaEvent_t *g_k2ev = g_k2ring[0];
-static long g_k2calls = 0;
+// (the ring and the auxiliary stream live in the device context of the calling thread, api_internal.h)
+#define g_k2ev (ctx()->k2ring[ctx()->k2calls % K_EV_RING])
+#define g_k2aux (ctx()->k2aux)
+#define g_k2sub (ctx()->k2sub)
+#define g_k2join (ctx()->k2join)
+
+cudaError_t k2_prepare_codebook(K2Codebook *c, const float *d_codes, long M, int D, cudaStream_t st) {
+  K2CbArgs a = {d_codes, M, D};
+  return k2_build_codebook(c, a, st);
+}
 
 // Sub-batch pipeline shared by both GEMM kernels: the re-rank of sub-batch i runs on a second stream
 // beside the GEMM kernel of sub-batch i+1 (see k2_run_record).
-static cudaStream_t g_k2aux = nullptr;
-static cudaEvent_t g_k2sub[8], g_k2join = nullptr;
 
 static cudaError_t k2_pipeline_init() {
   cudaError_t e;
@@ -1357,8 +1364,9 @@ static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch
 
 cudaError_t k2_kernel_ms_history(int back, float out[4]) {
   out[0] = out[1] = out[2] = out[3] = 0.0f;
-  if (back < 0 || back >= K_EV_RING || back >= g_k2calls) return cudaSuccess;
-  cudaEvent_t *ev = g_k2ring[(g_k2calls - 1 - back) % K_EV_RING];
+  DevCtx *cx = ctx();
+  if (back < 0 || back >= K_EV_RING || back >= cx->k2calls) return cudaSuccess;
+  cudaEvent_t *ev = cx->k2ring[(cx->k2calls - 1 - back) % K_EV_RING];
   cudaError_t e = cudaEventSynchronize(ev[4]);
   if (e != cudaSuccess) return e;
   for (int i = 0; i < 4; i++)
@@ -1370,11 +1378,10 @@ cudaError_t k2_last_kernel_ms(float out[4]) { return k2_kernel_ms_history(0, out
 
 cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *scratch_bytes, cudaStream_t st) {
   cudaError_t e;
-  g_k2ev = g_k2ring[g_k2calls % K_EV_RING];
   if (!g_k2ev[0])
     for (int i = 0; i < 5; i++)
       if ((e = cudaEventCreate(&g_k2ev[i])) != cudaSuccess) return e;
-  if (!c->valid && (e = k2_build_codebook(c, a, st)) != cudaSuccess) return e;
+  if (!c->valid && (e = k2_prepare_codebook(c, a.codes, a.M, a.D, st)) != cudaSuccess) return e;
   const int Kp = c->Kp;
   // k == 1 and a code tile that fits a shared-memory stage: record kernel; else K streamed in slabs
   const bool record = a.k == 1 && Kp <= K2R_MAX_KP;
@@ -1417,7 +1424,7 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   // rows that failed the certificate + masked / tiny rows, then the non-finite rows
   if ((e = k1_run_lists(a, st)) != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[4], st);
-  g_k2calls++;
+  ctx()->k2calls++;
   return cudaSuccess;
 }
 

@@ -17,6 +17,8 @@ struct K2Codebook {
 };
 
 bool k2_eligible(int path, long M, int D, long N, int k, unsigned cb_flags);
+// centred / scaled fp16 operand image, statistics and the regrouped FP32 copy, queued on `st`
+cudaError_t k2_prepare_codebook(K2Codebook *c, const float *d_codes, long M, int D, cudaStream_t st);
 void k2_codebook_invalidate(K2Codebook *c);
 void k2_codebook_free(K2Codebook *c);
 // scratch: grow-only device buffer owned by the caller

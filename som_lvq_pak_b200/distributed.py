@@ -1,76 +1,95 @@
-"""Data-parallel batch search over the GPUs of one node.
+"""Process-per-GPU plumbing for the data-parallel batch search.
 
-One process per GPU (torch.distributed).  Samples are independent and the codebook is
-read-only, so the rows are cut into contiguous shards (which keeps the data order for the
-host replay), the codebook is replicated by one broadcast, every rank searches its shard
-with no data-path collective, and only the small statistics vector -- qerror sum, found
-count, BMU histogram, confusion counts -- is combined by ONE all-reduce.  torch.distributed
-is plumbing here; all compute is in libbmu_b200.so.  Online training does not shard
-(step t+1 reads the codebook of step t): replicas only."""
+The split itself -- contiguous row shards, replicated codebook, per-shard statistics, ONE grouped
+NCCL all-reduce of {double sum} + {int64 counts} -- lives in libbmu_b200.so (csrc/bmu_multi.cu):
+`bmu_multi_*` when one process drives all GPUs (the C hosts), `bmu_comm_*` when a launcher starts
+one process per GPU (torchrun; bench.py --gpus N).  What is left here is the launcher's part of
+the second mode: torch.distributed moves the 128-byte NCCL unique id from rank 0 to the other
+ranks (gloo in the CPU tests, NCCL on the GPUs), and `ShardedSearch` strings the library calls
+together on device buffers.  No arithmetic happens in this module.  Online training does not
+shard (step t+1 reads the codebook of step t): replicas only (see `vfind`)."""
+import ctypes as C
+
 import numpy as np
 
-TILE = 128
 
 
 def shard_bounds(n_rows, rank, world):
-    """contiguous, balanced row shard [lo, hi) of rank; boundaries on 128-row tiles"""
-    tiles = (n_rows + TILE - 1) // TILE
-    base, rem = divmod(tiles, world)
-    lo_t = rank * base + min(rank, rem)
-    hi_t = lo_t + base + (1 if rank < rem else 0)
-    return min(lo_t * TILE, n_rows), min(hi_t * TILE, n_rows)
+    """rows [lo, hi) of a rank: the library's own rule (bmu_multi_shard_bounds: contiguous,
+    balanced, cut at multiples of 512 rows), so that both modes shard identically"""
+    from . import _lib
+    lo, hi = C.c_long(), C.c_long()
+    _lib.load().bmu_multi_shard_bounds(n_rows, world, rank, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
 
 
-def pack_stats(qsum, n_found, hist=None, confusion=None):
-    """one float64 vector for the all-reduce; integer counts < 2^53 stay exact"""
-    parts = [np.array([qsum, n_found], np.float64)]
-    if hist is not None:
-        parts.append(np.asarray(hist, np.float64).ravel())
-    if confusion is not None:
-        parts.append(np.asarray(confusion, np.float64).ravel())
-    return np.concatenate(parts)
-
-
-def unpack_stats(vec, M=0, L=0):
-    vec = np.asarray(vec)
-    out = {"qsum": float(vec[0]), "n_found": int(round(vec[1]))}
-    off = 2
-    if M:
-        out["hist"] = np.rint(vec[off:off + M]).astype(np.int64)
-        off += M
-    if L:
-        out["confusion"] = np.rint(vec[off:off + L * L]).astype(np.int64).reshape(L, L)
-    return out
-
-
-def allreduce_stats(vec, group=None):
-    """sum the packed statistics over all ranks (NCCL on GPUs, gloo in the CPU tests)"""
-    import torch
-    import torch.distributed as dist
-    t = vec if isinstance(vec, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vec, np.float64))
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, group=group)
-    return t
-
-
-def gather_rows(local, n_rows, group=None):
-    """concatenate per-rank row results on rank 0 in shard (= data) order for the host replay"""
+def exchange_unique_id(make_id, group=None):
+    """rank 0 calls make_id() -> 128 bytes; every rank returns those bytes (one broadcast)"""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = [hi - lo for lo, hi in (shard_bounds(n_rows, r, world) for r in range(world))]
-    big = max(sizes)
-    # gather needs equal shapes: pad every shard to the largest one, trim on rank 0
-    padded = local
-    if local.shape[0] < big:
-        pad = torch.zeros((big - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
-                          device=local.device)
-        padded = torch.cat([local, pad])
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
-    dist.gather(padded.contiguous(), bufs, dst=0, group=group)
-    return torch.cat([b[:n] for b, n in zip(bufs, sizes)]) if rank == 0 else None
+        return bytes(make_id())
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    t = t.to(dev)
+    dist.broadcast(t, 0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def comm_init(group=None):
+    """bind this rank's bmu_init device to a library-owned NCCL communicator spanning the ranks of
+    the torch.distributed group; returns (rank, world)"""
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0, 1
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def make_id():
+        buf = (C.c_ubyte * 128)()
+        _lib.check(lib.bmu_comm_unique_id(buf))
+        return bytes(buf)
+    uid = exchange_unique_id(make_id, group)
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+    _lib.check(lib.bmu_comm_init_rank(world, rank, buf))
+    return rank, world
+
+
+class ShardedSearch:
+    """One rank's part of a sharded search on DEVICE buffers (torch tensors are only the allocator):
+    search the local rows, reduce the shard's statistics on the device, combine them over the ranks
+    with the library's grouped NCCL all-reduce.  `stats` is ONE int64 buffer: [0] the bits of the
+    double sum of sqrt(diff), [1] n_found, [2:2+M] BMU hits per code vector."""
+
+    def __init__(self, cb_handle, M, rows, k, device):
+        import torch
+        self.cb, self.M, self.rows, self.k = cb_handle, M, rows, k
+        self.idx = torch.empty((rows, k), dtype=torch.int32, device=device)
+        self.diff = torch.empty((rows, k), dtype=torch.float32, device=device)
+        self.nf = torch.empty(rows, dtype=torch.int32, device=device)
+        self.stats = torch.zeros(2 + M, dtype=torch.int64, device=device)
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+
+    def step(self, d_data, allreduce=True):
+        from . import _lib
+        lib = _lib.load()
+        p = self.stats.data_ptr()
+        self.stats.zero_()
+        _lib.check(lib.bmu_search_dev(self.cb, d_data, None, self.rows, self.k, self.idx.data_ptr(),
+                                      self.diff.data_ptr(), self.nf.data_ptr(), self.stream))
+        _lib.check(lib.bmu_search_stats_dev(self.idx.data_ptr(), self.diff.data_ptr(), self.nf.data_ptr(), self.rows,
+                                            self.k, self.M, p, p + 8, p + 16, None, None, 0, None, self.stream))
+        if allreduce:
+            _lib.check(lib.bmu_comm_allreduce_stats_dev(p, 1, p + 8, 1 + self.M, self.stream))
+
+    def totals(self):
+        """(sum of sqrt(diff) as float, n_found, hist) -- synchronises"""
+        h = self.stats.cpu().numpy()
+        return float(h[:1].view(np.float64)[0]), int(h[1]), h[2:]
 
 
 # ---------------------------------------------------------------------------- vfind

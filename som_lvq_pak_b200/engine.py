@@ -113,6 +113,86 @@ class Codebook:
                                               d_nfound, stream))
 
 
+class MultiCodebook:
+    """The codebook replicated over every shard of the data-parallel search (bmu_multi_*,
+    SURVEY.md 8e): rows are split into contiguous slices, one per GPU (or per logical shard),
+    per-row results land in the caller's arrays in data order, statistics are combined by one
+    grouped NCCL all-reduce."""
+
+    def __init__(self, codes, nshards=0, code_label=None):
+        lib = _lib.load()
+        _lib.check(lib.bmu_multi_init(nshards))
+        codes = _f32(codes)
+        self.M, self.D = codes.shape
+        self._h = lib.bmu_mcodebook_create(_ptr(codes), self.M, self.D)
+        if not self._h:
+            raise RuntimeError("bmu_mcodebook_create: " + lib.bmu_last_error().decode())
+        if code_label is not None:
+            cl = np.ascontiguousarray(code_label, np.int32)
+            _lib.check(lib.bmu_mcodebook_set_labels(self._h, _ptr(cl)))
+
+    @staticmethod
+    def shards():
+        return _lib.load().bmu_multi_shards()
+
+    def update(self, codes):
+        codes = _f32(codes)
+        _lib.check(_lib.load().bmu_mcodebook_update(self._h, _ptr(codes)))
+
+    def find_winners(self, data, knn=1, mask=None, stats=False, hist=False, sample_label=None, n_labels=0):
+        """(idx, diff, nfound[, stats dict]) -- stats: sum_sqrt (double), n_found, hist[M],
+        confusion[n_labels, n_labels] totals over all shards"""
+        data = _f32(data)
+        mask = _opt(mask, np.uint8)
+        N = data.shape[0]
+        idx = np.empty((N, knn), np.int32)
+        diff = np.empty((N, knn), np.float32)
+        nf = np.empty(N, np.int32)
+        st = None
+        keep = []
+        if stats:
+            st = _lib.Stats()
+            if hist:
+                h = np.zeros(self.M, np.int64)
+                keep.append(h)
+                st.hist = h.ctypes.data
+            if sample_label is not None:
+                sl = np.ascontiguousarray(sample_label, np.int32)
+                cf = np.zeros((n_labels, n_labels), np.int64)
+                keep += [sl, cf]
+                st.sample_label = sl.ctypes.data
+                st.confusion = cf.ctypes.data
+                st.n_labels = n_labels
+        _lib.check(_lib.load().bmu_multi_search(self._h, _ptr(data), _ptr(mask), N, knn, _ptr(idx), _ptr(diff),
+                                                _ptr(nf), C.byref(st) if st is not None else None))
+        if not stats:
+            return idx, diff, nf
+        out = {"sum_sqrt": float(st.sum_sqrt), "n_found": int(st.n_found)}
+        if hist:
+            out["hist"] = keep[0]
+        if sample_label is not None:
+            out["confusion"] = keep[-1]
+        return idx, diff, nf, out
+
+    def close(self):
+        if self._h:
+            _lib.load().bmu_mcodebook_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def search_stats_dev(d_idx, d_diff, d_nfound, N, k, M, d_sum, d_nfound_total, d_hist=None, d_sample_label=None,
+                     d_code_label=None, n_labels=0, d_confusion=None, stream=None):
+    """bmu_search_stats_dev: per-shard sums of a finished search, device addresses in and out"""
+    _lib.check(_lib.load().bmu_search_stats_dev(d_idx, d_diff, d_nfound, N, k, M, d_sum, d_nfound_total, d_hist,
+                                                d_sample_label, d_code_label, n_labels, d_confusion, stream))
+
+
 def find_winner_euc(codes, data, mask=None):
     cb = Codebook(codes)
     try:

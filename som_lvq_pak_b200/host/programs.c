@@ -16,8 +16,8 @@
  *   vfind trials                vfind.c:247-306       bmu_randinit_codes + 2 x bmu_som_train + qerror, per trial
  *   pick_inside_codes           lvq_rout.c:151-211    bmu_search (k) of the data set against itself (eveninit / propinit)
  *
- * Not carried over (outside SURVEY.md section 8): -buffer (files are loaded whole), -selfuncs,
- * background (forked) snapshots, compressed / piped file names.
+ * Not carried over (outside SURVEY.md section 8): -selfuncs, background (forked) snapshots.
+ * Compressed (.gz/.Z) and piped (|cmd) file names ARE handled by the file layer (entries.c).
  */
 #include "somhost.h"
 
@@ -74,8 +74,11 @@ struct winners {
   float *diff;
 };
 static void winners_free(struct winners *w) { free(w->idx); free(w->nfound); free(w->diff); }
+/* One funnel for every program's winner loop (find_qerror som_rout.c:710-721, accuracy.c:82, classify.c:66,
+ * knntest.c:98, vcal.c:109, visual.c:113, cmatr.c:84, elimin.c:81, setlabel.c:73): the rows are sharded over
+ * every GPU the process can see ($SOMLVQ_GPUS limits them), results come back in data order. */
 static int find_winners(const struct pak_entries *codes, const struct pak_entries *data, int knn, struct winners *w) {
-  bmu_codebook *cb;
+  bmu_mcodebook *cb;
   int rc;
   size_t n = (size_t)(data->n > 0 ? data->n : 1);
   w->idx = (int32_t *)malloc(sizeof(int32_t) * n * knn);
@@ -83,11 +86,19 @@ static int find_winners(const struct pak_entries *codes, const struct pak_entrie
   w->nfound = (int32_t *)malloc(sizeof(int32_t) * n);
   if (!w->idx || !w->diff || !w->nfound) { fprintf(stderr, "out of memory\n"); return 1; }
   if (data->n == 0) return 0;
-  cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
-  if (!cb) return engine_failed("bmu_codebook_create");
-  rc = bmu_search(cb, data->points, data->mask, data->n, knn, w->idx, w->diff, w->nfound);
-  bmu_codebook_destroy(cb);
-  return rc ? engine_failed("bmu_search") : 0;
+  {
+    /* small searches (the demo recipes) stay on one GPU: opening every device and a communicator costs
+     * more than they take; $SOMLVQ_GPUS overrides */
+    const char *env = getenv("SOMLVQ_GPUS");
+    const double work = (double)data->n * (double)codes->n * (double)codes->dim;
+    const int shards = (env && atoi(env) > 0) ? atoi(env) : (work < 2e10 ? 1 : 0);
+    if (bmu_multi_init(shards)) return engine_failed("bmu_multi_init");
+  }
+  cb = bmu_mcodebook_create(codes->points, codes->n, codes->dim);
+  if (!cb) return engine_failed("bmu_mcodebook_create");
+  rc = bmu_multi_search(cb, data->points, data->mask, data->n, knn, w->idx, w->diff, w->nfound, NULL);
+  bmu_mcodebook_destroy(cb);
+  return rc ? engine_failed("bmu_multi_search") : 0;
 }
 
 static int open_pair(int argc, char **argv, int data_labels_needed, int code_labels_needed, int skip_empty,

@@ -1,7 +1,8 @@
-"""CPU, world_size 2 over gloo: the host-side logic of the sharded batch search -- shard
-bounds, the packed statistics all-reduce and the in-order gather for the host replay.
-The per-shard winners come from the oracle here (no GPU); on the GPU box the same functions
-run over NCCL inside bench.py."""
+"""CPU, world_size 2 over gloo: the launcher-side logic of the sharded batch search in its
+process-per-GPU mode -- the library's shard bounds, the broadcast of the 128-byte communicator id,
+per-shard results landing in data order, int64 counts summed exactly.  The per-shard winners come
+from the oracle here (no GPU); on the GPU box the same split runs inside libbmu_b200.so
+(tests/test_multi_gpu.py) and the id exchange feeds bmu_comm_init_rank (bench.py --gpus N)."""
 import os
 import sys
 
@@ -16,14 +17,16 @@ from conftest import ROOT
 
 def test_shard_bounds_cover_rows():
     from som_lvq_pak_b200.distributed import shard_bounds
-    for n in (0, 1, 127, 128, 129, 1000, 10_000_000, 1962):
+    for n in (0, 1, 127, 128, 129, 1000, 10_000_000, 1962, 1_000_000, 40_000):
         for world in (1, 2, 3, 4, 8):
             b = [shard_bounds(n, r, world) for r in range(world)]
             assert b[0][0] == 0 and b[-1][1] == n
             for (l0, h0), (l1, h1) in zip(b, b[1:]):
                 assert h0 == l1 and l0 <= h0
             sizes = [h - l for l, h in b]
-            assert max(sizes) - min(sizes) <= 256
+            assert max(sizes) - min(sizes) <= 1024
+            if n >= 4096 * world:
+                assert all(l % 512 == 0 for l, _ in b)          # whole CTA passes
 
 
 def _worker(rank, world, port, tmp):
@@ -35,32 +38,43 @@ def _worker(rank, world, port, tmp):
     from oracle.pyoracle import Oracle
     from som_lvq_pak_b200 import distributed as D
     o = Oracle()
+    # the communicator id: made on rank 0 only, identical bytes on every rank afterwards
+    uid = D.exchange_unique_id(lambda: bytes(range(128)) if rank == 0 else b"\0" * 128)
+    assert uid == bytes(range(128))
     rng = np.random.default_rng(5)
     M, dim, N, L = 40, 6, 1000, 4
     codes = rng.random((M, dim), dtype=np.float32)
     data = rng.random((N, dim), dtype=np.float32)
     cl = rng.integers(0, L, M)
     dl = rng.integers(0, L, N)
-    # "broadcast" of the codebook: rank 0's copy wins
     ct = torch.from_numpy(codes.copy() if rank == 0 else np.zeros_like(codes))
-    dist.broadcast(ct, 0)
+    dist.broadcast(ct, 0)                                  # codebook replicated from rank 0
     lo, hi = D.shard_bounds(N, rank, world)
     idx, diff, ret = o.search(ct.numpy(), data[lo:hi], 1)
-    hist = np.bincount(idx[:, 0], minlength=M)
-    conf = np.zeros((L, L), np.int64)
-    np.add.at(conf, (dl[lo:hi], cl[idx[:, 0]]), 1)
-    vec = D.pack_stats(np.sqrt(diff[:, 0].astype(np.float64)).sum(), len(idx), hist, conf)
-    tot = D.unpack_stats(D.allreduce_stats(vec).numpy(), M, L)
-    allidx = D.gather_rows(torch.from_numpy(idx), N)
+    # {double sum} + {int64 n_found, hist, confusion}: the two vectors of the grouped all-reduce
+    counts = np.zeros(1 + M + L * L, np.int64)
+    counts[0] = len(idx)
+    counts[1:1 + M] = np.bincount(idx[:, 0], minlength=M)
+    np.add.at(counts[1 + M:].reshape(L, L), (dl[lo:hi], cl[idx[:, 0]]), 1)
+    tsum = torch.tensor([np.sqrt(diff[:, 0].astype(np.float64)).sum()], dtype=torch.float64)
+    tcnt = torch.from_numpy(counts)
+    dist.all_reduce(tsum)
+    dist.all_reduce(tcnt)
+    # per-row results: every rank owns rows [lo, hi) of the caller's arrays (no gather in the product;
+    # the test collects them to compare with the unsharded search)
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, hi, idx))
     if rank == 0:
         gidx, gdiff, _ = o.search(codes, data, 1)
-        assert tot["n_found"] == N
-        assert np.array_equal(tot["hist"], np.bincount(gidx[:, 0], minlength=M))
+        whole = np.concatenate([p[2] for p in sorted(parts, key=lambda t: t[0])])
+        assert np.array_equal(whole, gidx)
+        tot = tcnt.numpy()
+        assert tot[0] == N
+        assert np.array_equal(tot[1:1 + M], np.bincount(gidx[:, 0], minlength=M))
         gconf = np.zeros((L, L), np.int64)
         np.add.at(gconf, (dl, cl[gidx[:, 0]]), 1)
-        assert np.array_equal(tot["confusion"], gconf)
-        assert abs(tot["qsum"] - np.sqrt(gdiff[:, 0].astype(np.float64)).sum()) < 1e-9
-        assert np.array_equal(allidx.numpy(), gidx)
+        assert np.array_equal(tot[1 + M:].reshape(L, L), gconf)
+        assert abs(float(tsum[0]) - np.sqrt(gdiff[:, 0].astype(np.float64)).sum()) < 1e-9
         open(os.path.join(tmp, "ok"), "w").write("ok")
     dist.barrier()
     dist.destroy_process_group()
