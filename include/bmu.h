@@ -191,7 +191,13 @@ int bmu_set_copy_threads(int n);
  *   talp[t]    learning rate of step t   (lvq_pak.c:903-921, som_rout.c:617-624)
  *   trad[t]    neighbourhood radius      (som_rout.c:615)
  * fixed_xy: NULL or N x 2 int16 (x,y) with x < 0 = no fixed point (som_rout.c:628-632).
- * codes (M x D, M = xdim*ydim) is updated in place. */
+ * codes (M x D, M = xdim*ydim) is updated in place.
+ * Two documented deviations from the reference, both outside what its own loaders can produce:
+ * (1) masks travel to the device as a NaN sentinel inside the data, so once ANY component of the
+ * data set is masked, a genuine NaN in an unmasked component is treated as masked too (the
+ * reference would propagate it into the codebook); (2) a step whose sample has no winner (every
+ * component masked) is skipped, as som_rout.c:635-640 does -- data whose distance is NaN for every
+ * unit (index -1 in the reference, which then adapts around unit -1) is skipped as well. */
 int bmu_som_train(float *codes, long M, int D, int xdim, int ydim, int topol, int neigh,
                   const float *data, const unsigned char *mask, long N,
                   const int16_t *fixed_xy, const int32_t *sample, const float *talp,

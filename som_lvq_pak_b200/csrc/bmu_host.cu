@@ -3,16 +3,23 @@
 //
 // The reference's hosts hold their vectors in plain calloc'd memory (datafile.c:472), so the caller's
 // buffers are normally PAGEABLE.  A cudaMemcpyAsync from pageable memory is staged by the driver through
-// one small pinned buffer by one thread and never overlaps anything.  Here the staging is ours:
+// one small pinned buffer by one thread (11 GB/s measured) and never overlaps anything.  Here the
+// staging is ours:
 //
-//   caller rows --(T copy threads, memcpy)--> pinned ring slot --(DMA, copy stream)--> device slot
-//        --> search kernels (+ statistics) on the compute stream --> results --(DMA, out stream)-->
-//        pinned ring slot --(memcpy)--> caller's idx / diff / nfound
+//   caller rows --(T copy threads)--> small pinned ring (pieces of 8 MB) --(DMA, copy stream)--> device
+//        chunk slot --> search kernels (+ statistics) on the compute stream --> results --(DMA, out
+//        stream)--> pinned --(copy threads)--> caller's idx / diff / nfound
 //
-// with BMU_NSLOT chunks in flight, so that the memcpy of chunk c+1, the H2D copy of chunk c, the
-// kernels of chunk c-1 and the D2H copy of chunk c-2 all run at the same time.  Buffers that are
-// already page-locked (bmu_host_alloc, bmu_host_register, cudaHostAlloc, torch pin_memory) are
-// recognised with cudaPointerGetAttributes and copied by DMA directly, without the staging hop.
+// with BMU_NSLOT device chunks in flight, so that the staging of chunk c+1, the H2D copy of chunk c, the
+// kernels of chunk c-1 and the D2H copy of chunk c-2 all run at the same time.  The pinned ring is kept
+// SMALL on purpose (4 x 8 MB): written with ordinary stores it stays in the CPU's last-level cache, the
+// DMA engine reads the pieces from there, and DRAM only sees the one read of the caller's rows.  Measured
+// on the B200 box (tools/ubench/host_pipe.cu, profiles/r02_host_copy_ubench.txt): 54 GB/s end to end with
+// 8 threads against 55.3 GB/s for the DMA alone from pinned memory; a large ring written with
+// non-temporal stores reached 52 GB/s, glibc memcpy into a large ring 37-47 GB/s, cudaHostRegister of the
+// caller's pages on the fly 7-10 GB/s.  Buffers that are already page-locked (bmu_host_alloc,
+// bmu_host_register, cudaHostAlloc, torch pin_memory) are recognised with cudaPointerGetAttributes and
+// read by the DMA engine directly.
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,82 +33,9 @@
 
 #include "api_internal.h"
 #include "common.cuh"
+#include "copy_pool.h"
 
 namespace bmu {
-
-// ------------------------------------------------------------------ copy threads
-// A small pool of threads that split one memcpy into contiguous slices (a single thread moves
-// 6-12 GB/s; PCIe Gen5 x16 takes 55 GB/s).
-class CopyPool {
- public:
-  explicit CopyPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads) {
-    for (int i = 1; i < n_; i++) workers_.emplace_back([this, i] { loop(i); });
-  }
-  ~CopyPool() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      stop_ = true;
-      gen_++;
-    }
-    cv_.notify_all();
-    for (auto &t : workers_) t.join();
-  }
-  int threads() const { return n_; }
-  // blocking: returns when every byte has been copied
-  void copy(void *dst, const void *src, size_t bytes) {
-    if (bytes == 0) return;
-    const size_t kMinSlice = 1u << 20;
-    int parts = (int)((bytes + kMinSlice - 1) / kMinSlice);
-    if (parts > n_) parts = n_;
-    if (parts <= 1) { memcpy(dst, src, bytes); return; }
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; parts_ = parts;
-      pending_ = parts - 1;
-      gen_++;
-    }
-    cv_.notify_all();
-    slice(0);
-    std::unique_lock<std::mutex> lk(m_);
-    done_.wait(lk, [this] { return pending_ == 0; });
-  }
-
- private:
-  void slice(int i) {
-    // slices on 4 KiB boundaries so that two threads never share a page of the destination
-    const size_t per = ((bytes_ + parts_ - 1) / parts_ + 4095) & ~(size_t)4095;
-    const size_t lo = per * i, hi = lo + per < bytes_ ? lo + per : bytes_;
-    if (lo < hi) memcpy(dst_ + lo, src_ + lo, hi - lo);
-  }
-  void loop(int i) {
-    unsigned long seen = 0;
-    for (;;) {
-      int parts;
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-        parts = parts_;
-      }
-      if (i < parts) {
-        slice(i);
-        std::lock_guard<std::mutex> lk(m_);
-        if (--pending_ == 0) done_.notify_one();
-      }
-    }
-  }
-  int n_;
-  std::vector<std::thread> workers_;
-  std::mutex m_;
-  std::condition_variable cv_, done_;
-  unsigned long gen_ = 0;
-  bool stop_ = false;
-  char *dst_ = nullptr;
-  const char *src_ = nullptr;
-  size_t bytes_ = 0;
-  int parts_ = 0, pending_ = 0;
-};
 
 // ------------------------------------------------------------------ pinned ring
 struct Pinned {
@@ -127,8 +61,15 @@ struct Pinned {
   }
 };
 
+#define RING_PIECES 4
+#define RING_PIECE_BYTES ((size_t)8 << 20)
+
 struct HostRing {
-  Pinned in[BMU_NSLOT], mask[BMU_NSLOT], idx[BMU_NSLOT], diff[BMU_NSLOT], nf[BMU_NSLOT], lab[BMU_NSLOT];
+  Pinned pieces;                                   // RING_PIECES x RING_PIECE_BYTES, H2D staging
+  cudaEvent_t piece_done[RING_PIECES] = {};        // the DMA that read piece i has finished
+  bool piece_used[RING_PIECES] = {};
+  unsigned long next_piece = 0;
+  Pinned idx[BMU_NSLOT], diff[BMU_NSLOT], nf[BMU_NSLOT];   // D2H landing buffers per device chunk slot
   CopyPool *pool = nullptr;
 };
 
@@ -167,10 +108,10 @@ static HostRing *ring_of(DevCtx *c, int threads_hint) {
 
 void host_ring_free(DevCtx *c) {
   if (!c->ring) return;
-  for (int b = 0; b < BMU_NSLOT; b++) {
-    c->ring->in[b].release(); c->ring->mask[b].release(); c->ring->idx[b].release();
-    c->ring->diff[b].release(); c->ring->nf[b].release(); c->ring->lab[b].release();
-  }
+  c->ring->pieces.release();
+  for (int i = 0; i < RING_PIECES; i++)
+    if (c->ring->piece_done[i]) cudaEventDestroy(c->ring->piece_done[i]);
+  for (int b = 0; b < BMU_NSLOT; b++) { c->ring->idx[b].release(); c->ring->diff[b].release(); c->ring->nf[b].release(); }
   delete c->ring->pool;
   delete c->ring;
   c->ring = nullptr;
@@ -234,6 +175,33 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
   const bool st_out = !tiny && !(is_pinned(idx) && is_pinned(diff) && is_pinned(nfound));
   const bool st_lab = !tiny && want_conf && !is_pinned(hs->sample_label);
   HostRing *ring = (st_in || st_mask || st_out || st_lab) ? ring_of(c, 0) : nullptr;
+  if (ring && (st_in || st_mask || st_lab)) {
+    if ((rc = ring->pieces.ensure(RING_PIECES * RING_PIECE_BYTES))) return rc;
+    for (int i = 0; i < RING_PIECES; i++)
+      if (!ring->piece_done[i]) CK(cudaEventCreateWithFlags(&ring->piece_done[i], cudaEventDisableTiming));
+  }
+  struct PoolSession {                       // the copy threads spin for the duration of this call only
+    CopyPool *p;
+    explicit PoolSession(CopyPool *q) : p(q) { if (p) p->begin(); }
+    ~PoolSession() { if (p) p->end(); }
+  } session(ring ? ring->pool : nullptr);
+  // host -> device on the copy stream: page-locked sources are read by the DMA engine as they are,
+  // pageable ones go through the ring piece by piece (copy threads fill piece i+1 while the DMA reads piece i)
+  auto h2d = [&](void *dst, const void *src, size_t bytes, bool staged) -> cudaError_t {
+    if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy);
+    for (size_t off = 0; off < bytes; off += RING_PIECE_BYTES) {
+      const size_t len = bytes - off < RING_PIECE_BYTES ? bytes - off : RING_PIECE_BYTES;
+      const int r = (int)(ring->next_piece++ % RING_PIECES);
+      char *piece = (char *)ring->pieces.p + (size_t)r * RING_PIECE_BYTES;
+      cudaError_t e;
+      if (ring->piece_used[r] && (e = cudaEventSynchronize(ring->piece_done[r])) != cudaSuccess) return e;
+      ring->pool->copy(piece, (const char *)src + off, len, COPY_CACHED);
+      if ((e = cudaMemcpyAsync((char *)dst + off, piece, len, cudaMemcpyHostToDevice, c->copy)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(ring->piece_done[r], c->copy)) != cudaSuccess) return e;
+      ring->piece_used[r] = true;
+    }
+    return cudaSuccess;
+  };
   const int nslot = (int)(nchunks < BMU_NSLOT ? nchunks : BMU_NSLOT);
   for (int b = 0; b < nslot; b++) {
     if ((rc = c->stage_in[b].ensure((size_t)chunk * D * 4))) return rc;
@@ -242,9 +210,6 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
     if ((rc = c->stage_diff[b].ensure((size_t)chunk * k * 4))) return rc;
     if ((rc = c->stage_nf[b].ensure((size_t)chunk * 4))) return rc;
     if (want_conf && (rc = c->stage_lab[b].ensure((size_t)chunk * 4))) return rc;
-    if (st_in && (rc = ring->in[b].ensure((size_t)chunk * D * 4))) return rc;
-    if (st_mask && (rc = ring->mask[b].ensure((size_t)chunk * D))) return rc;
-    if (st_lab && (rc = ring->lab[b].ensure((size_t)chunk * 4))) return rc;
     if (st_out) {
       if ((rc = ring->idx[b].ensure((size_t)chunk * k * 4))) return rc;
       if ((rc = ring->diff[b].ensure((size_t)chunk * k * 4))) return rc;
@@ -262,9 +227,9 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
     cudaError_t e = cudaEventSynchronize(c->ev_out[b]);
     if (e != cudaSuccess || !st_out) return e;
     const long n0 = cc * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
-    ring->pool->copy(idx + n0 * (long)k, ring->idx[b].p, (size_t)n * k * 4);
-    ring->pool->copy(diff + n0 * (long)k, ring->diff[b].p, (size_t)n * k * 4);
-    ring->pool->copy(nfound + n0, ring->nf[b].p, (size_t)n * 4);
+    ring->pool->copy(idx + n0 * (long)k, ring->idx[b].p, (size_t)n * k * 4, COPY_CACHED);
+    ring->pool->copy(diff + n0 * (long)k, ring->diff[b].p, (size_t)n * k * 4, COPY_CACHED);
+    ring->pool->copy(nfound + n0, ring->nf[b].p, (size_t)n * 4, COPY_CACHED);
     return cudaSuccess;
   };
 
@@ -275,22 +240,16 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
     const int b = (int)(cc % BMU_NSLOT);
     const long n0 = cc * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
     if (cc >= BMU_NSLOT) {
-      // slot b comes free: its results (chunk cc - NSLOT) go to the caller, its pinned input was consumed
+      // slot b comes free: its results (chunk cc - NSLOT) go to the caller
       if ((e = drain(cc - BMU_NSLOT)) != cudaSuccess) break;
       drained = cc - BMU_NSLOT + 1;
-      if ((e = cudaEventSynchronize(c->ev_in[b])) != cudaSuccess) break;
       if ((e = cudaStreamWaitEvent(c->copy, c->ev_work[b], 0)) != cudaSuccess) break;   // device slot searched
     }
     const void *src = data + n0 * (long)D, *msrc = mask ? mask + n0 * (long)D : nullptr;
     const void *lsrc = want_conf ? hs->sample_label + n0 : nullptr;
-    if (st_in) { ring->pool->copy(ring->in[b].p, src, (size_t)n * D * 4); src = ring->in[b].p; }
-    if (st_mask) { ring->pool->copy(ring->mask[b].p, msrc, (size_t)n * D); msrc = ring->mask[b].p; }
-    if (st_lab) { ring->pool->copy(ring->lab[b].p, lsrc, (size_t)n * 4); lsrc = ring->lab[b].p; }
-    e = cudaMemcpyAsync(c->stage_in[b].p, src, (size_t)n * D * 4, cudaMemcpyHostToDevice, c->copy);
-    if (e == cudaSuccess && mask)
-      e = cudaMemcpyAsync(c->stage_mask[b].p, msrc, (size_t)n * D, cudaMemcpyHostToDevice, c->copy);
-    if (e == cudaSuccess && want_conf)
-      e = cudaMemcpyAsync(c->stage_lab[b].p, lsrc, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy);
+    e = h2d(c->stage_in[b].p, src, (size_t)n * D * 4, st_in);
+    if (e == cudaSuccess && mask) e = h2d(c->stage_mask[b].p, msrc, (size_t)n * D, st_mask);
+    if (e == cudaSuccess && want_conf) e = h2d(c->stage_lab[b].p, lsrc, (size_t)n * 4, st_lab);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_in[b], c->copy);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->compute, c->ev_in[b], 0);
     if (e == cudaSuccess && cc >= BMU_NSLOT) e = cudaStreamWaitEvent(c->compute, c->ev_out[b], 0);

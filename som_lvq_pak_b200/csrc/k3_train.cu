@@ -682,6 +682,9 @@ static size_t k3_fixed_smem(int D, int U) {
 K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
   K3Plan best{};
   double best_cost = 1e300;
+  // the grid exchange polls at most K3_MAX_GRID slots (NQ = 5 rounds of 32 lanes): a part with more SMs
+  // than that simply leaves the extra ones idle (B200: 148)
+  if (num_sms > K3_MAX_GRID) num_sms = K3_MAX_GRID;
   for (int G = 1; G <= num_sms; G = (G < num_sms && G * 2 > num_sms) ? num_sms : G * 2) {
     int U = (int)((M + G - 1) / G);
     int Us = (U + 1) & ~1;                 // even: unit pairs stay 8-byte aligned
@@ -703,6 +706,7 @@ K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
 }
 
 cudaError_t k3_launch(const K3Params &p, const K3Plan &plan, bool has_mask, cudaStream_t st) {
+  if (plan.grid < 1 || plan.grid > K3_MAX_GRID) return cudaErrorInvalidConfiguration;   // winners of CTAs >= 160 would never be read
   const bool top2 = p.mode == K3_LVQ2 || p.mode == K3_LVQ3;
   void *fn;
   {

@@ -8,6 +8,7 @@ namespace bmu {
 enum K3Mode { K3_SOM_BUBBLE = 0, K3_SOM_GAUSSIAN = 1, K3_LVQ1 = 2, K3_LVQ2 = 3, K3_LVQ3 = 4, K3_OLVQ1 = 5 };
 
 #define K3_THREADS 256
+#define K3_MAX_GRID 160              // CTA slots the grid exchange polls (5 x 32 lanes)
 #define K3_MASK_SENTINEL 0x7fc00b00u   // quiet NaN payload that marks a masked component
 
 struct K3Params {
