@@ -46,8 +46,14 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 int ensure_init() {
-  if (ctx()->dev >= 0) return BMU_OK;
-  return bmu_init(0);
+  DevCtx *c = ctx();
+  if (c->dev < 0) return bmu_init(0);
+  // the calling thread may have been left on another device (the multi-GPU entry points, the host's own
+  // CUDA code): the streams and buffers of this context belong to c->dev
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != c->dev)
+    if (cudaSetDevice(c->dev) != cudaSuccess) return fail(BMU_ERR_CUDA, "cudaSetDevice(%d) failed", c->dev);
+  return BMU_OK;
 }
 int Scratch::ensure(size_t need) {
   if (need <= bytes) return BMU_OK;

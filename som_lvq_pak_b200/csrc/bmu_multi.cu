@@ -178,12 +178,15 @@ int bmu_multi_devices(void) { return g_multi.ndev; }
 
 void bmu_mcodebook_destroy(bmu_mcodebook *mc) {
   if (!mc) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
   for (int s = 0; s < BMU_MAX_GPUS; s++)
     if (mc->rep[s]) {
       bind_ctx(mc->rep[s]->owner);
       bmu_codebook_destroy(mc->rep[s]);
     }
   bind_ctx(nullptr);
+  cudaSetDevice(cur);
   free(mc);
 }
 

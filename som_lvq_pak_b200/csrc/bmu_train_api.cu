@@ -93,6 +93,7 @@ bmu_trainer *bmu_trainer_create(const float *codes, long M, int D, const float *
 
 int bmu_trainer_set_som(bmu_trainer *t, int xdim, int ydim, int topol, int neigh,
                         const int16_t *fixed_xy) {
+  if (int rc0 = ensure_init()) return rc0;
   if (!t) return fail(BMU_ERR_ARG, "NULL trainer");
   if ((long)xdim * ydim != t->M) return fail(BMU_ERR_ARG, "xdim*ydim=%ld != M=%ld", (long)xdim * ydim, t->M);
   if (topol != BMU_TOPOL_HEXA && topol != BMU_TOPOL_RECT) return fail(BMU_ERR_ARG, "bad topology %d", topol);
@@ -111,6 +112,7 @@ int bmu_trainer_set_som(bmu_trainer *t, int xdim, int ydim, int topol, int neigh
 int bmu_trainer_set_lvq(bmu_trainer *t, int algo, const int32_t *code_label,
                         const int32_t *data_label, float win_thr, float epsilon,
                         float alpha_cap, const float *unit_alpha) {
+  if (int rc0 = ensure_init()) return rc0;
   if (!t || !code_label || !data_label) return fail(BMU_ERR_ARG, "NULL argument");
   switch (algo) {
     case BMU_LVQ1: t->mode = K3_LVQ1; break;
@@ -132,6 +134,7 @@ int bmu_trainer_set_lvq(bmu_trainer *t, int algo, const int32_t *code_label,
 
 int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
                       const float *trad, long nsteps) {
+  if (int rc0 = ensure_init()) return rc0;
   if (!t || !sample) return fail(BMU_ERR_ARG, "NULL argument");
   if (t->mode < 0) return fail(BMU_ERR_ARG, "trainer mode not set (bmu_trainer_set_som/_lvq)");
   if (nsteps <= 0) return BMU_OK;
@@ -175,6 +178,7 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
 }
 
 int bmu_trainer_get_codes(bmu_trainer *t, float *codes) {
+  if (int rc0 = ensure_init()) return rc0;
   if (!t || !codes) return fail(BMU_ERR_ARG, "NULL argument");
   CK(cudaMemcpyAsync(codes, t->d_codes, (size_t)t->M * t->D * 4, cudaMemcpyDeviceToHost, g_compute));
   CK(cudaStreamSynchronize(g_compute));
@@ -182,6 +186,7 @@ int bmu_trainer_get_codes(bmu_trainer *t, float *codes) {
 }
 
 int bmu_trainer_get_unit_alpha(bmu_trainer *t, float *unit_alpha) {
+  if (int rc0 = ensure_init()) return rc0;
   if (!t || !unit_alpha || !t->d_unit_alpha) return fail(BMU_ERR_ARG, "no unit_alpha state");
   CK(cudaMemcpyAsync(unit_alpha, t->d_unit_alpha, (size_t)t->M * 4, cudaMemcpyDeviceToHost, g_compute));
   CK(cudaStreamSynchronize(g_compute));
