@@ -417,74 +417,79 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
   }
 }
 
-// ---------------------------------------------------------------- K1-warp8 (k == 1, no masks)
-// Short lists -- the K2 certificate failures -- are bound by L2 bandwidth when every row streams
-// the whole codebook by itself.  Here a warp takes EIGHT listed rows against each 128-code tile
-// (8 rows x 4 codes per lane in registers), which divides the codebook traffic by eight.
-__global__ void __launch_bounds__(256)
-k1_warp8_kernel(const float *__restrict__ data, const float *__restrict__ cT, long M, int D,
-                const int *__restrict__ list, const int *__restrict__ count, int min_cnt,
-                int32_t *__restrict__ idx, float *__restrict__ diff, int32_t *__restrict__ nfound) {
-  __shared__ u64 skey[8][8];
+// ---------------------------------------------------------------- K1-list8 (k == 1, no masks)
+// The rows of a work list -- the K2 certificate failures, tiny-magnitude rows -- answered exactly.  One
+// row per warp streams the whole codebook through L2 by itself (C4: 294 rows x 8 MB = 2.4 GB, 0.5 ms), so a
+// warp takes EIGHT listed rows against each 128-code tile (8 rows x 4 codes per lane in registers), which
+// divides that traffic by eight; and because a short list then has far fewer groups than the GPU has
+// warps, the code tiles of a group are cut into S slices that go to different warps ANYWHERE in the grid.
+// The slices of a row meet in a 64-bit atomicMin on (distance bits << 32 | index) -- distances are
+// non-negative, so the unsigned order is (distance, then lower index): the first-minimum rule of
+// lvq_pak.c:79 -- and the warp that finishes a group last writes the results and resets the scratch.
+__global__ void __launch_bounds__(256, 2)
+k1_list8_kernel(const float *__restrict__ data, const float *__restrict__ cT, long M, int D,
+                const int *__restrict__ list, const int *__restrict__ count, u64 *__restrict__ keys,
+                int *__restrict__ done, int32_t *__restrict__ idx, float *__restrict__ diff,
+                int32_t *__restrict__ nfound) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cnt = *count;
-  if (cnt < min_cnt) return;                             // very short list: one row per warp is faster
+  if (cnt <= 0) return;
+  const long W = (long)gridDim.x * 8, wid = (long)blockIdx.x * 8 + warp;
   const long groups = (cnt + 7) / 8;
   const int nct = (int)((M + K1_TC - 1) / K1_TC);
-  int S = 1;                                             // warps of a CTA sharing one group of rows
-  const long total_warps = (long)gridDim.x * 8;
-  while (S < 8 && S * 2 <= nct && groups * S * 2 <= total_warps) S *= 2;
-  const int groups_per_cta = 8 / S;
-  const int gloc = warp / S, sub = warp % S;
-  for (long base = (long)blockIdx.x * groups_per_cta; base < groups; base += (long)gridDim.x * groups_per_cta) {
-    const long gidx = base + gloc;
-    const bool valid = gidx < groups;
+  long S = W / groups;                                   // slices per group: uniform over the grid
+  S = S < 1 ? 1 : (S > nct ? nct : S);
+  const long items = groups * S;
+  for (long item = wid; item < items; item += W) {
+    const long gidx = item / S;
+    const int sl = (int)(item % S);
+    const int ct0 = (int)((long)sl * nct / S), ct1 = (int)((long)(sl + 1) * nct / S);
     const float *xp[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       long w = gidx * 8 + r;
-      if (!valid || w >= cnt) w = valid ? gidx * 8 : 0;     // harmless duplicate, never written
-      xp[r] = data + (long)list[cnt > 0 ? w : 0] * D;
+      if (w >= cnt) w = gidx * 8;                          // harmless duplicate, never written
+      xp[r] = data + (long)list[w] * D;
     }
     u64 best[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) best[r] = ~0ull;
-    if (valid)
-      for (int ct = sub; ct < nct; ct += S) {
-        const float *cbase = cT + (long)ct * D * K1_TC + lane;
-        float acc[8][4];
+    for (int ct = ct0; ct < ct1; ct++) {
+      const float *cbase = cT + (long)ct * D * K1_TC + lane;
+      float acc[8][4];
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+      for (int r = 0; r < 8; r++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+        for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
 #pragma unroll 4
-        for (int i = 0; i < D; i++) {
-          const float *cr = cbase + (long)i * K1_TC;
-          const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+      for (int i = 0; i < D; i++) {
+        const float *cr = cbase + (long)i * K1_TC;
+        const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
 #pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const float xi = __ldg(xp[r] + i);
-            acc[r][0] = sq_acc(acc[r][0], c0, xi);
-            acc[r][1] = sq_acc(acc[r][1], c1, xi);
-            acc[r][2] = sq_acc(acc[r][2], c2, xi);
-            acc[r][3] = sq_acc(acc[r][3], c3, xi);
-          }
+        for (int r = 0; r < 8; r++) {
+          const float xi = __ldg(xp[r] + i);
+          acc[r][0] = sq_acc(acc[r][0], c0, xi);
+          acc[r][1] = sq_acc(acc[r][1], c1, xi);
+          acc[r][2] = sq_acc(acc[r][2], c2, xi);
+          acc[r][3] = sq_acc(acc[r][3], c3, xi);
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int j = ct * K1_TC + tile_code(lane + 32 * q);
-          if (j >= M) continue;
+      for (int q = 0; q < 4; q++) {
+        const int j = ct * K1_TC + tile_code(lane + 32 * q);
+        if (j >= M) continue;
 #pragma unroll
-          for (int r = 0; r < 8; r++) {
-            // strict < against the FLT_MAX start value (lvq_pak.c:60,79); NaN never wins; the
-            // 64-bit key orders by distance, then by the lower index
-            if (acc[r][q] < FLT_MAX) {
-              const u64 key = ((u64)__float_as_uint(acc[r][q]) << 32) | (unsigned)j;
-              best[r] = key < best[r] ? key : best[r];
-            }
+        for (int r = 0; r < 8; r++) {
+          // strict < against the FLT_MAX start value (lvq_pak.c:60,79); NaN never wins; the
+          // 64-bit key orders by distance, then by the lower index
+          if (acc[r][q] < FLT_MAX) {
+            const u64 key = ((u64)__float_as_uint(acc[r][q]) << 32) | (unsigned)j;
+            best[r] = key < best[r] ? key : best[r];
           }
         }
       }
+    }
+    u64 mine = ~0ull;                                       // lane r < 8 ends up with row r's minimum
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       u64 b = best[r];
@@ -493,21 +498,29 @@ k1_warp8_kernel(const float *__restrict__ data, const float *__restrict__ cT, lo
         const u64 o = __shfl_xor_sync(0xffffffffu, b, off);
         b = o < b ? o : b;
       }
-      if (lane == 0) skey[warp][r] = b;
+      if (lane == r) mine = b;
     }
-    __syncthreads();
-    if (valid && sub == 0 && lane < 8) {
-      const long w = gidx * 8 + lane;
-      if (w < cnt) {
-        u64 b = ~0ull;
-        for (int q = 0; q < S; q++) { const u64 o = skey[warp + q][lane]; b = o < b ? o : b; }
+    const long w = gidx * 8 + lane;
+    if (lane < 8 && w < cnt && mine != ~0ull) atomicMin(&keys[w], mine);
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = atomicAdd(&done[gidx], 1) == (int)S - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      if (lane < 8 && w < cnt) {
+        const u64 b = atomicExch(&keys[w], ~0ull);          // read the minimum and leave the slot reset
         const long n = list[w];
         idx[n] = b == ~0ull ? -1 : (int)(unsigned)b;
         diff[n] = b == ~0ull ? -1.0f : __uint_as_float((unsigned)(b >> 32));
         nfound[n] = 1;
       }
+      if (lane == 0) done[gidx] = 0;
     }
-    __syncthreads();
   }
 }
 
@@ -634,22 +647,20 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
 
 // rows in listW (count in counters[0]): masked / tiny rows, k >= 2 rows, K2 certificate failures
 cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
+  // The list length is only known on the device.  k == 1 without masks: k1_list8_kernel (eight rows per
+  // warp, code tiles sliced over the whole grid, 2 CTAs per SM); k >= 2 or masks: k1_warp_kernel, whose
+  // warps share a row.  Both are persistent over the list and return at once when it is empty.
+  if (a.k == 1 && a.mask == nullptr && a.lkeys) {
+    k1_list8_kernel<<<a.num_sms * 2, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, a.lkeys, a.ldone,
+                                                  a.idx, a.diff, a.nfound);
+    k1_count_launch(1);
+    return cudaGetLastError();
+  }
   long warps = a.N < 8L * a.num_sms * 8 ? a.N : 8L * a.num_sms * 8;   // persistent over the list
   if (warps < 8) warps = 8;
   int grid = (int)((warps + 7) / 8);
-  // The list length is only known on the device.  With k == 1 and no masks, lists long enough to
-  // give every SM two warps of eight rows go to k1_warp8_kernel (codebook traffic / 8); shorter
-  // ones (and k >= 2, masks) to k1_warp_kernel, whose warps share a row.  Each kernel returns
-  // at once when the count is outside its range.
-  int split = 0x7fffffff;
-  if (a.k == 1 && a.mask == nullptr && a.short_list) {
-    split = 16 * a.num_sms;
-    k1_warp8_kernel<<<grid, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, split, a.idx, a.diff,
-                                          a.nfound);
-    k1_count_launch(1);
-  }
   k1_warp_kernel<<<grid, 256, 0, st>>>(a.data, a.mask, a.cT, a.M, a.D, a.k, a.listW,
-                                       a.counters + 0, split, a.idx, a.diff, a.nfound);
+                                       a.counters + 0, 0x7fffffff, a.idx, a.diff, a.nfound);
   k1_count_launch(1);
   return cudaGetLastError();
 }

@@ -26,6 +26,8 @@ struct K1Args {
   unsigned char *flags;         // N
   int *listW, *listS;           // N each
   int *counters;                // 4 ints
+  unsigned long long *lkeys;    // k1_list8_kernel: N keys, all ones between launches (nullptr: not available)
+  int *ldone;                   // k1_list8_kernel: N / 8 + 1 arrival counters, zero between launches
   // outputs
   int32_t *idx;
   float *diff;
