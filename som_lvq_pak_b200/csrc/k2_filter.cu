@@ -242,15 +242,30 @@ k2_row_prep_kernel(const float *__restrict__ data, const unsigned char *__restri
   unsigned f = 0;
   int nmasked = 0;
   __shared__ float mean_s[K2_PS];
-  const bool fast = mask == nullptr && n0 + K2_TM <= N && (D % K2_PS) == 0;   // full tile: no per-element checks
+  const bool fast = mask == nullptr && n0 + K2_TM <= N && (D % K2_PS) == 0 &&   // full tile: no per-element checks,
+                    (reinterpret_cast<uintptr_t>(data) & 15) == 0;              // rows readable as float4
 
   if (fast) {
     for (int d0 = 0; d0 < D; d0 += K2_PS) {
       __syncthreads();
       if (tid < K2_PS) mean_s[tid] = mean[d0 + tid];
-      // phase 1: coalesced load of 128 rows x 32 components
-#pragma unroll 4
-      for (int r = warp; r < K2_TM; r += 8) xs[r][lane] = data[(n0 + r) * (long)D + d0 + lane];
+      // phase 1: 128 rows x 32 components as float4 loads, all four of a thread in flight before the first
+      // use (the kernel is HBM-bound: with one scalar load per lane and row the SM had ~28 KB in flight,
+      // below the ~35 KB per SM that 6.5 TB/s at ~0.8 us latency needs; measured 1.15 -> see DESIGN.md)
+      {
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int f4 = tid + q * 256;                      // float4 index inside the slab: 8 per row
+          v[q] = __ldcs(reinterpret_cast<const float4 *>(data + (n0 + (f4 >> 3)) * (long)D + d0) + (f4 & 7));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int f4 = tid + q * 256;
+          float *dst = &xs[f4 >> 3][(f4 & 7) * 4];            // row stride 33 floats: the 32 lanes hit 32 banks
+          dst[0] = v[q].x; dst[1] = v[q].y; dst[2] = v[q].z; dst[3] = v[q].w;
+        }
+      }
       __syncthreads();
       // phase 2: centre, scale, round; each thread packs 2 x 8 components of one row
 #pragma unroll

@@ -110,7 +110,12 @@ static uint64_t codes_fingerprint(struct entries *codes) {
 }
 
 static int winner_batch(struct entries *codes, struct data_entry *sample, int knn) {
-  const uint64_t print = codes_fingerprint(codes);
+  uint64_t print;
+  if (codes->entries == NULL) {               /* not read yet: the reference loads on the first rewind (lvq_pak.c:55) */
+    eptr p;
+    rewind_entries(codes, &p);
+  }
+  print = codes_fingerprint(codes);
   if (W.cb == NULL || W.codes != codes || W.codes_print != print) {
     if (W.cb) bmu_mcodebook_destroy(W.cb);
     flat_free(&W.cflat);
@@ -221,6 +226,10 @@ struct entries *som_training(struct teach_params *teach) {
   if (data->dimension != codes->dimension) {
     fprintf(stderr, "code dimension (%d) != data dimension (%d)\n", codes->dimension, data->dimension);
     return NULL;
+  }
+  {
+    eptr p;
+    rewind_entries(codes, &p);                             /* make sure the map is loaded (lvq_pak.c:55) */
   }
   if (entries_flatten(codes->entries, codes->dimension, &fc)) return NULL;
   if (use_weights(-1)) {                                                   /* som_rout.c:622-624 */

@@ -108,3 +108,24 @@ def test_reference_buffered_reading_on_the_engine(box, golden):
     assert box.run("qerror", "-din", "ex.dat", "-cin", "ex.cod", "-buffer", "500") == str(g["som_qerror_stdout"])
     box.put("ex1l.cod", g["lvq_l_cod"])
     assert box.run("accuracy", "-din", "ex2.dat", "-cin", "ex1l.cod", "-buffer", "300") == str(g["lvq_l_accuracy_stdout"])
+
+
+def test_reference_planes_trajectory_on_the_engine(box, golden, tmp_path):
+    """scan_data_traj (planes.c:220-262): the per-sample winner trajectory and the hit density of the
+    reference's own `planes`, once with its stock winner function (oracle/_ref/bin, CPU) and once with the
+    engine behind the same slot -- every PostScript file must come out identical"""
+    g = golden.demo
+    stock = os.path.join(ROOT, "oracle", "_ref", "bin", "planes")
+    assert os.path.exists(stock), "stock reference binaries not built (make -C oracle ref)"
+    box.put("ex.cod", g["som_vcal_cod"])
+    ref_dir = tmp_path / "stock"
+    ref_dir.mkdir()
+    for f in ("ex.dat", "ex.cod"):
+        (ref_dir / f).write_text(box.text(f))
+    subprocess.run([stock, "-cin", "ex.cod", "-din", "ex.dat", "-plane", "0"], cwd=ref_dir, check=True,
+                   stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    box.run("planes", "-cin", "ex.cod", "-din", "ex.dat", "-plane", "0")
+    names = sorted(p.name for p in ref_dir.glob("*.eps"))
+    assert "ex_tr.eps" in names and len(names) >= 6
+    for n in names:
+        assert box.text(n) == (ref_dir / n).read_text(), n
