@@ -262,6 +262,12 @@ int bmu_sammon(const float *codes, const unsigned char *mask, long M, int D, lon
 /* lvq_pak.c:459-473 + datafile.c:1152-1188: order[i] = row used at list position i after
  * `-rand seed` (seed != 0; the reference maps seed 0 to time()). */
 void bmu_rand_order(long n, int seed, int32_t *order);
+/* the data row used at each of `nsteps` training steps (som_rout.c:602-610, lvq_rout.c:531-540): list
+ * order walked cyclically; with seed != 0 (`-rand`) the list is shuffled when it is read; with
+ * 0 < buffer <= N (`-buffer`) the file is held `buffer` entries at a time, every chunk is shuffled on its
+ * own each time it is (re-)read and the generator state runs on (datafile.c:237-344).  Feed the result to
+ * bmu_som_schedule / bmu_lvq_schedule as `order` with N = nsteps. */
+void bmu_sample_sequence(long N, long buffer, int seed, long nsteps, int32_t *sample);
 /* randinit_codes (som_rout.c:34-157): M = xdim*ydim code vectors drawn uniformly between the
  * per-component minimum and maximum of the (unmasked) data with the reference's generator seeded
  * by `seed` (init_random, lvq_pak.c:478-484); components without data become 0.  Used by the

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "bmu_identical_pairs": (C.c_int, [vp, vp, C.c_long, C.c_int, vp, C.c_long, vp]),
     "bmu_sammon": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_long, vp, vp, vp]),
     "bmu_rand_order": (None, [C.c_long, C.c_int, vp]),
+    "bmu_sample_sequence": (None, [C.c_long, C.c_long, C.c_int, C.c_long, vp]),
     "bmu_som_schedule": (None, [C.c_long, C.c_long, C.c_long, C.c_float, C.c_float, C.c_int,
                                 C.c_long, vp, vp, vp, vp, vp]),
     "bmu_replay_qerror": (C.c_float, [vp, vp, C.c_long, C.c_int]),

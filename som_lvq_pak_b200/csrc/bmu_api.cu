@@ -733,6 +733,47 @@ void bmu_rand_order(long n, int seed, int32_t *order) {
   }
 }
 
+// The row used at every training step.  Without -buffer (or with a buffer larger than the file) the list
+// is shuffled once when the file is read (datafile.c:340-341) and walked cyclically (som_rout.c:602-610).
+// With `-buffer B` the reference holds B entries at a time: every chunk it reads is shuffled on its own
+// (read_entries, datafile.c:237-344), at the end of the file it rewinds and reads -- and shuffles -- the
+// chunks again, and the generator's state (lvq_pak.c:459-473) simply runs on from shuffle to shuffle.  A
+// host that keeps the whole file in memory reproduces that order from the row counts alone.
+void bmu_sample_sequence(long N, long buffer, int seed, long nsteps, int32_t *sample) {
+  unsigned long state = (unsigned long)seed;
+  if (N <= 0 || nsteps <= 0) return;
+  const long chunk = (buffer <= 0 || buffer > N) ? N : buffer;
+  const bool reread = chunk == buffer;                      // buffered: every pass re-reads and re-shuffles
+  int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)chunk);
+  int32_t *once = reread ? nullptr : (int32_t *)malloc(sizeof(int32_t) * (size_t)N);
+  if (!tmp || (!reread && !once)) { free(tmp); free(once); return; }
+  auto shuffle = [&](int32_t *t, long n, long first) {
+    for (long i = 0; i < n; i++) t[i] = (int32_t)(first + i);
+    if (!seed) return;
+    for (long i = 0; i < n; i++) {                          // datafile.c:1169-1175
+      state = (state * 23UL) % 100000001UL;
+      const long j = (long)(int)(state % 32767UL) % n;
+      const int32_t v = t[i];
+      t[i] = t[j];
+      t[j] = v;
+    }
+  };
+  if (!reread) {
+    shuffle(once, N, 0);
+    for (long le = 0; le < nsteps; le++) sample[le] = once[le % N];
+  } else {
+    long le = 0;
+    while (le < nsteps)
+      for (long c0 = 0; c0 < N && le < nsteps; c0 += chunk) {
+        const long n = N - c0 < chunk ? N - c0 : chunk;
+        shuffle(tmp, n, c0);
+        for (long i = 0; i < n && le < nsteps; i++) sample[le++] = tmp[i];
+      }
+  }
+  free(tmp);
+  free(once);
+}
+
 // som_rout.c:97-152.  The maximum starts at FLT_MIN (the smallest POSITIVE float), a quirk kept on
 // purpose; the value expression mixes float and double exactly as the reference's does:
 //   mival + (maval - mival) * ((float) orand() / 32768.0)

@@ -13,10 +13,12 @@
 /* ------------------------------------------------------------------ label table */
 static char **g_labels = NULL;
 static int g_nlabels = 0, g_labcap = 0;
+/* the streamed reader (pak_stream_*) interns the labels of the next chunk on its own thread while the
+ * program prints labels of the current one */
+static pthread_mutex_t g_label_lock = PTHREAD_MUTEX_INITIALIZER;
 
-int label_index(const char *str) {
+static int label_index_locked(const char *str) {
   int i;
-  if (str == NULL || str[0] == '\0') return LABEL_EMPTY;          /* labels.c:86-91 */
   for (i = 0; i < g_nlabels; i++)
     if (strcmp(g_labels[i], str) == 0) return i + 1;
   if (g_nlabels == g_labcap) {
@@ -29,6 +31,14 @@ int label_index(const char *str) {
   if (!g_labels[g_nlabels]) return -1;
   return ++g_nlabels;
 }
+int label_index(const char *str) {
+  int r;
+  if (str == NULL || str[0] == '\0') return LABEL_EMPTY;          /* labels.c:86-91 */
+  pthread_mutex_lock(&g_label_lock);
+  r = label_index_locked(str);
+  pthread_mutex_unlock(&g_label_lock);
+  return r;
+}
 
 void label_reset(void) {                   /* a fresh table per program of `bmu_pak batch` */
   int i;
@@ -37,8 +47,11 @@ void label_reset(void) {                   /* a fresh table per program of `bmu_
 }
 
 const char *label_string(int ind) {
-  if (ind <= 0 || ind > g_nlabels) return NULL;
-  return g_labels[ind - 1];
+  const char *r = NULL;
+  pthread_mutex_lock(&g_label_lock);
+  if (ind > 0 && ind <= g_nlabels) r = g_labels[ind - 1];    /* the strings themselves never move */
+  pthread_mutex_unlock(&g_label_lock);
+  return r;
 }
 
 /* ------------------------------------------------------------------ entries */
@@ -332,8 +345,20 @@ static FILE *pak_open(const char *name, int writing, int *piped) {
   }
   dot = strrchr(name, '.');
   if (dot && (strcmp(dot, ".gz") == 0 || strcmp(dot, ".z") == 0 || strcmp(dot, ".Z") == 0)) {
-    if (strlen(name) > 4000) return NULL;
-    sprintf(cmd, writing ? "gzip -9 -c >%s" : "gzip -d -c %s", name);
+    /* the reference interpolates the name as it is ("gzip -d -c %s", fileio.h:33-38); here it is single-quoted
+     * so that a file name cannot carry shell syntax ('|cmd' names are commands by definition) */
+    char quoted[4100];
+    size_t q = 0;
+    const char *c;
+    if (strlen(name) > 1000) return NULL;
+    quoted[q++] = '\'';
+    for (c = name; *c; c++) {
+      if (*c == '\'') { memcpy(quoted + q, "'\\''", 4); q += 4; }
+      else quoted[q++] = *c;
+    }
+    quoted[q++] = '\'';
+    quoted[q] = '\0';
+    snprintf(cmd, sizeof cmd, writing ? "gzip -9 -c >%s" : "gzip -d -c %s", quoted);
     *piped = 1;
     return popen(cmd, writing ? "w" : "r");
   }
@@ -344,27 +369,30 @@ static void pak_close(FILE *fp, int piped) {
   if (piped) pclose(fp); else fclose(fp);
 }
 
-struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
-  int piped = 0;
-  FILE *fp = pak_open(name, 0, &piped);
-  char *buf, *p, *endbuf, tokbuf[64];
-  size_t len = 0;
-  long header_lines = 0, total = 0, totlab = 0, i;
+/* Parses the text in buf[0, len) (NUL-terminated, whole lines; consumed: the tokenizer writes into it).
+ * head == NULL: the text starts with the file header; otherwise it is a later part of the file whose
+ * header was `head`.  *lines_io: lines of the file in front of this text (for error messages), advanced. */
+static struct pak_entries *parse_text(char *buf, size_t len, const char *name, int labels_needed, int skip_empty,
+                                      const struct pak_entries *head, long *lines_io) {
+  char *p, *endbuf, tokbuf[64];
+  long header_lines = lines_io ? *lines_io : 0, total = 0, totlab = 0, i;
   struct pak_entries *e = NULL;
   struct blk *blks = NULL;
   pthread_t *tids = NULL;
   int dim, nthreads, nb = 0, t, any_mask = 0, failed = 0;
   const char *env = getenv("BMU_PAK_THREADS");
-  if (!fp) return NULL;
-  buf = slurp(fp, &len);
-  pak_close(fp, piped);
-  if (!buf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
   endbuf = buf + len;
   /* header: first line that is not a comment (datafile.c:112-148) */
   p = buf;
+  if (head) {
+    e = (struct pak_entries *)calloc(1, sizeof(*e));
+    if (!e) return NULL;
+    dim = head->dim;
+    e->dim = head->dim; e->topol = head->topol; e->neigh = head->neigh; e->xdim = head->xdim; e->ydim = head->ydim;
+  } else
   for (;;) {
     char *nl;
-    if (p >= endbuf) { fprintf(stderr, "Can't read file %s", name); free(buf); return NULL; }
+    if (p >= endbuf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
     nl = (char *)memchr(p, '\n', (size_t)(endbuf - p));
     if (nl) *nl = '\0';
     header_lines++;
@@ -373,11 +401,10 @@ struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty
       p = nl ? nl + 1 : endbuf;
       if (sscanf(line, "%d", &dim) <= 0 || dim <= 0) {
         fprintf(stderr, "Can't read dimension parameter in file %s", name);
-        free(buf);
         return NULL;
       }
       e = (struct pak_entries *)calloc(1, sizeof(*e));
-      if (!e) { free(buf); return NULL; }
+      if (!e) return NULL;
       e->dim = dim;
       e->topol = name_id(topol_names, 5, header_token(line, 1, tokbuf, sizeof tokbuf));
       e->xdim = header_token(line, 2, tokbuf, sizeof tokbuf) ? atoi(tokbuf) : 0;
@@ -462,15 +489,217 @@ struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty
       row += b->n;
     }
   }
+  if (lines_io) {
+    *lines_io = header_lines;
+    for (t = 0; t < nb; t++) *lines_io += blks[t].lines;
+  }
   for (t = 0; t < nb; t++) blk_release(&blks[t]);
-  free(blks); free(tids); free(buf);
+  free(blks); free(tids);
   return e;
 fail:
   if (blks) for (t = 0; t < nb; t++) blk_release(&blks[t]);
-  free(blks); free(tids); free(buf);
+  free(blks); free(tids);
   pak_free(e);
   return NULL;
 }
+
+struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
+  int piped = 0;
+  FILE *fp = pak_open(name, 0, &piped);
+  struct pak_entries *e;
+  char *buf;
+  size_t len = 0;
+  if (!fp) return NULL;
+  buf = slurp(fp, &len);
+  pak_close(fp, piped);
+  if (!buf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
+  e = parse_text(buf, len, name, labels_needed, skip_empty, NULL, NULL);
+  free(buf);
+  return e;
+}
+
+/* ------------------------------------------------------------------ streamed reading (-buffer N)
+ * The reference's `-buffer N` (datafile.c:237-344) keeps N entries in memory at a time.  Here the file is
+ * read in text blocks of PAK_TEXT_BLOCK bytes, each parsed by the block-parallel parser above, and handed
+ * out in chunks of exactly N entries; the NEXT text block is read and parsed on a helper thread while
+ * the caller searches the current chunk (parse || H2D || kernel). */
+#define PAK_TEXT_BLOCK pak_text_block()
+static size_t pak_text_block(void) {       /* $BMU_PAK_TEXT_BLOCK: bytes per text block (tests use small ones) */
+  const char *env = getenv("BMU_PAK_TEXT_BLOCK");
+  return (env && atol(env) > 0) ? (size_t)atol(env) : ((size_t)64 << 20);
+}
+struct pak_stream {
+  FILE *fp;
+  int piped, labels_needed, skip_empty, eof, failed;
+  char *name;
+  long buffer, lines;
+  struct pak_entries head;          /* dim / topol / ... of the file (no rows) */
+  int have_head;
+  char *carry;                      /* the unfinished last line of the block before */
+  size_t carry_len;
+  struct pak_entries *pending;      /* parsed, not handed out yet */
+  long pending_pos;
+  pthread_t th;
+  int th_running;
+  struct pak_entries *fetched;      /* result of the helper thread */
+  int fetched_eof, fetched_failed;
+};
+
+/* read and parse the next text block; returns NULL at the end of the file or on error (st->failed) */
+static struct pak_entries *stream_block(struct pak_stream *st, int *eof, int *failed) {
+  const size_t block = PAK_TEXT_BLOCK;
+  size_t cap = block + st->carry_len + 1, n = st->carry_len, got, cut;
+  char *buf = (char *)malloc(cap + 1);
+  struct pak_entries *e;
+  *failed = 0;
+  if (!buf) { *failed = 1; return NULL; }
+  if (st->carry_len) memcpy(buf, st->carry, st->carry_len);
+  free(st->carry);
+  st->carry = NULL;
+  st->carry_len = 0;
+  got = fread(buf + n, 1, block, st->fp);
+  n += got;
+  if (got < block) *eof = 1;
+  if (n == 0) { free(buf); return NULL; }
+  cut = n;
+  if (!*eof) {                                         /* keep the unfinished last line for the next block */
+    while (cut > 0 && buf[cut - 1] != '\n') cut--;
+    if (cut == 0) {                                    /* one line longer than a block: read on */
+      st->carry = buf;
+      st->carry_len = n;
+      return stream_block(st, eof, failed);
+    }
+    st->carry_len = n - cut;
+    st->carry = (char *)malloc(st->carry_len + 1);
+    if (!st->carry) { free(buf); *failed = 1; return NULL; }
+    memcpy(st->carry, buf + cut, st->carry_len);
+  }
+  buf[cut] = '\0';
+  e = parse_text(buf, cut, st->name, st->labels_needed, st->skip_empty, st->have_head ? &st->head : NULL, &st->lines);
+  free(buf);
+  if (!e) { *failed = 1; return NULL; }
+  if (!st->have_head) {
+    st->head = *e;
+    st->head.n = 0;
+    st->head.points = NULL; st->head.mask = NULL; st->head.lab_off = NULL; st->head.lab_pool = NULL;
+    st->head.weight = NULL; st->head.fixed_xy = NULL;
+    st->have_head = 1;
+  }
+  return e;
+}
+
+static void *stream_fetch(void *arg) {
+  struct pak_stream *st = (struct pak_stream *)arg;
+  st->fetched_eof = 0;
+  st->fetched = stream_block(st, &st->fetched_eof, &st->fetched_failed);
+  return NULL;
+}
+
+struct pak_stream *pak_stream_open(const char *name, int labels_needed, int skip_empty, long buffer) {
+  struct pak_stream *st = (struct pak_stream *)calloc(1, sizeof(*st));
+  if (!st) return NULL;
+  st->fp = pak_open(name, 0, &st->piped);
+  if (!st->fp) { free(st); return NULL; }
+  st->name = strdup(name);
+  st->labels_needed = labels_needed;
+  st->skip_empty = skip_empty;
+  st->buffer = buffer;
+  /* the first block is parsed here: it carries the header, which the caller wants before the first chunk */
+  st->pending = stream_block(st, &st->eof, &st->failed);
+  if (st->failed || !st->have_head) { pak_stream_close(st); return NULL; }
+  return st;
+}
+
+const struct pak_entries *pak_stream_header(const struct pak_stream *st) { return &st->head; }
+
+/* rows [from, from + n) of `src` appended to `dst` (same file, same dim) */
+static int entries_append(struct pak_entries *dst, const struct pak_entries *src, long from, long n) {
+  const int dim = dst->dim;
+  const long nn = dst->n + n, lab0 = dst->lab_off ? dst->lab_off[dst->n] : 0;
+  const long nl = src->lab_off[from + n] - src->lab_off[from];
+  long i;
+  float *p = (float *)realloc(dst->points, sizeof(float) * (size_t)(nn > 0 ? nn : 1) * dim);
+  long *lo = (long *)realloc(dst->lab_off, sizeof(long) * (size_t)(nn + 1));
+  int *lp = (int *)realloc(dst->lab_pool, sizeof(int) * (size_t)(lab0 + nl > 0 ? lab0 + nl : 1));
+  short *w = (short *)realloc(dst->weight, sizeof(short) * (size_t)(nn > 0 ? nn : 1));
+  short *f = (short *)realloc(dst->fixed_xy, sizeof(short) * 2 * (size_t)(nn > 0 ? nn : 1));
+  if (p) dst->points = p;
+  if (lo) dst->lab_off = lo;
+  if (lp) dst->lab_pool = lp;
+  if (w) dst->weight = w;
+  if (f) dst->fixed_xy = f;
+  if (!p || !lo || !lp || !w || !f) return 1;
+  if (dst->n == 0) dst->lab_off[0] = 0;
+  if (src->mask || dst->mask) {
+    unsigned char *m = (unsigned char *)realloc(dst->mask, (size_t)(nn > 0 ? nn : 1) * dim);
+    if (!m) return 1;
+    if (!dst->mask) memset(m, 0, (size_t)dst->n * dim);
+    dst->mask = m;
+    if (src->mask) memcpy(m + (size_t)dst->n * dim, src->mask + (size_t)from * dim, (size_t)n * dim);
+    else memset(m + (size_t)dst->n * dim, 0, (size_t)n * dim);
+  }
+  memcpy(dst->points + (size_t)dst->n * dim, src->points + (size_t)from * dim, sizeof(float) * (size_t)n * dim);
+  memcpy(dst->weight + dst->n, src->weight + from, sizeof(short) * (size_t)n);
+  memcpy(dst->fixed_xy + 2 * dst->n, src->fixed_xy + 2 * from, sizeof(short) * 2 * (size_t)n);
+  memcpy(dst->lab_pool + lab0, src->lab_pool + src->lab_off[from], sizeof(int) * (size_t)nl);
+  for (i = 1; i <= n; i++) dst->lab_off[dst->n + i] = lab0 + (src->lab_off[from + i] - src->lab_off[from]);
+  dst->n = nn;
+  return 0;
+}
+
+/* the next chunk: `buffer` entries (fewer at the end of the file; the whole file when buffer <= 0);
+ * NULL when the file is exhausted or on error (pak_stream_failed tells which).  The caller frees it. */
+struct pak_entries *pak_stream_next(struct pak_stream *st) {
+  struct pak_entries *out;
+  if (st->failed) return NULL;
+  out = (struct pak_entries *)calloc(1, sizeof(*out));
+  if (!out) { st->failed = 1; return NULL; }
+  *out = st->head;
+  for (;;) {
+    const long want = st->buffer > 0 ? st->buffer - out->n : -1;
+    if (st->pending) {
+      const long have = st->pending->n - st->pending_pos, take = (want < 0 || have < want) ? have : want;
+      if (take > 0 && entries_append(out, st->pending, st->pending_pos, take)) { st->failed = 1; break; }
+      st->pending_pos += take;
+      if (st->pending_pos >= st->pending->n) { pak_free(st->pending); st->pending = NULL; st->pending_pos = 0; }
+    }
+    if (st->buffer > 0 && out->n >= st->buffer) break;
+    if (st->pending) continue;
+    /* need more text: take what the helper thread fetched, or read now */
+    if (st->th_running) {
+      pthread_join(st->th, NULL);
+      st->th_running = 0;
+      st->pending = st->fetched;
+      st->fetched = NULL;
+      st->eof = st->fetched_eof;
+      if (st->fetched_failed) { st->failed = 1; break; }
+    } else if (!st->eof) {
+      st->pending = stream_block(st, &st->eof, &st->failed);
+      if (st->failed) break;
+    }
+    if (!st->pending && st->eof) break;
+  }
+  /* read ahead while the caller works on this chunk */
+  if (!st->failed && !st->eof && !st->th_running && (!st->pending || st->pending->n - st->pending_pos < st->buffer || st->buffer <= 0)) {
+    if (pthread_create(&st->th, NULL, stream_fetch, st) == 0) st->th_running = 1;
+  }
+  if (st->failed || out->n == 0) { pak_free(out); return NULL; }
+  return out;
+}
+
+int pak_stream_failed(const struct pak_stream *st) { return st->failed; }
+
+void pak_stream_close(struct pak_stream *st) {
+  if (!st) return;
+  if (st->th_running) { pthread_join(st->th, NULL); pak_free(st->fetched); }
+  if (st->fp) pak_close(st->fp, st->piped);
+  pak_free(st->pending);
+  free(st->carry);
+  free(st->name);
+  free(st);
+}
+
+
 
 void pak_write_header(FILE *fp, const struct pak_entries *e) {     /* datafile.c:396-415 */
   fprintf(fp, "%d", e->dim);
@@ -481,14 +710,10 @@ void pak_write_header(FILE *fp, const struct pak_entries *e) {     /* datafile.c
   fprintf(fp, "\n");
 }
 
-int pak_save(const struct pak_entries *e, const char *name) {
-  int piped = 0;
-  FILE *fp = pak_open(name, 1, &piped);
+void pak_write_entries(FILE *fp, const struct pak_entries *e) {     /* datafile.c:420-447 */
   long i, l;
   int c;
-  if (!fp) { fprintf(stderr, "save_entries: Can't open file '%s'\n", name); return 1; }
-  pak_write_header(fp, e);
-  for (i = 0; i < e->n; i++) {                                     /* datafile.c:420-447 */
+  for (i = 0; i < e->n; i++) {
     const float *pt = e->points + (size_t)i * e->dim;
     const unsigned char *mk = e->mask ? e->mask + (size_t)i * e->dim : NULL;
     for (c = 0; c < e->dim; c++) {
@@ -498,6 +723,14 @@ int pak_save(const struct pak_entries *e, const char *name) {
     for (l = e->lab_off[i]; l < e->lab_off[i + 1]; l++) fprintf(fp, "%s ", label_string(e->lab_pool[l]));
     fprintf(fp, "\n");
   }
+}
+
+int pak_save(const struct pak_entries *e, const char *name) {
+  int piped = 0;
+  FILE *fp = pak_open(name, 1, &piped);
+  if (!fp) { fprintf(stderr, "save_entries: Can't open file '%s'\n", name); return 1; }
+  pak_write_header(fp, e);
+  pak_write_entries(fp, e);
   pak_close(fp, piped);
   return 0;
 }

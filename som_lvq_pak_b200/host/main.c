@@ -28,6 +28,7 @@ static int dispatch(const char *prog, int argc, char **argv) {
   if (strcmp(prog, "elimin") == 0) return elimin_main(argc, argv);
   if (strcmp(prog, "pakcat") == 0) return pakcat_main(argc, argv);
   if (strcmp(prog, "pakstat") == 0) return pakstat_main(argc, argv);
+  if (strcmp(prog, "paksynth") == 0) return paksynth_main(argc, argv);
   if (strcmp(prog, "lvq1") == 0 || strcmp(prog, "lvq2") == 0 || strcmp(prog, "lvq3") == 0 ||
       strcmp(prog, "olvq1") == 0 || strcmp(prog, "lvqtrain") == 0)
     return lvqtrain_main(argc, argv, prog);

@@ -16,6 +16,9 @@
  *   vfind trials                vfind.c:247-306       bmu_randinit_codes + 2 x bmu_som_train + qerror, per trial
  *   pick_inside_codes           lvq_rout.c:151-211    bmu_search (k) of the data set against itself (eveninit / propinit)
  *
+ * -buffer N: qerror and accuracy stream the data file in chunks of N entries (the next chunk is parsed
+ * while the current one is searched); vsom / lvq1..3 / olvq1 reproduce the reference's chunk-wise -rand
+ * order (bmu_sample_sequence); the other programs read the file whole -- for them -buffer changes no output.
  * Not carried over (outside SURVEY.md section 8): -selfuncs, background (forked) snapshots.
  * Compressed (.gz/.Z) and piped (|cmd) file names ARE handled by the file layer (entries.c).
  */
@@ -57,8 +60,8 @@ static void global_options(int argc, char **argv) {                     /* lvq_p
   if (s) pak_mask_string = s;
   s = opt(argc, argv, "-v");
   verbose_level = s ? atoi(s) : 1;
-  if (opt(argc, argv, "-buffer") || opt(argc, argv, "-selfuncs"))
-    fprintf(stderr, "note: -buffer and -selfuncs are not supported by the B200 host; ignored\n");
+  if (opt(argc, argv, "-selfuncs"))
+    fprintf(stderr, "note: -selfuncs is not supported by the B200 host; ignored\n");
 }
 
 static void lra_name(const char *codefile, char *out, size_t outsz);
@@ -118,41 +121,71 @@ static int open_pair(int argc, char **argv, int data_labels_needed, int code_lab
 }
 
 /* ------------------------------------------------------------------ qerror */
+/* data file opened as a stream of chunks (`-buffer N`, datafile.c:237-344; without it one chunk = the whole
+ * file) plus the code file, checked like open_pair */
+static int open_stream_pair(int argc, char **argv, int data_labels_needed, int code_labels_needed, int skip_empty,
+                            int want_map, struct pak_stream **ds, struct pak_entries **codes) {
+  const char *din = need(argc, argv, "-din"), *cin = need(argc, argv, "-cin"), *b = opt(argc, argv, "-buffer");
+  *ds = pak_stream_open(din, data_labels_needed, skip_empty, b ? atol(b) : 0);
+  if (!*ds) { fprintf(stderr, "Can't open data file '%s'\n", din); return 1; }
+  *codes = pak_load(cin, code_labels_needed, 1);
+  if (!*codes) { fprintf(stderr, "Can't open code file '%s'\n", cin); return 1; }
+  if (want_map && (*codes)->topol < TOPOL_HEXA) { fprintf(stderr, "File %s is not a map file\n", cin); return 1; }
+  if (pak_stream_header(*ds)->dim != (*codes)->dim) {
+    fprintf(stderr, "Data and codebook vectors have different dimensions (%d != %d)", pak_stream_header(*ds)->dim,
+            (*codes)->dim);
+    return 1;
+  }
+  if (bmu_init(0)) return engine_failed("bmu_init");
+  return 0;
+}
+
 int qerror_main(int argc, char **argv) {
+  struct pak_stream *ds = NULL;
   struct pak_entries *data = NULL, *codes = NULL;
   const char *s;
   float radius, qerror = 0.0f;
+  long total = 0;
   int qmode;
+  bmu_codebook *cb = NULL;
   global_options(argc, argv);
   s = opt(argc, argv, "-radius");
   radius = s ? (float)atof(s) : 1.0f;
   s = opt(argc, argv, "-qetype");
   qmode = s ? atoi(s) : 0;
-  if (open_pair(argc, argv, 0, 0, 1, 1, &data, &codes)) return 1;
-  if (qmode > 0) {
-    /* find_qerror2: per-sample neighbourhood-weighted error on the GPU, added in data order */
-    float *per = (float *)malloc(sizeof(float) * (size_t)(data->n > 0 ? data->n : 1));
-    bmu_codebook *cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
+  if (open_stream_pair(argc, argv, 0, 0, 1, 1, &ds, &codes)) return 1;
+  /* chunk by chunk (one chunk without -buffer): the next chunk is being read and parsed while this one is
+   * searched; the accumulator is ONE float carried across the chunks in data order (som_rout.c:697,715) */
+  while ((data = pak_stream_next(ds)) != NULL) {
     long i;
-    if (!per || !cb) return engine_failed("bmu_codebook_create");
-    if (bmu_qerror2(cb, codes->xdim, codes->ydim, codes->topol, codes->neigh, radius, data->points, data->mask,
-                    data->n, per))
-      return engine_failed("bmu_qerror2");
-    for (i = 0; i < data->n; i++) qerror += per[i];                 /* som_rout.c:872 */
-    bmu_codebook_destroy(cb);
-    free(per);
-  } else {
-    struct winners w;
-    if (find_winners(codes, data, 1, &w)) return 1;
-    qerror = bmu_replay_qerror(w.diff, w.nfound, data->n, 1);      /* som_rout.c:715 */
-    winners_free(&w);
+    if (qmode > 0) {
+      /* find_qerror2: per-sample neighbourhood-weighted error on the GPU, added in data order */
+      float *per = (float *)malloc(sizeof(float) * (size_t)data->n);
+      if (!cb) cb = bmu_codebook_create(codes->points, codes->n, codes->dim);
+      if (!per || !cb) return engine_failed("bmu_codebook_create");
+      if (bmu_qerror2(cb, codes->xdim, codes->ydim, codes->topol, codes->neigh, radius, data->points, data->mask,
+                      data->n, per))
+        return engine_failed("bmu_qerror2");
+      for (i = 0; i < data->n; i++) qerror += per[i];                 /* som_rout.c:872 */
+      free(per);
+    } else {
+      struct winners w;
+      if (find_winners(codes, data, 1, &w)) return 1;
+      for (i = 0; i < data->n; i++)                                   /* som_rout.c:712-715 */
+        if (w.nfound[i] != 0) qerror += sqrt((double)w.diff[i]);
+      winners_free(&w);
+    }
+    total += data->n;
+    pak_free(data);
   }
+  if (pak_stream_failed(ds)) { fprintf(stderr, "Can't read data file '%s'\n", need(argc, argv, "-din")); return 1; }
+  if (cb) bmu_codebook_destroy(cb);
   if (verbose_level >= 1)                                          /* qerror.c:114-118 */
     fprintf(stdout, "Quantization error of %s with map %s is %f per sample (%ld samples)\n",
-            need(argc, argv, "-din"), need(argc, argv, "-cin"), qerror / (float)data->n, data->n);
+            need(argc, argv, "-din"), need(argc, argv, "-cin"), qerror / (float)total, total);
   else
-    fprintf(stdout, "%f\n", qerror / (float)data->n);
-  pak_free(data);
+    fprintf(stdout, "%f\n", qerror / (float)total);
+  pak_stream_close(ds);
   pak_free(codes);
   return 0;
 }
@@ -261,37 +294,42 @@ static void print_accuracy(const struct pak_hitlist *totals, const struct pak_hi
 }
 
 int accuracy_main(int argc, char **argv) {
+  struct pak_stream *ds = NULL;
   struct pak_entries *data = NULL, *codes = NULL;
-  struct winners w;
   struct pak_hitlist correct, totals;
   const char *cfout;
   FILE *ocf = NULL;
   long i, total = 0, stotal = 0;
   global_options(argc, argv);
   cfout = opt(argc, argv, "-cfout");
-  if (open_pair(argc, argv, 1, 1, 1, 0, &data, &codes)) return 1;
+  if (open_stream_pair(argc, argv, 1, 1, 1, 0, &ds, &codes)) return 1;
   if (cfout && !(ocf = fopen(cfout, "w"))) { fprintf(stderr, "Cannot open '%s' for output\n", cfout); return 1; }
-  if (find_winners(codes, data, 1, &w)) return 1;
   hit_init(&correct);
   hit_init(&totals);
-  for (i = 0; i < data->n; i++) {                                  /* accuracy.c:80-105 */
-    const int datalabel = pak_label(data, i);
-    const int winlabel = w.idx[i] >= 0 ? pak_label(codes, w.idx[i]) : -1;
-    if (winlabel == datalabel) {
-      stotal++;
-      hit_add(&correct, datalabel);
-      if (ocf) fprintf(ocf, "1\n");
-    } else if (ocf) {
-      fprintf(ocf, "0\n");
+  while ((data = pak_stream_next(ds)) != NULL) {                     /* one chunk unless -buffer N */
+    struct winners w;
+    if (find_winners(codes, data, 1, &w)) return 1;
+    for (i = 0; i < data->n; i++) {                                  /* accuracy.c:80-105 */
+      const int datalabel = pak_label(data, i);
+      const int winlabel = w.idx[i] >= 0 ? pak_label(codes, w.idx[i]) : -1;
+      if (winlabel == datalabel) {
+        stotal++;
+        hit_add(&correct, datalabel);
+        if (ocf) fprintf(ocf, "1\n");
+      } else if (ocf) {
+        fprintf(ocf, "0\n");
+      }
+      hit_add(&totals, datalabel);
+      total++;
     }
-    hit_add(&totals, datalabel);
-    total++;
+    winners_free(&w);
+    pak_free(data);
   }
+  if (pak_stream_failed(ds)) { fprintf(stderr, "Can't read data file '%s'\n", need(argc, argv, "-din")); return 1; }
   print_accuracy(&totals, &correct, total, stotal, 0);
   if (ocf) fclose(ocf);
   hit_free(&correct); hit_free(&totals);
-  winners_free(&w);
-  pak_free(data);
+  pak_stream_close(ds);
   pak_free(codes);
   return 0;
 }
@@ -546,18 +584,25 @@ static int alpha_type_of(int argc, char **argv, int *type) {
   return 1;
 }
 
-/* list order of the data: identity, or the reference's shuffle when -rand is given
- * (datafile.c:1152-1188; seed 0 means "seed from the clock", lvq_pak.c:476-484) */
-static int32_t *sample_order(int argc, char **argv, long n) {
-  const char *s = opt(argc, argv, "-rand");
-  int32_t *order;
-  int seed;
-  if (!s) return NULL;
-  seed = atoi(s);
-  if (seed == 0) seed = (int)time(NULL);
-  order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
-  if (order) bmu_rand_order(n, seed, order);
-  return order;
+/* the data row of every training step: list order walked cyclically; `-rand seed` shuffles the list when
+ * it is read (datafile.c:1152-1188; seed 0 means "seed from the clock", lvq_pak.c:476-484); `-buffer B`
+ * makes the reference hold B entries at a time and shuffle every chunk each time it is (re-)read
+ * (datafile.c:237-344) -- reproduced from the row counts by bmu_sample_sequence, the file itself stays
+ * resident on the device.  Returns `length` row indices (the caller passes them to the schedule helpers
+ * as `order` with N = length), or NULL for plain list order. */
+static int32_t *sample_sequence(int argc, char **argv, long n, long length) {
+  const char *s = opt(argc, argv, "-rand"), *b = opt(argc, argv, "-buffer");
+  const long buffer = b ? atol(b) : 0;
+  int32_t *seq;
+  int seed = 0;
+  if (!s && buffer <= 0) return NULL;
+  if (s) {
+    seed = atoi(s);
+    if (seed == 0) seed = (int)time(NULL);
+  }
+  seq = (int32_t *)malloc(sizeof(int32_t) * (size_t)(length > 0 ? length : 1));
+  if (seq) bmu_sample_sequence(n, buffer, seed, length, seq);
+  return seq;
 }
 
 /* ---- snapshots (lvq_pak.c:663-764, som_rout.c:650-658): every `interval` steps the codebook is
@@ -585,6 +630,21 @@ static int snap_setup(struct snap *sn, int argc, char **argv, const char *defaul
   else if (s && strcasecmp(s, "file") != 0) fprintf(stderr, "note: snapshot type %s is written synchronously\n", s);
   return 0;
 }
+/* the -snapfile name may hold ONE integer conversion for the iteration (lvq_pak.c:700-703 passes it to
+ * sprintf as it is); anything else a user-supplied string could smuggle into a format is refused */
+static int snap_pattern_ok(const char *p) {
+  int conversions = 0;
+  for (; *p; p++) {
+    if (*p != '%') continue;
+    p++;
+    if (*p == '%') continue;
+    while (*p == '0' || (*p >= '1' && *p <= '9')) p++;      /* width */
+    if (*p == 'l') p++;
+    if (*p != 'd' && *p != 'i') return 0;
+    if (++conversions > 1) return 0;
+  }
+  return 1;
+}
 static int snap_save(struct snap *sn, const struct pak_entries *codes, long iter, long length) {
   FILE *fp = sn->fp;
   long i, l;
@@ -592,7 +652,8 @@ static int snap_save(struct snap *sn, const struct pak_entries *codes, long iter
   sn->counter++;
   if (!fp) {
     char name[1024];
-    snprintf(name, sizeof name, sn->pattern, iter);
+    if (snap_pattern_ok(sn->pattern)) snprintf(name, sizeof name, sn->pattern, iter);
+    else snprintf(name, sizeof name, "%s", sn->pattern);
     fp = fopen(name, "w");
     if (!fp) return 1;
     if (sn->keepopen) sn->fp = fp;
@@ -643,12 +704,13 @@ int vsom_main(int argc, char **argv) {
   if (open_pair(argc, argv, 0, 0, 1, 1, &data, &codes)) return 1;
   snap_setup(&sn, argc, argv, cout_name);
   if (length > 0 && data->n > 0) {
-    order = sample_order(argc, argv, data->n);
+    order = sample_sequence(argc, argv, data->n, length);
     sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)length);
     talp = (float *)malloc(sizeof(float) * (size_t)length);
     trad = (float *)malloc(sizeof(float) * (size_t)length);
     if (!sample || !talp || !trad) { fprintf(stderr, "out of memory\n"); return 1; }
-    bmu_som_schedule(0, length, length, alpha, radius, alpha_type, data->n, order,
+    /* with a sequence the modulus is the run length: step le uses order[le] */
+    bmu_som_schedule(0, length, length, alpha, radius, alpha_type, order ? length : data->n, order,
                      use_weights ? data->weight : NULL, sample, talp, trad);
     if (!sn.interval) {
       rc = bmu_som_train(codes->points, codes->n, codes->dim, codes->xdim, codes->ydim, codes->topol, codes->neigh,
@@ -748,11 +810,11 @@ int lvqtrain_main(int argc, char **argv, const char *progname) {
     win_thr = (1 - w) / (1 + w);                                     /* lvq_rout.c:770, float arithmetic */
   }
   if (length > 0 && data->n > 0) {
-    order = sample_order(argc, argv, data->n);
+    order = sample_sequence(argc, argv, data->n, length);
     sample = (int32_t *)malloc(sizeof(int32_t) * (size_t)length);
     talp = (float *)malloc(sizeof(float) * (size_t)length);
     if (!sample || !talp) { fprintf(stderr, "out of memory\n"); return 1; }
-    bmu_lvq_schedule(0, length, length, alpha, alpha_type, data->n, order, sample, talp);
+    bmu_lvq_schedule(0, length, length, alpha, alpha_type, order ? length : data->n, order, sample, talp);
     snap_setup(&sn, argc, argv, cout_name);
     if (!sn.interval) {
       rc = bmu_lvq_train(algo, codes->points, code_label, codes->n, codes->dim, data->points, data->mask, data_label,
@@ -1612,10 +1674,69 @@ int pakstat_main(int argc, char **argv) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ paksynth */
+/* a synthetic .dat / map file for wall-time measurements (tools/bench_cli_qerror.py): the counter-based
+ * generator of bench.py (splitmix64(seed, index) -> 24-bit uniform in [0,1)), written with the package's
+ * own "%g " entry grammar */
+int paksynth_main(int argc, char **argv) {
+  const long rows = atol(need(argc, argv, "-rows"));
+  const int dim = atoi(need(argc, argv, "-dim"));
+  const char *s = opt(argc, argv, "-seed"), *xd = opt(argc, argv, "-xdim");
+  const unsigned long long seed = s ? (unsigned long long)atoll(s) : 1ULL;
+  FILE *fp = fopen(need(argc, argv, "-dout"), "w");
+  char *buf;
+  long r;
+  int c;
+  if (!fp || rows < 0 || dim < 1) return 1;
+  buf = (char *)malloc((size_t)dim * 16 + 16);
+  if (!buf) return 1;
+  if (xd) fprintf(fp, "%d hexa %d %ld bubble\n", dim, atoi(xd), rows / atoi(xd));
+  else fprintf(fp, "%d\n", dim);
+  for (r = 0; r < rows; r++) {
+    size_t n = 0;
+    for (c = 0; c < dim; c++) {
+      unsigned long long z = (unsigned long long)(r * (long)dim + c) + seed * 0x632BE59BD9B4E019ULL;
+      z *= 0x9E3779B97F4A7C15ULL;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      z ^= z >> 31;
+      n += (size_t)sprintf(buf + n, "%g ", (double)((float)((z >> 40) & 0xFFFFFF) * (1.0f / 16777216.0f)));
+    }
+    buf[n++] = '\n';
+    fwrite(buf, 1, n, fp);
+  }
+  free(buf);
+  return fclose(fp) != 0;
+}
+
 /* ------------------------------------------------------------------ pakcat */
 int pakcat_main(int argc, char **argv) {
   struct pak_entries *e;
+  const char *b;
   global_options(argc, argv);
+  b = opt(argc, argv, "-buffer");
+  if (b) {
+    /* through the streamed reader: chunks of N entries, written out one after the other */
+    struct pak_stream *st = pak_stream_open(need(argc, argv, "-din"), 0, !flag(argc, argv, "-noskip"), atol(b));
+    const char *dout = need(argc, argv, "-dout");
+    FILE *fp;
+    long chunks = 0;
+    if (!st) return 1;
+    fp = fopen(dout, "w");
+    if (!fp) return 1;
+    pak_write_header(fp, pak_stream_header(st));
+    while ((e = pak_stream_next(st)) != NULL) {
+      if (atol(b) > 0 && e->n > atol(b)) { fprintf(stderr, "chunk of %ld entries\n", e->n); return 1; }
+      pak_write_entries(fp, e);
+      pak_free(e);
+      chunks++;
+    }
+    fclose(fp);
+    if (pak_stream_failed(st)) return 1;
+    pak_stream_close(st);
+    fprintf(stderr, "%ld chunks\n", chunks);
+    return 0;
+  }
   e = pak_load(need(argc, argv, "-din"), 0, !flag(argc, argv, "-noskip"));
   if (!e) return 1;
   if (pak_save(e, need(argc, argv, "-dout"))) return 1;

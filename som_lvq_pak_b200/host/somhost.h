@@ -44,10 +44,20 @@ struct pak_entries {
 /* labels_needed: a line without a label is an error (datafile.c:737-745);
  * skip_empty: drop entries whose components are all masked (datafile.c:677-690) */
 struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty);
+/* streamed reading, the reference's `-buffer N` (datafile.c:237-344): the file is handed out in chunks of
+ * N entries (N <= 0: one chunk, the whole file); the next block of text is read and parsed on a helper
+ * thread while the caller works on the current chunk */
+struct pak_stream;
+struct pak_stream *pak_stream_open(const char *name, int labels_needed, int skip_empty, long buffer);
+const struct pak_entries *pak_stream_header(const struct pak_stream *st);   /* dim, topology (no rows) */
+struct pak_entries *pak_stream_next(struct pak_stream *st);                 /* NULL: end of file or error */
+int pak_stream_failed(const struct pak_stream *st);
+void pak_stream_close(struct pak_stream *st);
 struct pak_entries *pak_alloc(int dim, long n);
 void pak_free(struct pak_entries *e);
 int pak_save(const struct pak_entries *e, const char *name);
 void pak_write_header(FILE *fp, const struct pak_entries *e);
+void pak_write_entries(FILE *fp, const struct pak_entries *e);   /* the entry lines, datafile.c:420-447 */
 /* first label of entry i (get_entry_label, labels.h:45) */
 int pak_label(const struct pak_entries *e, long i);
 /* replace the labels of every entry: nlab[i] labels taken from labs (concatenated) */
@@ -85,6 +95,7 @@ int mindist_main(int argc, char **argv);
 int sammon_main(int argc, char **argv);
 int balance_main(int argc, char **argv);
 int pakcat_main(int argc, char **argv);   /* load + save: exercises the file layer alone */
-int pakstat_main(int argc, char **argv);  /* load only, prints counts and the load time */
+int pakstat_main(int argc, char **argv);
+int paksynth_main(int argc, char **argv); /* synthetic .dat / map files for wall-time measurements */  /* load only, prints counts and the load time */
 
 #endif

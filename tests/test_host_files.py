@@ -100,6 +100,36 @@ def test_parallel_loader_is_thread_count_independent(tmp_path):
     assert outs[0].count(b"\n") == len(kept) + 1
 
 
+def test_streamed_reader_equals_whole_file_load(tmp_path):
+    """-buffer N (datafile.c:237-344) through the streamed reader: chunks of exactly N entries (text blocks of
+    64 MB parsed block-parallel, the next one on a helper thread), concatenated = the whole-file load;
+    masks, multiple labels and skipped all-masked lines included"""
+    text = _big_file(40_000, 24)
+    src = tmp_path / "big.dat"
+    src.write_text(text)
+    whole = tmp_path / "whole.dat"
+    subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(whole)], check=True)
+    for buf in ("1", "777", "5000", "40000", "100000"):
+        if buf == "1" and len(text) > 1_000_000:
+            continue                                # one entry per chunk: covered on the small file below
+        dst = tmp_path / ("b%s.dat" % buf)
+        for block in ("", "300000", "1000"):        # text blocks of 64 MB (default), 300 KB, 1000 bytes (~4 lines)
+            env = dict(os.environ, BMU_PAK_TEXT_BLOCK=block) if block else dict(os.environ)
+            if block == "1000" and buf != "777":
+                continue
+            subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(dst), "-buffer", buf], check=True,
+                           stderr=subprocess.PIPE, env=env)
+            assert dst.read_bytes() == whole.read_bytes(), (buf, block)
+    small = tmp_path / "small.dat"
+    small.write_text("3\n# c\n1 2 3 a b\nx x x dropped\n4 x 6 c\n\n7 8 9\n")
+    outs = []
+    for extra in ((), ("-buffer", "1"), ("-buffer", "2")):
+        dst = tmp_path / "s.out"
+        subprocess.run([PAK, "pakcat", "-din", str(small), "-dout", str(dst), *extra], check=True, stderr=subprocess.PIPE)
+        outs.append(dst.read_text())
+    assert outs[0] == outs[1] == outs[2] == "3\n1 2 3 a b \n4 x 6 c \n7 8 9 \n"
+
+
 def test_parallel_loader_reports_the_file_line(tmp_path):
     text = _big_file(60_000, 24).splitlines()
     bad_line = 41_234
