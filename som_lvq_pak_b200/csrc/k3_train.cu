@@ -558,6 +558,8 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
   }
   for (long t = 0; t < p.nsteps; t++) {
     const float talp = p.talp[t], trad = p.trad[t];
+    // 1 / (2 r^2) of this step: needed only after the grid exchange, so the division runs while the CTA waits
+    const double inv_den = gaussian ? __ddiv_rn(1.0, __dmul_rn(__dmul_rn(2.0, (double)trad), (double)trad)) : 0.0;
     const int b1 = b0 == 2 ? 0 : b0 + 1, b2 = b1 == 2 ? 0 : b1 + 1;
     // ---- winner of step t: CTA minimum, then the grid exchange
     u64 k1 = (active && acc < FLT_MAX) ? make_key(acc, gidx, false) : K3_NOKEY;   // lvq_pak.c:57,79
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
       float dd;
       if (small_map) dd = p.topol == 4 ? rect_dist_small(bx, by, tx, ty) : hexa_dist_small(bx, by, tx, ty);
       else dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
-      if (gaussian) { a = gauss_alpha_dev(talp, dd, trad); upd = active; }
+      if (gaussian) { a = gauss_alpha_fast(talp, dd, trad, inv_den); upd = active; }
       else upd = active && dd <= trad;                     // som_rout.c:496
     }
     const float *xt = xs + b0 * Dp;

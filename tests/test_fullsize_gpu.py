@@ -112,9 +112,48 @@ def test_c5_schedule_prefix(engine, oracle):
     assert nbad <= got.size // 1_000_000 + 4, "%d of %d floats differ" % (nbad, got.size)
 
 
+def test_c5_shape_bubble_bit_exact(engine, oracle):
+    """the C5 shape (256x256 hexa, 128-dim, fused K3 kernel) with the BUBBLE neighbourhood: no exp(), so the
+    codebook must be bit-identical to the oracle's after every step of the prefix (radius 100: most of the
+    map moves at each step)"""
+    N, D, xdim, ydim, length, steps = 100_000, 128, 256, 256, 1_000_000, 100
+    data = synth_numpy(4, 0, N * D).reshape(N, D)
+    codes = synth_numpy(5, 0, xdim * ydim * D).reshape(xdim * ydim, D)
+    order = engine.rand_order(N, 3)
+    s, ta, tr = engine.som_schedule(0, steps, length, 0.05, 100.0, engine.ALPHA_LINEAR, N, order)
+    t = engine.Trainer(codes, data)
+    t.set_som(xdim, ydim, engine.TOPOL_HEXA, engine.NEIGH_BUBBLE)
+    t.steps(s, ta, tr)
+    got = t.codes()
+    t.close()
+    exp = oracle.som_train_prefix(codes, data, xdim, ydim, 3, 1, length, steps, 0.05, 100.0, 1, order=order)
+    assert_bits_equal(got, exp, "bubble C5 prefix")
+
+
+@pytest.mark.parametrize("neigh", [1, 2])
+def test_long_run_reaches_the_late_schedule(engine, oracle, neigh):
+    """a COMPLETE run of 20 000 steps on a reduced map (32 x 24 hexa, 128-dim: the fused large-dimension
+    kernel, several CTAs) over 3 000 samples: the sample list wraps six times (som_rout.c:602-610), the
+    radius falls linearly from 12 to 1 (trad < 2 for the last 1 800 steps: single-unit neighbourhoods) and
+    alpha to ~0.  Bubble: bit-exact.  Gaussian: the documented 1e-6 relative tolerance (double exp)."""
+    N, D, xdim, ydim, length = 3000, 128, 32, 24, 20_000
+    data = synth_numpy(14, 0, N * D).reshape(N, D)
+    codes = synth_numpy(15, 0, xdim * ydim * D).reshape(xdim * ydim, D)
+    order = engine.rand_order(N, 11)
+    got = engine.som_training(codes, data, xdim, ydim, engine.TOPOL_HEXA, neigh, length, 0.05, 12.0, rand_seed=11)
+    exp = oracle.som_train(codes, data, xdim, ydim, 3, neigh, length, 0.05, 12.0, 1, order=order)
+    if neigh == 1:
+        assert_bits_equal(got, exp, "bubble long run")
+    else:
+        np.testing.assert_allclose(got, exp, rtol=1e-6, atol=0)
+        nbad = int((got.view(np.int32) != exp.view(np.int32)).sum())
+        assert nbad <= got.size // 1000, "%d of %d floats differ" % (nbad, got.size)
+
+
 def test_host_pointer_search_through_filter_path(engine, oracle):
-    """bmu_search() with host buffers: 2.3 M x 64 rows are cut into three 256 MB chunks whose copies
-    overlap the kernels; every chunk goes through the tensor-core filter.  A sample must agree with
+    """bmu_search() with host buffers: 2.3 M x 64 rows are cut into eleven 58 MB chunks (pageable numpy
+    memory: staged through the pinned ring) whose copies overlap the kernels; every chunk goes through the
+    tensor-core filter.  A sample must agree with
     the oracle bit for bit and the chunk seams must not lose or duplicate rows."""
     rng = np.random.default_rng(9)
     N, D, M = 2_300_003, 64, 3000
@@ -124,8 +163,8 @@ def test_host_pointer_search_through_filter_path(engine, oracle):
     bd = engine.last_search_breakdown()
     assert bd["k2_certified"] > 0
     assert (nf == 1).all() and idx.min() >= 0 and idx.max() < M
-    seam = 1_048_576                                               # rows per 256 MB chunk at D = 64
-    sub = np.r_[0:300, seam - 150:seam + 150, 2 * seam - 150:2 * seam + 150, N - 300:N]
+    seam = 148 * 512 * 3                                           # rows per chunk at D = 64: 64 MB in whole waves
+    sub = np.r_[0:300, seam - 150:seam + 150, 2 * seam - 150:2 * seam + 150, 9 * seam - 150:9 * seam + 150, N - 300:N]
     e = oracle.search(codes, data[sub], 1)
     assert_bits_equal(idx[sub], e[0])
     assert_bits_equal(diff[sub], e[1])
