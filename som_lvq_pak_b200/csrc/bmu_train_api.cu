@@ -1,5 +1,6 @@
 // bmu_train_api.cu -- C ABI for online training (bmu_trainer_*, bmu_som_train,
 // bmu_lvq_train) on top of the persistent kernel K3.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -167,6 +168,16 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
   p.nsteps = nsteps;
   p.slots = t->d_slots; p.gslice = t->d_gslice;
   p.U = t->plan.U; p.Us = t->plan.Us; p.slice_in_smem = t->plan.slice_in_smem;
+  long long *d_prof = nullptr;
+  if (getenv("BMU_K3_PROF")) {                       // diagnostic: phase cycles of the fused large-map kernel
+    if (cudaMalloc((void **)&d_prof, sizeof(long long) * 8 * (size_t)t->plan.grid) != cudaSuccess) d_prof = nullptr;
+    else cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * (size_t)t->plan.grid, g_compute);
+  }
+  p.prof = d_prof;
+  {
+    const char *env = getenv("BMU_K3_POLL_DELAY_NS");
+    p.poll_delay_ns = env ? atoi(env) : K3_POLL_DELAY_NS;
+  }
   CK(cudaEventRecord(t->ev0, g_compute));
   cudaError_t e = k3_launch(p, t->plan, t->has_mask, g_compute);
   k1_count_launch(1);
@@ -174,6 +185,25 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
   CK(cudaEventRecord(t->ev1, g_compute));
   CK(cudaStreamSynchronize(g_compute));
   CK(cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1));
+  if (d_prof) {
+    const int G = t->plan.grid;
+    long long *h = (long long *)malloc(sizeof(long long) * 8 * (size_t)G);
+    if (h && cudaMemcpy(h, d_prof, sizeof(long long) * 8 * (size_t)G, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char *names[5] = {"cta_min", "exchange", "barrier", "weights", "pass"};
+      fprintf(stderr, "K3 phase cycles per step (mean over %d CTAs / min / max), %ld steps, %.3f us per step:\n", G, nsteps,
+              1e3 * t->last_ms / (double)nsteps);
+      for (int i = 0; i < 5; i++) {
+        double sum = 0, mn = 1e300, mx = 0;
+        for (int g = 0; g < G; g++) {
+          const double v = (double)h[(size_t)g * 8 + i] / (double)nsteps;
+          sum += v; mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+        }
+        fprintf(stderr, "  %-9s %8.0f %8.0f %8.0f\n", names[i], sum / G, mn, mx);
+      }
+    }
+    free(h);
+    cudaFree(d_prof);
+  }
   return BMU_OK;
 }
 

@@ -556,11 +556,22 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     __syncthreads();
     acc = pass(xs, xs, false, 0.0f);              // distances to the first sample, no update
   }
+  // phase cycles of thread 0 ($BMU_K3_PROF): [0] CTA minimum, [1] grid exchange (own key stored -> global minimum
+  // known), [2] barrier after the exchange (waiting for warp 0 + the staged sample), [3] lattice distance and
+  // gaussian weight, [4] fused update + search pass
+  long long pc[5] = {0, 0, 0, 0, 0}, c0 = 0, c1;
+  const bool prof = p.prof != nullptr && tid == 0;
+#define K3_TICK(i) do { if (prof) { c1 = clock64(); pc[i] += c1 - c0; c0 = c1; } } while (0)
+  if (prof) c0 = clock64();
   for (long t = 0; t < p.nsteps; t++) {
     const float talp = p.talp[t], trad = p.trad[t];
     // 1 / (2 r^2) of this step: needed only after the grid exchange, so the division runs while the CTA waits
     const double inv_den = gaussian ? __ddiv_rn(1.0, __dmul_rn(__dmul_rn(2.0, (double)trad), (double)trad)) : 0.0;
     const int b1 = b0 == 2 ? 0 : b0 + 1, b2 = b1 == 2 ? 0 : b1 + 1;
+    // row of the sample two steps ahead: loaded HERE so that its L2 latency hides behind the exchange.  (Loaded
+    // where it is used -- after the exchange, by warp 0, the warp every other one waits for -- it cost ~800 of
+    // the ~9200 cycles of a step: $BMU_K3_PROF, profiles/r02_k3_phase_cycles.txt.)
+    const long srow2 = (t + 2 < p.nsteps) ? (long)p.sample[t + 2] : 0;
     // ---- winner of step t: CTA minimum, then the grid exchange
     u64 k1 = (active && acc < FLT_MAX) ? make_key(acc, gidx, false) : K3_NOKEY;   // lvq_pak.c:57,79
     k1 = warp_min_u64(k1);
@@ -569,10 +580,15 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     if (warp == 0) {
       u64 bk = lane < K3F_THREADS / 32 ? wred[lane] : K3_NOKEY;
       bk = warp_min_u64(bk);
+      K3_TICK(0);
       if (G > 1) {
         const u64 tag = (u64)((bstep + 1) & 0xFFu);
         u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
         if (lane == 0) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, bk | tag);
+        // All CTAs publish within ~50 cycles of each other and a store needs a few hundred cycles to reach L2:
+        // polls issued at once arrive BEFORE the keys and cost a whole extra L2 round trip, so the first poll
+        // waits a moment (tuned with $BMU_K3_POLL_DELAY_NS, profiles/r02_k3_phase_cycles.txt)
+        if (p.poll_delay_ns > 0) __nanosleep((unsigned)p.poll_delay_ns);
         constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
         u64 v1[NQ];
         unsigned pending = 0;
@@ -596,13 +612,15 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
         bk = warp_min_u64(m1);
       }
       if (lane == 0) gw[0] = bk;
+      K3_TICK(1);
     }
     bstep++;
     // sample t+1 (staged one step ago) must have landed before the fused pass reads it
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    K3_TICK(2);
     const u64 g1 = gw[0];
-    if (t + 2 < p.nsteps) stage(b2, p.sample[t + 2]);      // buffer b2 was last read two passes ago
+    if (t + 2 < p.nsteps) stage(b2, srow2);                // buffer b2 was last read two passes ago
     // ---- update of step t fused with the search of step t+1
     bool upd = false;
     float a = talp;
@@ -617,9 +635,14 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     }
     const float *xt = xs + b0 * Dp;
     const float *xn = (t + 1 < p.nsteps) ? xs + b1 * Dp : xt;
+    K3_TICK(3);
     acc = pass(xt, xn, upd, a);
+    K3_TICK(4);
     b0 = b1;
   }
+  if (prof)
+    for (int i = 0; i < 5; i++) p.prof[(size_t)blockIdx.x * 8 + i] = pc[i];
+#undef K3_TICK
 
   // ---- write the unit back
   __syncthreads();

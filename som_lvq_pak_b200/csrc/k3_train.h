@@ -8,6 +8,7 @@ namespace bmu {
 enum K3Mode { K3_SOM_BUBBLE = 0, K3_SOM_GAUSSIAN = 1, K3_LVQ1 = 2, K3_LVQ2 = 3, K3_LVQ3 = 4, K3_OLVQ1 = 5 };
 
 #define K3_THREADS 256
+#define K3_POLL_DELAY_NS 100           // default pause before the first poll of the fused kernel's exchange (see k3_train.cu)
 #define K3_MAX_GRID 160              // CTA slots the grid exchange polls (5 x 32 lanes)
 #define K3_MASK_SENTINEL 0x7fc00b00u   // quiet NaN payload that marks a masked component
 
@@ -36,6 +37,8 @@ struct K3Params {
   float *gslice;                 // [grid][D][Us] when the slices do not fit shared memory
   int U, Us;                     // units per CTA and padded row stride
   int slice_in_smem;
+  int poll_delay_ns;             // pause between publishing the CTA's key and the first poll of the others' slots
+  long long *prof;               // nullptr, or [grid][8] cycle counters of the fused kernel's phases ($BMU_K3_PROF)
 };
 
 struct K3Plan {
