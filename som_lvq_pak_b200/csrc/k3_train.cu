@@ -611,7 +611,13 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
           if (lane + 32 * q < G) { const u64 a1 = v1[q] & ~0xFFull; m1 = a1 < m1 ? a1 : m1; }
         bk = warp_min_u64(m1);
       }
-      if (lane == 0) gw[0] = bk;
+      if (lane == 0) {
+        gw[0] = bk;
+        // the winner's lattice position (som_rout.c:641-642) is the same for every unit: the two integer
+        // divisions are done once here instead of by all 512 threads behind the barrier
+        const int w = bk != K3_NOKEY ? key_idx(bk, false) : 0;
+        gw[1] = (u64)(unsigned)(w % p.xdim) | ((u64)(unsigned)(w / p.xdim) << 32);
+      }
       K3_TICK(1);
     }
     bstep++;
@@ -625,8 +631,8 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     bool upd = false;
     float a = talp;
     if (g1 != K3_NOKEY) {                                  // no winner (all distances NaN/Inf): step skipped
-      const int w = key_idx(g1, false);
-      const int bx = w % p.xdim, by = w / p.xdim;          // som_rout.c:641-642
+      const u64 bxy = gw[1];
+      const int bx = (int)(unsigned)bxy, by = (int)(bxy >> 32);
       float dd;
       if (small_map) dd = p.topol == 4 ? rect_dist_small(bx, by, tx, ty) : hexa_dist_small(bx, by, tx, ty);
       else dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
