@@ -239,6 +239,7 @@ def main_reference(args, w):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     return 0
 
 
@@ -481,6 +482,7 @@ def main_gpu(args, w):
                                               "(reference find_winner_euc, gcc -O3), %.1f s wall"
                                               % (rpc, cores, wall_s)}
         print(json.dumps(line))
+        sys.stdout.flush()
     lib.bmu_codebook_destroy(cb)
     if world > 1:
         lib.bmu_comm_destroy()
@@ -602,6 +604,12 @@ def vsom_c5(bmu, args):
 
 
 def main():
+    # exactly ONE line on stdout: libraries print there too (NCCL's version banner), so file descriptor 1 is
+    # pointed at stderr for the run and the JSON line goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -62,10 +62,11 @@ struct Pinned {
 };
 
 #define RING_PIECES 4
-#define RING_PIECE_BYTES ((size_t)8 << 20)
+#define RING_PIECE_MAX ((size_t)8 << 20)
 
 struct HostRing {
-  Pinned pieces;                                   // RING_PIECES x RING_PIECE_BYTES, H2D staging
+  Pinned pieces;                                   // RING_PIECES x piece_bytes, H2D staging
+  size_t piece_bytes = 0;
   cudaEvent_t piece_done[RING_PIECES] = {};        // the DMA that read piece i has finished
   bool piece_used[RING_PIECES] = {};
   unsigned long next_piece = 0;
@@ -98,6 +99,23 @@ static int copy_threads_default() {
   if (n < 1) n = 1;
   if (n > 64) n = 64;
   return n;
+}
+
+static std::atomic<int> g_host_sharers{0};      // shards of this process that stage at the same time (bmu_multi_search)
+void host_set_sharers(int n) { g_host_sharers = n; }
+
+// The ring only pays while it stays in the last-level cache, and every rank / shard that feeds a GPU from
+// this host has one: 8 MB pieces for a single feeder (54 GB/s, profiles/r02_host_copy_ubench.txt), smaller
+// ones when several share the cache ($SOMLVQ_RING_PIECE_MB overrides).
+static size_t ring_piece_bytes() {
+  const char *env = getenv("SOMLVQ_RING_PIECE_MB");
+  if (env && atoi(env) > 0) return (size_t)atoi(env) << 20;
+  int sharers = g_host_sharers.load();
+  const char *lw = getenv("LOCAL_WORLD_SIZE");
+  if (lw && atoi(lw) > sharers) sharers = atoi(lw);
+  size_t piece = RING_PIECE_MAX;
+  while (sharers > 1 && piece > ((size_t)1 << 20)) { piece >>= 1; sharers >>= 1; }
+  return piece;
 }
 
 static HostRing *ring_of(DevCtx *c, int threads_hint) {
@@ -176,7 +194,8 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
   const bool st_lab = !tiny && want_conf && !is_pinned(hs->sample_label);
   HostRing *ring = (st_in || st_mask || st_out || st_lab) ? ring_of(c, 0) : nullptr;
   if (ring && (st_in || st_mask || st_lab)) {
-    if ((rc = ring->pieces.ensure(RING_PIECES * RING_PIECE_BYTES))) return rc;
+    ring->piece_bytes = ring_piece_bytes();
+    if ((rc = ring->pieces.ensure(RING_PIECES * ring->piece_bytes))) return rc;
     for (int i = 0; i < RING_PIECES; i++)
       if (!ring->piece_done[i]) CK(cudaEventCreateWithFlags(&ring->piece_done[i], cudaEventDisableTiming));
   }
@@ -189,10 +208,11 @@ int search_host_pipeline(bmu_codebook *cb, const float *data, const unsigned cha
   // pageable ones go through the ring piece by piece (copy threads fill piece i+1 while the DMA reads piece i)
   auto h2d = [&](void *dst, const void *src, size_t bytes, bool staged) -> cudaError_t {
     if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy);
-    for (size_t off = 0; off < bytes; off += RING_PIECE_BYTES) {
-      const size_t len = bytes - off < RING_PIECE_BYTES ? bytes - off : RING_PIECE_BYTES;
+    const size_t pb = ring->piece_bytes;
+    for (size_t off = 0; off < bytes; off += pb) {
+      const size_t len = bytes - off < pb ? bytes - off : pb;
       const int r = (int)(ring->next_piece++ % RING_PIECES);
-      char *piece = (char *)ring->pieces.p + (size_t)r * RING_PIECE_BYTES;
+      char *piece = (char *)ring->pieces.p + (size_t)r * pb;
       cudaError_t e;
       if (ring->piece_used[r] && (e = cudaEventSynchronize(ring->piece_done[r])) != cudaSuccess) return e;
       ring->pool->copy(piece, (const char *)src + off, len, COPY_CACHED);

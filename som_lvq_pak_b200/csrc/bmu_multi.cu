@@ -34,6 +34,7 @@ bmu_codebook *codebook_alloc(long M, int D);
 int codebook_ready(bmu_codebook *cb);
 int codebook_set_labels(bmu_codebook *cb, const int32_t *label);
 void host_set_copy_threads(int n);
+void host_set_sharers(int n);
 }  // namespace bmu
 
 using namespace bmu;
@@ -55,10 +56,16 @@ struct Nccl {
 
 int nccl_load() {
   if (g_nccl.h) return BMU_OK;
+  // A copy that the process has loaded already (PyTorch ships its own libnccl.so.2) is reused: two NCCL
+  // builds in one process, the second one opened RTLD_GLOBAL, made a later `import torch` bind to the wrong
+  // one.  Otherwise the system library is opened with local scope.
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   void *h = nullptr;
   for (const char *n : names)
-    if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if ((h = dlopen(n, RTLD_NOW | RTLD_NOLOAD))) break;
+  if (!h)
+    for (const char *n : names)
+      if ((h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
   if (!h) return fail(BMU_ERR_NODEV, "NCCL is needed for more than one GPU and libnccl.so.2 could not be loaded: %s", dlerror());
 #define SYM(field, name)                                                     \
   g_nccl.field = (decltype(g_nccl.field))dlsym(h, name);                     \
@@ -310,6 +317,7 @@ int bmu_multi_search(bmu_mcodebook *mc, const float *data, const unsigned char *
     long cores = sysconf(_SC_NPROCESSORS_ONLN);
     int per = (int)(cores / S);
     host_set_copy_threads(per < 1 ? 1 : (per > 8 ? 8 : per));
+    host_set_sharers(S);
   }
   int rcs[BMU_MAX_GPUS] = {0};
   char errs[BMU_MAX_GPUS][512];
@@ -332,6 +340,7 @@ int bmu_multi_search(bmu_mcodebook *mc, const float *data, const unsigned char *
     for (auto &t : th) t.join();
   }
   host_set_copy_threads(0);
+  host_set_sharers(0);
   for (int s = 0; s < S; s++)
     if (rcs[s]) {
       memcpy(g_err, errs[s], sizeof(errs[s]));

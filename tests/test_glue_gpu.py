@@ -1,6 +1,6 @@
 """GPU: the drop-in boundary against the reference's OWN structs.
 
-som_lvq_pak_b200/glue/_build/bin/* are the reference's unmodified programs (qerror.c, visual.c, vcal.c,
+glue/_build/bin/* are the reference's unmodified programs (qerror.c, visual.c, vcal.c,
 accuracy.c, knntest.c, classify.c, cmatr.c, vsom.c, lvqtrain.c, compiled from /root/reference by
 glue/Makefile) linked with bmu_glue.c -- entries_flatten -> bmu_multi_search / bmu_trainer_* ->
 entries_scatter on struct entries / data_entry / winner_info / teach_params (lvq_pak.h:73-124,186-204)
@@ -16,7 +16,7 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-BIN = os.path.join(ROOT, "som_lvq_pak_b200", "glue", "_build", "bin")
+BIN = os.path.join(ROOT, "glue", "_build", "bin")
 
 
 class Box:
@@ -41,7 +41,7 @@ class Box:
 @pytest.fixture()
 def box(tmp_path, golden):
     assert os.path.exists(os.path.join(BIN, "qerror")), \
-        "glue programs not built (make -C som_lvq_pak_b200/glue in the build container)"
+        "glue programs not built (make -C glue in the build container)"
     return Box(tmp_path, golden.demo)
 
 
