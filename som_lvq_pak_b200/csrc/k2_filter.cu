@@ -1046,338 +1046,6 @@ k2_rec_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
   if (warp == 17) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
-// ---------------------------------------------------------------- record kernel with the row prep fused in
-// k2_recf_kernel = k2_rec_kernel that reads the caller's FP32 rows itself.  Same passes,
-// same MMA order, same record epilogue, same exact re-rank; what changes:
-//   * A is no longer an fp16 image in global memory loaded by TMA.  The four re-rank warps also PREPARE the row
-//     tiles of the next pass while the current one runs: coalesced float4 loads of the rows, centre / scale /
-//     round to fp16 (the same operations as k2_row_prep_kernel), 16-byte stores of the K-major core-matrix image
-//     straight into shared memory, per-row ||x'||^2, fp16 residual and the error bound E (RowStats, flags and the
-//     work lists go to global memory as before; the epilogue and the re-rank read them back through L2).
-//   * A is double buffered (pass p uses buffer p & 1): 2 x 4 tiles x 128 rows x Dk fp16 with Dk = K - 16, the
-//     data columns only.  The last 16 K columns of the old image were the same for every row -- {1, 1, 1, 0 ...}
-//     against the three ||m'||^2 terms of the B operand -- so ONE 4 KB "ones" slab serves every row tile and
-//     every pass as the A operand of the last MMA of an accumulation.  That is what makes two A buffers fit:
-//     128 KB + 4 KB + 80 KB of code tiles + 12 KB of hand-off = 224.5 KB at K = 80.
-//   * The producer warp only streams code tiles.  Generic-proxy writes of A are made visible to the tensor core's
-//     async proxy with fence.proxy.async before the arrive on afull[buf]; a buffer is rewritten only after
-//     tcgen05.commit of the pass that read it (afree[buf]).
-// Eligible: no masks, D a multiple of 4 with Dp = 16, 32 or 64 (the norm columns then sit alone in the last
-// 16-column slab), rows 16-byte aligned.  Everything else keeps k2_row_prep_kernel + k2_rec_kernel.
-struct K2FHand { int g0, g1; float thr; };      // 12 bytes per row (the 16-byte version did not fit)
-
-struct K2FArgs {
-  const float *data;            // N x D
-  const float *mean;            // D
-  const CbStats *cst;
-  RowStats *rs;                 // N (written here)
-  unsigned char *flags;         // N (written here)
-  int *listW, *listS, *counters;
-  long N;
-  int D, Dk;                    // Dk = Kp - 16
-};
-
-// rows [n0, n0 + 128) -> fp16 image [Dk/8][128][8] at `dst` (shared memory), RowStats, flags, work lists.
-// 128 threads; LPR = Dk / 8 lanes share a row (one 16-byte image entry each), so a warp reads 32 / LPR whole rows.
-template <int LPR>
-__device__ __forceinline__ void k2f_prep_tile(const K2FArgs &F, long n0, uint4 *dst, int t, int Kp) {
-  const int lane = t & 31;
-  const int D = F.D;
-  const float sc = F.cst->scale;
-  constexpr int RPI = 128 / LPR;                       // rows per iteration of the 128 threads
-#pragma unroll 2
-  for (int r0 = 0; r0 < K2_TM; r0 += RPI) {
-    const int row = r0 + t / LPR, kc = t % LPR;
-    const long n = n0 + row;
-    float v[8];
-    const bool live = n < F.N;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int k = kc * 8 + 4 * h;
-      float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (live && k < D) x = __ldcs(reinterpret_cast<const float4 *>(F.data + n * (long)D + k));
-      v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
-    }
-    float n2 = 0.0f, nr2 = 0.0f;
-    unsigned f = 0;
-    uint32_t hw[4];
-#pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-      float hv[2];
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int k = kc * 8 + q + e;
-        hv[e] = 0.0f;
-        if (live && k < D) {
-          const float x = v[q + e];
-          f |= k2_classify(x);
-          const float c = __fmul_rn(__fsub_rn(x, __ldg(F.mean + k)), sc);
-          const float h = __half2float(__float2half_rn(c));
-          if (!(fabsf(h) < INFINITY)) f |= ROW_RANGE;
-          const float res = __fsub_rn(c, h);
-          hv[e] = h;
-          n2 = __fadd_rn(n2, __fmul_rn(c, c));
-          nr2 = __fadd_rn(nr2, __fmul_rn(res, res));
-        }
-      }
-      hw[q >> 1] = half2_bits(hv[0], hv[1]);
-    }
-    dst[kc * K2_TM + row] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    // the LPR lanes of a row: sums and flags (any summation order is inside the (D + 4) 2^-23 margin below)
-#pragma unroll
-    for (int off = LPR / 2; off >= 1; off >>= 1) {
-      n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-      nr2 += __shfl_xor_sync(0xffffffffu, nr2, off);
-      f |= __shfl_xor_sync(0xffffffffu, f, off);
-    }
-    if (kc == 0 && live) {
-      // ---- error bound of the tensor-core score for this row: the formulas of k2_row_prep_kernel (pack_bits = 0)
-      F.flags[n] = (unsigned char)f;
-      const CbStats cs = *F.cst;
-      const double up = 1.0001;
-      const double facc = (double)(D + 4) * ldexp(1.0, -23);
-      const double nx = sqrt((double)n2 * (1.0 + facc)) * up, nrx = sqrt((double)nr2 * (1.0 + facc)) * up;
-      const double NM = cs.nm, nrm = cs.nrm, nm2 = cs.nm2;
-      const double nxh = nx + nrx, NMh = NM + nrm;
-      const double amag = 2.0 * nxh * NMh + nm2;
-      const double e_dot = 2.0 * (nrx * NM + nxh * nrm);
-      const double e_norm = ldexp(nm2, -23) + ldexp(1.0, -22);
-      const double e_acc = 2.0 * (double)(Kp / 16) * 17.0 * ldexp(amag, -23);
-      const double E = (e_dot + e_norm + e_acc) * up;
-      const double dmax = (nx + NM) * (nx + NM);
-      const double eta = ldexp(nx + NM, -23);
-      const double gamma = (double)(D + 2) * ldexp(1.0, -24) * 1.01 + 1e-6;
-      const double slack = 4.0 * (2.0 * eta * (nx + NM) + gamma * dmax) + 2.0 * facc * (double)n2;
-      RowStats st;
-      st.nx2 = (double)n2 * (1.0 - facc);
-      st.nx = (float)nx * 1.0001f;
-      st.E = (float)E * 1.0001f;
-      st.delta = (float)(2.02 * E + slack) * 1.0001f;
-      st.pad = 0.0f;
-      F.rs[n] = st;
-      if (f & ROW_NONFINITE) F.listS[atomicAdd(&F.counters[1], 1)] = (int)n;
-      else if (f & (ROW_TINY | ROW_RANGE)) F.listW[atomicAdd(&F.counters[0], 1)] = (int)n;
-    }
-    (void)lane;
-  }
-}
-
-constexpr int K2F_THREADS = 832;   // k2_rec_kernel's 22 warps + warps 22-25: row prep of the next pass.  (The re-rank
-                                   // warps alone could not also do the prep: they are latency-bound gatherers that are
-                                   // busy for most of a pass already -- 16.5 instead of 12.3 + 0.9 ms on C3.)
-template <int R, int NK>
-__global__ void __launch_bounds__(K2F_THREADS, 1)
-k2_recf_kernel(const __half *__restrict__ Bimg, long N, long M, int Kp, int nst, const K2FArgs F, const K2RRerankArgs RA) {
-  static_assert(R == 4, "one epilogue group and one 128-column accumulator per row tile");
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const int Dk = F.Dk;
-  const uint32_t a_tile_bytes = (uint32_t)K2_TM * Dk * 2, b_tile_bytes = (uint32_t)K2_TN * Kp * 2;
-  unsigned char *sA = smem;                                            // [2][R] row tiles, data columns only
-  unsigned char *sOnes = smem + (size_t)2 * R * a_tile_bytes;          // [2][128][8] fp16: {1,1,1,0..} per row
-  unsigned char *sB = sOnes + (size_t)K2_TM * 16 * 2;                  // nst (<= K2R_BST) code tiles
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)nst * b_tile_bytes);
-  uint64_t *full = bars, *empty = bars + K2R_BST;
-  uint64_t *tfull = bars + 2 * K2R_BST, *tempty = tfull + R;
-  uint64_t *afull = tempty + R, *afree = afull + 2;                    // per A buffer
-  uint64_t *rfull = afree + 2, *rempty = rfull + 2;                    // hand-off to the re-rank warps, double buffered
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(rempty + 2);
-  K2FHand *hand = reinterpret_cast<K2FHand *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [2][R * 128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long ntiles = (N + K2_TM - 1) / K2_TM;
-  const long nsuper = (ntiles + R - 1) / R;
-  const int nct = (int)((M + K2_TN - 1) / K2_TN);
-  const int nacc = (int)((M + K2R_TNH - 1) / K2R_TNH);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < K2R_BST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < R; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
-    for (int b = 0; b < 2; b++) { mbar_init(&afull[b], 128); mbar_init(&afree[b], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&rfull[b], 16); mbar_init(&rempty[b], 4); }
-    fence_barrier_init();
-  }
-  // the shared "ones" slab: image entry (kc, row) = 8 halves; kc 0 holds columns Dk..Dk+7 = {1, 1, 1, 0, 0, 0, 0, 0}
-  for (int e = threadIdx.x; e < 2 * K2_TM; e += blockDim.x) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (e < K2_TM) { v.x = half2_bits(1.0f, 1.0f); v.y = half2_bits(1.0f, 0.0f); }
-    reinterpret_cast<uint4 *>(sOnes)[e] = v;
-  }
-  fence_proxy_async();
-  if (warp == 17) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 16) {
-    // ===================== TMA producer: code tiles only =====================
-    if (lane == 0) {
-      unsigned bseq = 0;
-      for (long st = blockIdx.x; st < nsuper; st += gridDim.x) {
-        for (int ct = 0; ct < nct; ct++, bseq++) {
-          const int s = bseq % nst;
-          mbar_wait(&empty[s], ((bseq / nst) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[s], b_tile_bytes);
-          bulk_g2s(sB + (size_t)s * b_tile_bytes,
-                   reinterpret_cast<const unsigned char *>(Bimg) + (size_t)ct * b_tile_bytes, b_tile_bytes, &full[s]);
-        }
-      }
-    }
-  } else if (warp == 17) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = k2r_idesc();
-    const bool leader = elect_one();
-    const uint64_t da0 = umma_desc(smem_u32(sA), K2_TM * 16, 128);
-    const uint64_t dones = umma_desc(smem_u32(sOnes), K2_TM * 16, 128);
-    const uint64_t db0 = umma_desc(smem_u32(sB), K2_TN * 16, 128);
-    const uint64_t a_tile_step = (uint64_t)(a_tile_bytes >> 4), b_tile_step = (uint64_t)(b_tile_bytes >> 4);
-    unsigned bseq = 0, pcount = 0, use = 0;
-    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, pcount++) {
-      const int ab = pcount & 1;
-      mbar_wait(&afull[ab], (pcount >> 1) & 1);            // the re-rank warps finished this pass's row tiles
-      tc_fence_after();
-      const uint64_t dab = da0 + (uint64_t)(ab * R) * a_tile_step;
-      for (int ct = 0; ct < nct; ct++, bseq++) {
-        const int s = bseq % nst;
-        mbar_wait(&full[s], (bseq / nst) & 1);
-        tc_fence_after();
-        const uint64_t dbs = db0 + (uint64_t)s * b_tile_step;
-        const int nh = (2 * ct + 1 < nacc) ? 2 : 1;
-#pragma unroll 1
-        for (int h = 0; h < nh; h++, use++) {
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            mbar_wait(&tempty[r], (use & 1) ^ 1);
-            tc_fence_after();
-            if (leader) {
-              const uint64_t da = dab + (uint64_t)r * a_tile_step;
-              const uint64_t db = dbs + (uint64_t)(h * ((K2R_TNH * 16) >> 4));
-              const uint32_t d_tmem = tmem_base + r * K2R_TNH;
-#pragma unroll
-              for (int kk = 0; kk < NK - 1; kk++)          // the data columns
-                umma_f16(d_tmem, da + (uint64_t)(kk * ((2 * K2_TM * 16) >> 4)),
-                         db + (uint64_t)(kk * ((2 * K2_TN * 16) >> 4)), idesc, kk ? 1u : 0u);
-              // the norm columns: ones x {||m'||^2 as three fp16 terms}
-              umma_f16(d_tmem, dones, db + (uint64_t)((NK - 1) * ((2 * K2_TN * 16) >> 4)), idesc, NK > 1 ? 1u : 0u);
-              umma_commit(&tfull[r]);
-            }
-            __syncwarp();
-          }
-        }
-        if (leader) umma_commit(&empty[s]);
-        __syncwarp();
-      }
-      if (leader) umma_commit(&afree[ab]);                  // this pass's A buffer may be rewritten once its MMAs retire
-      __syncwarp();
-    }
-  } else if (warp >= 22) {
-    // ===================== row prep: the row tiles of pass p + 1 while pass p runs =====================
-    const int t = threadIdx.x - 22 * 32;                  // 0 .. 127
-    unsigned pc = 0;
-    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, pc++) {
-      const int ab = pc & 1;
-      mbar_wait(&afree[ab], ((pc >> 1) & 1) ^ 1);          // the pass two before has released this buffer
-      for (int r = 0; r < R; r++) {
-        uint4 *dst = reinterpret_cast<uint4 *>(sA + (size_t)(ab * R + r) * a_tile_bytes);
-        const long n0 = (st * R + r) * K2_TM;
-        if (Dk == 64) k2f_prep_tile<8>(F, n0, dst, t, Kp);
-        else if (Dk == 32) k2f_prep_tile<4>(F, n0, dst, t, Kp);
-        else k2f_prep_tile<2>(F, n0, dst, t, Kp);
-      }
-      fence_proxy_async();                                 // generic writes of A -> visible to the tensor core
-      mbar_arrive(&afull[ab]);
-    }
-  } else if (warp >= 18) {
-    // ===================== exact re-rank of the pass the epilogue handed over =====================
-    const int t = threadIdx.x - 18 * 32;                  // 0 .. 127
-    unsigned cnt = 0;
-    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, cnt++) {
-      const int par = cnt & 1;
-      mbar_wait(&rfull[par], (cnt >> 1) & 1);
-#pragma unroll 1
-      for (int r = 0; r < R; r++) {
-        const K2FHand h = hand[par * (R * K2_TM) + r * K2_TM + t];
-        k2r_rerank_row(RA, (st * R + r) * K2_TM + t, h.g0, h.g1, h.thr);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rempty[par]);
-    }
-  } else {
-    // ===================== epilogue: group g = warp / 4 owns row tile g and accumulator g =====
-    const int g = warp >> 2, quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + g * K2R_TNH;
-    unsigned use = 0, cnt = 0;
-    for (long st = blockIdx.x; st < nsuper; st += gridDim.x, cnt++) {
-      const long n = (st * R + g) * K2_TM + row;
-      mbar_wait(&afull[cnt & 1], (cnt >> 1) & 1);          // this pass's RowStats have been written
-      const float delta = n < N ? F.rs[n].delta : 0.0f;
-      K2RRow r = {INFINITY, INFINITY, INFINITY, INFINITY, -1, -1};
-      for (int q = 0; q < nacc; q++, use++) {
-        mbar_wait(&tfull[g], use & 1);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32_nowait(tbase, v);
-#pragma unroll 1
-        for (int c0 = 0; c0 < K2R_TNH; c0 += 32) {
-          tmem_ld_wait32(v);
-          float gm[8];
-#pragma unroll
-          for (int t2 = 0; t2 < 8; t2++)
-            gm[t2] = fminf(fminf(fminf(__uint_as_float(v[4 * t2]), __uint_as_float(v[4 * t2 + 1])), __uint_as_float(v[4 * t2 + 2])),
-                           __uint_as_float(v[4 * t2 + 3]));
-          if (c0 + 32 < K2R_TNH) {
-            tmem_ld32_nowait(tbase + c0 + 32, v);
-          } else {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[g]);
-          }
-          const float a3 = fminf(fminf(gm[0], gm[1]), gm[2]), b3 = fminf(fminf(gm[3], gm[4]), gm[5]), c2 = fminf(gm[6], gm[7]);
-          const float m = fminf(fminf(a3, b3), c2);
-          const bool ins = m < r.thr;
-          if (__any_sync(0xffffffffu, ins)) {
-            const bool inA = a3 == m, inB = !inA && b3 == m;
-            const float t0 = inA ? gm[0] : (inB ? gm[3] : gm[6]);
-            const float t1 = inA ? gm[1] : (inB ? gm[4] : gm[7]);
-            const float t2 = inA ? gm[2] : (inB ? gm[5] : INFINITY);
-            const bool e0 = t0 == m, e1 = !e0 && t1 == m;
-            const int qs = (inA ? 0 : (inB ? 3 : 6)) + (e0 ? 0 : (e1 ? 1 : 2));
-            const float s2 = fminf(fminf(fminf(inA ? b3 : a3, (inA || inB) ? c2 : b3), e0 ? t1 : t0), (e0 || e1) ? t2 : t1);
-            const int gi = q * K2R_TNH + c0 + K2R_GW * qs;
-            const bool first = m < r.k0, second = ins && !first && m < r.k1;
-            r.lost = fminf(r.lost, (first || second) ? r.k1 : (ins ? m : INFINITY));
-            r.k1 = first ? r.k0 : (second ? m : r.k1);
-            r.i1 = first ? r.i0 : (second ? gi : r.i1);
-            r.k0 = first ? m : r.k0;
-            r.i0 = first ? gi : r.i0;
-            r.thr = first ? __fadd_ru(m, delta) : r.thr;
-            r.lost = (ins && s2 < r.thr) ? fminf(r.lost, s2) : r.lost;
-          }
-        }
-      }
-      {
-        const int par = cnt & 1;
-        mbar_wait(&rempty[par], ((cnt >> 1) & 1) ^ 1);
-        const float bound = r.thr;
-        K2FHand h;
-        h.g0 = (r.k0 < bound && r.i0 < M) ? r.i0 : -1;
-        h.g1 = (r.k1 < bound && r.i1 < M) ? r.i1 : -1;
-        h.thr = fminf(bound, r.lost);
-        hand[par * (R * K2_TM) + g * K2_TM + row] = h;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rfull[par]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
-}
-
 // ---------------------------------------------------------------- exact re-rank + certificate
 // LPR lanes per row (power of two >= TG): lane g of a row's group computes the exact distance
 // of candidate g, so the loads of x are shared by the group and every lane streams one code
@@ -1683,41 +1351,6 @@ static cudaError_t k2_launch_prep(K2Codebook *c, const K1Args &a, const K2Scratc
   return cudaGetLastError();
 }
 
-// the fused variant: two A buffers of data columns + the shared ones slab
-static size_t k2f_smem_bytes(int Kp) {
-  const int Dk = Kp - 16;
-  return (size_t)2 * K2R_R * K2_TM * Dk * 2 + (size_t)K2_TM * 16 * 2 + (size_t)k2r_stages(Kp) * K2_TN * Kp * 2 + 256 +
-         2 * (size_t)K2R_R * K2_TM * sizeof(K2FHand);
-}
-// no masks, rows readable as float4, the norm columns alone in the last 16-column slab, and it must fit
-static bool k2f_eligible(const K1Args &a, int Kp) {
-  static const int off = getenv("BMU_K2_FUSED") && atoi(getenv("BMU_K2_FUSED")) == 0;      // A/B switch for measurements
-  const int Dp = k2_dp(a.D);
-  return !off && a.k == 1 && a.mask == nullptr && (a.D & 3) == 0 && (Dp == 16 || Dp == 32 || Dp == 64) && Kp == Dp + 16 &&
-         (reinterpret_cast<uintptr_t>(a.data) & 15) == 0 && k2f_smem_bytes(Kp) <= 227 * 1024;
-}
-
-template <int NK>
-static cudaError_t k2_launch_recf(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
-  const int Kp = c->Kp;
-  const size_t smem = k2f_smem_bytes(Kp);
-  cudaError_t e = cudaFuncSetAttribute(k2_recf_kernel<K2R_R, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const long ntiles = (a.N + K2_TM - 1) / K2_TM;
-  const long nsuper = (ntiles + K2R_R - 1) / K2R_R;
-  const int grid = (int)(nsuper < a.num_sms ? nsuper : a.num_sms);
-  K2RRerankArgs ra;
-  ra.data = a.data; ra.grp = c->d_grp; ra.flags = a.flags; ra.rs = s.rs;
-  ra.cst = (const CbStats *)c->d_norm; ra.listW = a.listW; ra.counters = a.counters;
-  ra.idx = a.idx; ra.nfound = a.nfound; ra.diff = a.diff;
-  ra.N = a.N; ra.M = a.M; ra.D = a.D;
-  K2FArgs f;
-  f.data = a.data; f.mean = c->d_norm + 16; f.cst = (const CbStats *)c->d_norm; f.rs = s.rs; f.flags = a.flags;
-  f.listW = a.listW; f.listS = a.listS; f.counters = a.counters; f.N = a.N; f.D = a.D; f.Dk = Kp - 16;
-  k2_recf_kernel<K2R_R, NK><<<grid, K2F_THREADS, smem, st>>>((const __half *)c->d_ops, a.N, a.M, Kp, k2r_stages(Kp), f, ra);
-  return cudaGetLastError();
-}
-
 // Record path (k == 1, short K): row prep, then ONE kernel that does the GEMM filter and the exact
 // re-rank.  History (measured on C3, same box): a separate re-rank kernel after the GEMM 16.5 ms per
 // step; that kernel on a second stream beside the GEMM of the next sub-batch 15.7 ms, but the GEMM
@@ -1728,20 +1361,7 @@ static cudaError_t k2_launch_recf(K2Codebook *c, const K1Args &a, const K2Scratc
 // CTA): the record launches stretched by exactly the prep time that was hidden (12.2 -> 13.1 ms at 4
 // sub-batches, step 13.9 ms either way), so prep stays one launch in front.
 static cudaError_t k2_run_record(K2Codebook *c, const K1Args &a, const K2Scratch &s, cudaStream_t st) {
-  cudaError_t e;
-  if (k2f_eligible(a, c->Kp)) {
-    // ONE launch: the row prep runs inside the record kernel (no fp16 image in global memory)
-    cudaEventRecord(g_k2ev[1], st);
-    switch (c->Kp / 16) {
-      case 2: e = k2_launch_recf<2>(c, a, s, st); break;
-      case 3: e = k2_launch_recf<3>(c, a, s, st); break;
-      default: e = k2_launch_recf<5>(c, a, s, st); break;
-    }
-    k1_count_launch(1);
-    cudaEventRecord(g_k2ev[2], st);
-    return e;
-  }
-  e = k2_launch_prep(c, a, s, 0, a.N, 0, st);
+  cudaError_t e = k2_launch_prep(c, a, s, 0, a.N, 0, st);
   if (e != cudaSuccess) return e;
   cudaEventRecord(g_k2ev[1], st);
   switch (c->Kp / 16) {                                 // K2R_MAX_KP / 16 = 6 unrolled issue loops
@@ -1785,8 +1405,7 @@ cudaError_t k2_search(K2Codebook *c, const K1Args &a, void **scratch, size_t *sc
   const long ntiles_alloc = (ntiles + K2R_R - 1) / K2R_R * K2R_R;   // the record kernel loads whole groups of tiles
   // scratch layout
   size_t off = 0;
-  const bool fused = record && k2f_eligible(a, Kp);       // no fp16 row image in global memory at all
-  const size_t oA = off; off = align_up(off + (fused ? 0 : (size_t)ntiles_alloc * K2_TM * Kp * 2), 256);
+  const size_t oA = off; off = align_up(off + (size_t)ntiles_alloc * K2_TM * Kp * 2, 256);
   const size_t oR = off; off = align_up(off + (size_t)a.N * sizeof(RowStats), 256);
   const size_t oC = off; off = align_up(off + (size_t)a.N * TG * 4, 256);
   const size_t oT = off; off = align_up(off + (size_t)a.N * 4, 256);
