@@ -43,7 +43,7 @@ MASK64 = (1 << 64) - 1
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
 # committed ncu --set full capture of exactly this shape (profiles/): (kernel, rows, D, M) -> bytes
-NCU_TRAFFIC = {("k2_rec_kernel", 10_000_000, 64, 10_000): 4423971000 + 121856768}   # profiles/r01_k2_rec_ncu_full.txt
+NCU_TRAFFIC = {("k2_rec_kernel", 10_000_000, 64, 10_000): 4423282000 + 122659584}   # profiles/r02_k2_rec_ncu_full.txt
 # (fp16 A image 1.6 GB + the FP32 rows 2.56 GB the fused re-rank reads + codebook misses)
 
 
