@@ -93,10 +93,28 @@ class Stats(C.Structure):
 _lib = None
 
 
+def _preload_env_nccl():
+    """libbmu_b200 resolves NCCL at run time by its soname (multi-GPU only).  In a Python environment that
+    ships its own libnccl.so.2 (the nvidia-nccl wheel PyTorch links against) that copy must be the one the
+    process loads FIRST: two builds with the same soname cannot coexist, and a later `import torch` would be
+    bound to whichever came first.  No-op when the wheel is absent (the system library is used then)."""
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            for f in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def load():
     """dlopen the CUDA library (built in-tree by `make -C som_lvq_pak_b200/csrc`)."""
     global _lib
     if _lib is None:
+        _preload_env_nccl()
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 "%s is missing: build it with `make -C som_lvq_pak_b200/csrc` "

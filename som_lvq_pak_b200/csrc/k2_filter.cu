@@ -43,7 +43,8 @@ namespace bmu {
 constexpr int K2_TM = 128;   // rows per sample tile (UMMA M)
 constexpr int K2_TN = 256;   // codes per code tile (UMMA N)
 constexpr int K2_KS = 64;    // K elements per pipeline stage (4 MMAs), streaming kernel
-constexpr int K2_NSTAGE = 4;
+constexpr int K2_NSTAGE = 4;      // slab stages of the default configuration
+constexpr int K2_NSTAGE_MAX = 8;  // barrier slots
 constexpr int K2_THREADS = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.  (Eight epilogue warps, two per
                                   // row splitting the 256 columns, were measured on C4: GEMM 4.0 -> 4.5 ms (k = 1), 4.95 -> 5.85
                                   // (k = 5), and the re-rank blocks that run beside the GEMM CTA got fewer registers.)
@@ -432,8 +433,8 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                : "memory");
 }
 struct K2Smem {
-  static size_t bytes(int Kp, bool a_res, int nst) {
-    size_t stage = (size_t)K2_TN * K2_KS * 2 + (a_res ? 0 : (size_t)K2_TM * K2_KS * 2);
+  static size_t bytes(int Kp, bool a_res, int nst, int ks = K2_KS) {
+    size_t stage = (size_t)K2_TN * ks * 2 + (a_res ? 0 : (size_t)K2_TM * ks * 2);
     return (a_res ? (size_t)K2_TM * Kp * 2 : 0) + nst * stage + 256;
   }
 };
@@ -466,28 +467,28 @@ __device__ __forceinline__ uint32_t k2_idesc() {
 template <int TG, int TT>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
-               const RowStats *__restrict__ rs, long N, long M, int Kp, int a_res, int nst, int k,
+               const RowStats *__restrict__ rs, long N, long M, int Kp, int a_res, int nst, int ks, int k,
                int32_t *__restrict__ cand, float *__restrict__ thr) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const size_t a_res_bytes = a_res ? (size_t)K2_TM * Kp * 2 : 0;
-  const size_t b_stage_bytes = (size_t)K2_TN * K2_KS * 2;
-  const size_t a_stage_bytes = a_res ? 0 : (size_t)K2_TM * K2_KS * 2;
+  const size_t b_stage_bytes = (size_t)K2_TN * ks * 2;
+  const size_t a_stage_bytes = a_res ? 0 : (size_t)K2_TM * ks * 2;
   const size_t stage_bytes = b_stage_bytes + a_stage_bytes;
   unsigned char *sAres = smem;
   unsigned char *sStage = smem + a_res_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + nst * stage_bytes);   // nst <= K2_NSTAGE slab stages
-  uint64_t *full = bars, *empty = bars + K2_NSTAGE;
-  uint64_t *tfull = bars + 2 * K2_NSTAGE, *tempty = tfull + 2;
+  uint64_t *full = bars, *empty = bars + K2_NSTAGE_MAX;
+  uint64_t *tfull = bars + 2 * K2_NSTAGE_MAX, *tempty = tfull + 2;
   uint64_t *afull = tempty + 2, *aempty = afull + 1;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(aempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long ntiles = (N + K2_TM - 1) / K2_TM;
   const int nct = (int)((M + K2_TN - 1) / K2_TN);
-  const int nslab = (Kp + K2_KS - 1) / K2_KS;
+  const int nslab = (Kp + ks - 1) / ks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < K2_NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < K2_NSTAGE_MAX; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     mbar_init(afull, 1);
     mbar_init(aempty, 1);
@@ -517,13 +518,13 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
           const unsigned char *gB = reinterpret_cast<const unsigned char *>(Bimg) + (size_t)ct * K2_TN * Kp * 2;
           for (int sl = 0; sl < nslab; sl++, seq++) {
             const int st = seq % nst;
-            const int kc = min(K2_KS, Kp - sl * K2_KS);               // K elements in this slab
+            const int kc = min(ks, Kp - sl * ks);               // K elements in this slab
             mbar_wait(&empty[st], ((seq / nst) & 1) ^ 1);
             const uint32_t bB = (uint32_t)K2_TN * kc * 2, bA = a_res ? 0u : (uint32_t)K2_TM * kc * 2;
             mbar_arrive_expect_tx(&full[st], bB + bA);
             unsigned char *dst = sStage + (size_t)st * stage_bytes;
-            bulk_g2s(dst, gB + (size_t)sl * K2_KS * K2_TN * 2, bB, &full[st]);
-            if (!a_res) bulk_g2s(dst + b_stage_bytes, gA + (size_t)sl * K2_KS * K2_TM * 2, bA, &full[st]);
+            bulk_g2s(dst, gB + (size_t)sl * ks * K2_TN * 2, bB, &full[st]);
+            if (!a_res) bulk_g2s(dst + b_stage_bytes, gA + (size_t)sl * ks * K2_TM * 2, bA, &full[st]);
           }
         }
       }
@@ -542,11 +543,11 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
           const uint32_t d_tmem = tmem_base + buf * K2_TN;
           for (int sl = 0; sl < nslab; sl++, seq++) {
             const int st = seq % nst;
-            const int kc = min(K2_KS, Kp - sl * K2_KS);
+            const int kc = min(ks, Kp - sl * ks);
             mbar_wait(&full[st], (seq / nst) & 1);
             tc_fence_after();
             const uint32_t bBase = smem_u32(sStage + (size_t)st * stage_bytes);
-            const uint32_t aBase = a_res ? smem_u32(sAres) + (uint32_t)sl * K2_KS * K2_TM * 2
+            const uint32_t aBase = a_res ? smem_u32(sAres) + (uint32_t)sl * ks * K2_TM * 2
                                          : bBase + (uint32_t)b_stage_bytes;
             for (int kk = 0; kk < kc / 16; kk++) {
               // one MMA consumes K=16 = two 8-element chunks, K2_T? * 16 bytes apart
@@ -1266,9 +1267,12 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
   const int Kp = c->Kp;
   // (A resident beyond K2_ARES_MAX_KP with the two slab stages that then fit was measured at K = 528:
   // slower, 4.08 -> 4.23 ms for k = 1; the slab ring needs its depth.)
+  // Round 2 repeated the experiment with HALF-size slabs (32 K columns, 16 KB of B per stage, five stages next to the
+  // 135 KB of A, the code tiles the only stream from L2): 5.50 instead of 4.00 ms (k = 1), 6.84 instead of 5.19 ms
+  // (k = 5).  Two MMAs per barrier round trip do not keep the tensor pipe fed; the slab size stays 64.
   const bool a_res = Kp <= K2_ARES_MAX_KP;
-  const int nst = K2_NSTAGE;
-  const size_t smem = K2Smem::bytes(Kp, a_res, nst);
+  const int nst = K2_NSTAGE, ks = K2_KS;
+  const size_t smem = K2Smem::bytes(Kp, a_res, nst, ks);
   cudaError_t e = cudaFuncSetAttribute(k2_gemm_kernel<TG, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long ntiles_all = (a.N + K2_TM - 1) / K2_TM;
@@ -1286,7 +1290,7 @@ static cudaError_t k2_run_stream(K2Codebook *c, const K1Args &a, const K2Scratch
     const long ntiles = (n + K2_TM - 1) / K2_TM;
     const int grid = (int)(ntiles < a.num_sms ? ntiles : a.num_sms);
     k2_gemm_kernel<TG, TT><<<grid, K2_THREADS, smem, st>>>(s.Aimg + (size_t)row0 * Kp, (const __half *)c->d_ops,
-                                                          s.rs + row0, n, a.M, Kp, a_res ? 1 : 0, nst, a.k,
+                                                          s.rs + row0, n, a.M, Kp, a_res ? 1 : 0, nst, ks, a.k,
                                                           s.cand + row0 * TG, s.thr + row0);
     k1_count_launch(1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
