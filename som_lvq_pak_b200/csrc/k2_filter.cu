@@ -432,6 +432,12 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 struct K2Smem {
   static size_t bytes(int Kp, bool a_res, int nst, int ks = K2_KS) {
     size_t stage = (size_t)K2_TN * ks * 2 + (a_res ? 0 : (size_t)K2_TM * ks * 2);
@@ -530,37 +536,47 @@ k2_gemm_kernel(const __half *__restrict__ Aimg, const __half *__restrict__ Bimg,
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = k2_idesc();
-      unsigned seq = 0, acc_seq = 0, tcount = 0;
-      for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-        if (a_res) { mbar_wait(afull, tcount & 1); tc_fence_after(); }
-        for (int ct = 0; ct < nct; ct++, acc_seq++) {
-          const int buf = acc_seq & 1;
-          mbar_wait(&tempty[buf], ((acc_seq >> 1) & 1) ^ 1);        // epilogue drained this buffer
+    // ===================== MMA issuer =====================
+    // As in k2_rec_kernel: the whole warp runs the loop (uniform control flow, barrier waits by every lane), one
+    // elected lane issues, and the descriptors are built ONCE and advanced by constant offsets.  Building two
+    // descriptors per MMA inside a `lane == 0` branch cost ~140 cycles per MMA there, more than the 128 cycles a
+    // 128x256x16 MMA takes -- the issuing thread, not the tensor pipe, was the bound of this kernel too.
+    const uint32_t idesc = k2_idesc();
+    const bool leader = elect_one();
+    const uint64_t dA0 = umma_desc(smem_u32(sAres), K2_TM * 16, 128);            // resident A (a_res)
+    const uint64_t dS0 = umma_desc(smem_u32(sStage), K2_TN * 16, 128);           // B of stage 0
+    const uint64_t dSA0 = umma_desc(smem_u32(sStage) + (uint32_t)b_stage_bytes, K2_TM * 16, 128);   // streamed A of stage 0
+    const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+    const uint64_t a_slab_step = (uint64_t)((ks * K2_TM * 2) >> 4);
+    constexpr uint64_t A_KK = (uint64_t)((2 * K2_TM * 16) >> 4), B_KK = (uint64_t)((2 * K2_TN * 16) >> 4);
+    unsigned seq = 0, acc_seq = 0, tcount = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+      if (a_res) { mbar_wait(afull, tcount & 1); tc_fence_after(); }
+      for (int ct = 0; ct < nct; ct++, acc_seq++) {
+        const int buf = acc_seq & 1;
+        mbar_wait(&tempty[buf], ((acc_seq >> 1) & 1) ^ 1);        // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * K2_TN;
+        for (int sl = 0; sl < nslab; sl++, seq++) {
+          const int st = seq % nst;
+          const int nk = min(ks, Kp - sl * ks) >> 4;               // MMAs in this slab
+          mbar_wait(&full[st], (seq / nst) & 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * K2_TN;
-          for (int sl = 0; sl < nslab; sl++, seq++) {
-            const int st = seq % nst;
-            const int kc = min(ks, Kp - sl * ks);
-            mbar_wait(&full[st], (seq / nst) & 1);
-            tc_fence_after();
-            const uint32_t bBase = smem_u32(sStage + (size_t)st * stage_bytes);
-            const uint32_t aBase = a_res ? smem_u32(sAres) + (uint32_t)sl * ks * K2_TM * 2
-                                         : bBase + (uint32_t)b_stage_bytes;
-            for (int kk = 0; kk < kc / 16; kk++) {
-              // one MMA consumes K=16 = two 8-element chunks, K2_T? * 16 bytes apart
-              const uint64_t da = umma_desc(aBase + kk * 2 * (K2_TM * 16), K2_TM * 16, 128);
-              const uint64_t db = umma_desc(bBase + kk * 2 * (K2_TN * 16), K2_TN * 16, 128);
-              umma_f16(d_tmem, da, db, idesc, (sl | kk) ? 1u : 0u);
-            }
+          if (leader) {
+            const uint64_t db = dS0 + (uint64_t)st * stage_step;
+            const uint64_t da = a_res ? dA0 + (uint64_t)sl * a_slab_step : dSA0 + (uint64_t)st * stage_step;
+#pragma unroll 4
+            for (int kk = 0; kk < nk; kk++)
+              umma_f16(d_tmem, da + (uint64_t)kk * A_KK, db + (uint64_t)kk * B_KK, idesc, (sl | kk) ? 1u : 0u);
             umma_commit(&empty[st]);                // smem slot reusable once these MMAs retire
           }
-          umma_commit(&tfull[buf]);                 // accumulator ready for the epilogue
+          __syncwarp();
         }
-        if (a_res) umma_commit(aempty);
+        if (leader) umma_commit(&tfull[buf]);       // accumulator ready for the epilogue
+        __syncwarp();
       }
+      if (a_res && leader) umma_commit(aempty);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: one row per thread =====================
@@ -727,12 +743,6 @@ struct K2RRow {
   int i0, i1;
 };
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-  return pred != 0;
-}
 
 // N = 128 variant of the instruction descriptor
 __device__ __forceinline__ uint32_t k2r_idesc() {
