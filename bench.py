@@ -343,8 +343,9 @@ def main_gpu(args, w):
                                   h_diff.ctypes.data, h_nf.ctypes.data))
 
     def wall(fn, steps):
-        fn()                                                   # warm-up (allocates the pinned ring)
-        barrier()
+        for _ in range(max(args.warmup, 3)):                   # untimed warm-up calls, like the device-resident leg (the
+            fn()                                               # first ones allocate the pinned ring and fault in the
+        barrier()                                              # caller's result arrays)
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()

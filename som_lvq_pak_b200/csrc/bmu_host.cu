@@ -12,7 +12,7 @@
 //
 // with BMU_NSLOT device chunks in flight, so that the staging of chunk c+1, the H2D copy of chunk c, the
 // kernels of chunk c-1 and the D2H copy of chunk c-2 all run at the same time.  The pinned ring is kept
-// SMALL on purpose (4 x 8 MB): written with ordinary stores it stays in the CPU's last-level cache, the
+// SMALL on purpose (6 x 8 MB): written with ordinary stores it stays in the CPU's last-level cache, the
 // DMA engine reads the pieces from there, and DRAM only sees the one read of the caller's rows.  Measured
 // on the B200 box (tools/ubench/host_pipe.cu, profiles/r02_host_copy_ubench.txt): 54 GB/s end to end with
 // 8 threads against 55.3 GB/s for the DMA alone from pinned memory; a large ring written with
@@ -61,7 +61,7 @@ struct Pinned {
   }
 };
 
-#define RING_PIECES 4
+#define RING_PIECES 6
 #define RING_PIECE_MAX ((size_t)8 << 20)
 
 struct HostRing {
