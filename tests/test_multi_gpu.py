@@ -179,3 +179,49 @@ def test_real_devices_nccl(engine, oracle):
     esum, efound, ehist, econf = _expected_stats(eidx, ediff, eret, M, L, cl, dl)
     assert st["n_found"] == efound and np.array_equal(st["hist"], ehist) and np.array_equal(st["confusion"], econf)
     assert abs(st["sum_sqrt"] - esum) <= N * np.spacing(esum)
+
+
+def test_page_locked_and_pageable_buffers_agree(engine, oracle, monkeypatch):
+    """bmu_search reads page-locked caller buffers (bmu_host_register / bmu_host_alloc) by DMA directly and stages
+    pageable ones through its pinned ring: same results either way, several chunks each"""
+    import ctypes as C
+    from som_lvq_pak_b200 import _lib
+    lib = _lib.load()
+    M, D, N = 700, 64, 40000                      # 10 MB of rows: above the 1 MB "leave it to the driver" limit
+    rng = np.random.default_rng(17)
+    codes = rng.random((M, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    monkeypatch.setenv("SOMLVQ_CHUNK_ROWS", "6000")
+    cb = engine.Codebook(codes)
+    out = []
+    for pinned in (False, True):
+        idx = np.empty((N, 1), np.int32)
+        diff = np.empty((N, 1), np.float32)
+        nf = np.empty(N, np.int32)
+        bufs = [data, idx, diff, nf]
+        if pinned:
+            for b in bufs:
+                _lib.check(lib.bmu_host_register(b.ctypes.data, b.nbytes))
+        try:
+            _lib.check(lib.bmu_search(cb._h, data.ctypes.data, None, N, 1, idx.ctypes.data, diff.ctypes.data,
+                                      nf.ctypes.data))
+        finally:
+            if pinned:
+                for b in bufs:
+                    lib.bmu_host_unregister(b.ctypes.data)
+        out.append((idx, diff, nf))
+    # library-allocated page-locked memory
+    p = lib.bmu_host_alloc(data.nbytes)
+    assert p
+    C.memmove(p, data.ctypes.data, data.nbytes)
+    idx3 = np.empty((N, 1), np.int32)
+    diff3 = np.empty((N, 1), np.float32)
+    nf3 = np.empty(N, np.int32)
+    _lib.check(lib.bmu_search(cb._h, p, None, N, 1, idx3.ctypes.data, diff3.ctypes.data, nf3.ctypes.data))
+    lib.bmu_host_free(p)
+    cb.close()
+    eidx, ediff, eret = oracle.search(codes, data, 1)
+    for idx, diff, nf in out + [(idx3, diff3, nf3)]:
+        assert_bits_equal(idx, eidx, "idx")
+        assert_bits_equal(diff, ediff, "diff")
+        assert_bits_equal(nf, eret, "ret")
