@@ -23,7 +23,7 @@ struct Scratch {
 
 // scratch of one search (row classes, work lists, counters, K2 operand image)
 struct SearchScratch {
-  Scratch xT, flags, listW, listS, counters, k2, lkeys, ldone;
+  Scratch xT, flags, listW, listS, counters, k2, lkeys, ldone, lparts;
 };
 
 // pinned host ring that feeds the device from pageable caller memory (bmu_search, host pointers)

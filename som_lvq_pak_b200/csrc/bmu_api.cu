@@ -117,7 +117,7 @@ void ctx_close(DevCtx *c) {
   cudaDeviceSynchronize();
   host_ring_free(c);
   c->ss.xT.release(); c->ss.flags.release(); c->ss.listW.release();
-  c->ss.listS.release(); c->ss.counters.release(); c->ss.k2.release(); c->ss.lkeys.release(); c->ss.ldone.release();
+  c->ss.listS.release(); c->ss.counters.release(); c->ss.k2.release(); c->ss.lkeys.release(); c->ss.ldone.release(); c->ss.lparts.release();
   for (int i = 0; i < BMU_NSLOT; i++) {
     c->stage_in[i].release(); c->stage_mask[i].release(); c->stage_idx[i].release();
     c->stage_diff[i].release(); c->stage_nf[i].release(); c->stage_lab[i].release();
@@ -352,16 +352,18 @@ int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned char *
   if ((rc = ss.listS.ensure((size_t)N * sizeof(int)))) return rc;
   if ((rc = ss.counters.ensure(16 * sizeof(int)))) return rc;
   const bool list8 = k == 1 && d_mask == nullptr;      // k1_list8_kernel: keys (all ones) + arrival counters (zero)
-  if (list8) {
-    // the kernel leaves both arrays as it found them; a new (larger) allocation is initialised once
-    if (ss.lkeys.bytes < (size_t)N * 8) {
+  const bool listk = k >= 2 && k <= 5 && d_mask == nullptr;   // k1_listk_kernel: per-slice keys + arrival counters
+  if (list8 || listk) {
+    // the kernels leave the arrays as they found them; a new (larger) allocation is initialised once
+    if (list8 && ss.lkeys.bytes < (size_t)N * 8) {
       if ((rc = ss.lkeys.ensure((size_t)N * 8))) return rc;
       CK(cudaMemsetAsync(ss.lkeys.p, 0xff, ss.lkeys.bytes, st));
     }
-    if (ss.ldone.bytes < ((size_t)N / 8 + 1) * sizeof(int)) {
-      if ((rc = ss.ldone.ensure(((size_t)N / 8 + 1) * sizeof(int)))) return rc;
+    if (ss.ldone.bytes < ((size_t)N / 4 + 1) * sizeof(int)) {
+      if ((rc = ss.ldone.ensure(((size_t)N / 4 + 1) * sizeof(int)))) return rc;
       CK(cudaMemsetAsync(ss.ldone.p, 0, ss.ldone.bytes, st));
     }
+    if (listk && (rc = ss.lparts.ensure(k1_listk_parts_bytes()))) return rc;
   }
 
   K1Args a;
@@ -373,7 +375,9 @@ int search_dev_impl(bmu_codebook *cb, const float *d_data, const unsigned char *
   a.xT = (float *)ss.xT.p; a.flags = (unsigned char *)ss.flags.p;
   a.listW = (int *)ss.listW.p; a.listS = (int *)ss.listS.p; a.counters = (int *)ss.counters.p;
   a.lkeys = nullptr; a.ldone = nullptr;
+  a.lparts = nullptr;
   if (list8) { a.lkeys = (unsigned long long *)ss.lkeys.p; a.ldone = (int *)ss.ldone.p; }
+  if (listk) { a.lparts = (unsigned long long *)ss.lparts.p; a.ldone = (int *)ss.ldone.p; }
   a.idx = d_idx; a.diff = d_diff; a.nfound = d_nfound;
   c->last_counters = a.counters;
   c->last_rows = N;

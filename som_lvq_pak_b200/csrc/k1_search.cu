@@ -524,6 +524,165 @@ k1_list8_kernel(const float *__restrict__ data, const float *__restrict__ cT, lo
   }
 }
 
+// ---------------------------------------------------------------- K1-listk (2 <= k <= 5, no masks)
+// The k-NN version of k1_list8_kernel: FOUR listed rows per warp against each 128-code tile (codebook traffic
+// through L2 / 4 compared with k1_warp_kernel, which this replaces for unmasked rows), per-lane sorted lists of
+// 64-bit keys (distance bits << 32 | ~index: the unsigned order is the reference's k-NN order, distance ascending
+// then index DESCENDING, lvq_pak.c:197), k rounds of warp minimum per row.  A short list is cut into S slices of
+// code tiles handled by warps anywhere in the grid; every slice leaves its sorted k keys per row in `parts`, the
+// warp that finishes a group last merges the S lists.  Long lists (more groups than warps) run with S = 1 and
+// write their results directly.
+#define K1_LISTK_KT 5
+#define K1_LISTK_SMAX 32
+#define K1_LISTK_CAP 16384        // listed rows that can be sliced (beyond that the list is long enough for S = 1)
+__global__ void __launch_bounds__(256, 2)
+k1_listk_kernel(const float *__restrict__ data, const float *__restrict__ cT, long M, int D, int k,
+                const int *__restrict__ list, const int *__restrict__ count, u64 *__restrict__ parts,
+                int *__restrict__ done, int32_t *__restrict__ idx, float *__restrict__ diff,
+                int32_t *__restrict__ nfound) {
+  constexpr int KT = K1_LISTK_KT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = *count;
+  if (cnt <= 0) return;
+  const long W = (long)gridDim.x * 8, wid = (long)blockIdx.x * 8 + warp;
+  const long groups = (cnt + 3) / 4;
+  const int nct = (int)((M + K1_TC - 1) / K1_TC);
+  long S = cnt <= K1_LISTK_CAP ? W / groups : 1;
+  S = S < 1 ? 1 : (S > nct ? nct : (S > K1_LISTK_SMAX ? K1_LISTK_SMAX : S));
+  const long items = groups * S;
+  for (long item = wid; item < items; item += W) {
+    const long gidx = item / S;
+    const int sl = (int)(item % S);
+    const int ct0 = (int)((long)sl * nct / S), ct1 = (int)((long)(sl + 1) * nct / S);
+    const float *xp[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      long w = gidx * 4 + r;
+      if (w >= cnt) w = gidx * 4;
+      xp[r] = data + (long)list[w] * D;
+    }
+    u64 ld[4][KT];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int t = 0; t < KT; t++) ld[r][t] = ~0ull;
+    for (int ct = ct0; ct < ct1; ct++) {
+      const float *cbase = cT + (long)ct * D * K1_TC + lane;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+#pragma unroll 4
+      for (int i = 0; i < D; i++) {
+        const float *cr = cbase + (long)i * K1_TC;
+        const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float xi = __ldg(xp[r] + i);
+          acc[r][0] = sq_acc(acc[r][0], c0, xi);
+          acc[r][1] = sq_acc(acc[r][1], c1, xi);
+          acc[r][2] = sq_acc(acc[r][2], c2, xi);
+          acc[r][3] = sq_acc(acc[r][3], c3, xi);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = ct * K1_TC + tile_code(lane + 32 * q);
+        if (j >= M) continue;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float d = acc[r][q];
+          if (!(d <= FLT_MAX)) continue;              // +Inf / NaN never enter (lvq_pak.c:197 against the FLT_MAX start)
+          u64 key = ((u64)__float_as_uint(d) << 32) | (u64)(0xFFFFFFFFu - (unsigned)j);
+          if (key < ld[r][KT - 1]) {
+            // sorted insertion with static indexing: once placed, the rest shifts down and the largest drops out
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+              const u64 cur = ld[r][t];
+              const bool sw = key < cur;
+              ld[r][t] = sw ? key : cur;
+              key = sw ? cur : key;
+            }
+          }
+        }
+      }
+    }
+    // k rounds of warp minimum per row: lane t < k keeps the t-th key of row r in out[r]
+    u64 out[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      out[r] = ~0ull;
+      for (int t = 0; t < k; t++) {
+        u64 b = ld[r][0];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const u64 o = __shfl_xor_sync(0xffffffffu, b, off);
+          b = o < b ? o : b;
+        }
+        if (b != ~0ull && ld[r][0] == b) {            // exactly one lane owns this (distance, code) pair: pop it
+#pragma unroll
+          for (int u = 0; u + 1 < KT; u++) ld[r][u] = ld[r][u + 1];
+          ld[r][KT - 1] = ~0ull;
+        }
+        if (lane == t) out[r] = b;
+      }
+    }
+    if (S == 1) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const long w = gidx * 4 + r;
+        if (w < cnt && lane < k) {
+          const long n = list[w];
+          const u64 b = out[r];
+          idx[n * k + lane] = b == ~0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)b);
+          diff[n * k + lane] = b == ~0ull ? FLT_MAX : __uint_as_float((unsigned)(b >> 32));
+          if (lane == 0) nfound[n] = k;
+        }
+      }
+      continue;
+    }
+    // sliced: leave the slice's sorted keys, the last warp of the group merges the S lists of every row
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const long w = gidx * 4 + r;
+      if (w < cnt && lane < KT) parts[((size_t)w * K1_LISTK_SMAX + sl) * KT + lane] = lane < k ? out[r] : ~0ull;
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = atomicAdd(&done[gidx], 1) == (int)S - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      const long w = gidx * 4 + lane;
+      if (lane < 4 && w < cnt) {
+        const long n = list[w];
+        const volatile u64 *pp = parts + (size_t)w * K1_LISTK_SMAX * KT;
+        unsigned char hp[K1_LISTK_SMAX];
+        for (int q = 0; q < (int)S; q++) hp[q] = 0;
+        for (int t = 0; t < k; t++) {
+          u64 b = ~0ull;
+          int bq = -1;
+          for (int q = 0; q < (int)S; q++) {
+            if (hp[q] >= KT) continue;
+            const u64 o = pp[q * KT + hp[q]];
+            if (o < b) { b = o; bq = q; }
+          }
+          if (bq >= 0) hp[bq]++;
+          idx[n * k + t] = b == ~0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)b);
+          diff[n * k + t] = b == ~0ull ? FLT_MAX : __uint_as_float((unsigned)(b >> 32));
+        }
+        nfound[n] = k;
+      }
+      if (lane == 0) done[gidx] = 0;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- K1-seq
 // One thread per listed row: the reference's loops verbatim in behaviour, including the
 // early exit `if (difference > bound) break` (lvq_pak.c:72,195).  With NaN in the inputs the
@@ -573,6 +732,7 @@ k1_seq_kernel(const float *__restrict__ data, const unsigned char *__restrict__ 
 // (launch counter: bmu_api.cu, one atomic for all device contexts)
 
 size_t k1_cT_floats(long M, int D) { return (size_t)((M + K1_TC - 1) / K1_TC) * D * K1_TC; }
+size_t k1_listk_parts_bytes() { return (size_t)K1_LISTK_CAP * K1_LISTK_SMAX * K1_LISTK_KT * sizeof(u64); }
 size_t k1_xT_floats(long N, int D) { return (size_t)((N + K1_TS - 1) / K1_TS) * D * K1_TS * 2; }
 
 cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT,
@@ -648,10 +808,16 @@ cudaError_t k1_search(const K1Args &a, cudaStream_t st) {
 // rows in listW (count in counters[0]): masked / tiny rows, k >= 2 rows, K2 certificate failures
 cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
   // The list length is only known on the device.  k == 1 without masks: k1_list8_kernel (eight rows per
-  // warp, code tiles sliced over the whole grid, 2 CTAs per SM); k >= 2 or masks: k1_warp_kernel, whose
-  // warps share a row.  Both are persistent over the list and return at once when it is empty.
+  // warp, code tiles sliced over the whole grid, 2 CTAs per SM); 2 <= k <= 5 without masks: k1_listk_kernel
+  // (four rows per warp); larger k or masks: k1_warp_kernel, whose warps share a row.  Both are persistent over the list and return at once when it is empty.
   if (a.k == 1 && a.mask == nullptr && a.lkeys) {
     k1_list8_kernel<<<a.num_sms * 2, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, a.lkeys, a.ldone,
+                                                  a.idx, a.diff, a.nfound);
+    k1_count_launch(1);
+    return cudaGetLastError();
+  }
+  if (a.k >= 2 && a.k <= K1_LISTK_KT && a.mask == nullptr && a.lparts) {
+    k1_listk_kernel<<<a.num_sms * 2, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.k, a.listW, a.counters + 0, a.lparts, a.ldone,
                                                   a.idx, a.diff, a.nfound);
     k1_count_launch(1);
     return cudaGetLastError();

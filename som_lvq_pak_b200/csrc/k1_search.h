@@ -27,7 +27,8 @@ struct K1Args {
   int *listW, *listS;           // N each
   int *counters;                // 4 ints
   unsigned long long *lkeys;    // k1_list8_kernel: N keys, all ones between launches (nullptr: not available)
-  int *ldone;                   // k1_list8_kernel: N / 8 + 1 arrival counters, zero between launches
+  int *ldone;                   // k1_list8 / k1_listk: N / 4 + 1 arrival counters, zero between launches
+  unsigned long long *lparts;   // k1_listk_kernel: k1_listk_parts_bytes() of per-slice keys (nullptr: not available)
   // outputs
   int32_t *idx;
   float *diff;
@@ -36,6 +37,7 @@ struct K1Args {
 
 size_t k1_cT_floats(long M, int D);
 size_t k1_xT_floats(long N, int D);
+size_t k1_listk_parts_bytes();
 cudaError_t k1_prepare_codebook(const float *d_codes, long M, int D, float *d_cT,
                                 unsigned *d_cb_flags, cudaStream_t st);
 cudaError_t k1_search(const K1Args &a, cudaStream_t st);
