@@ -225,3 +225,23 @@ def test_page_locked_and_pageable_buffers_agree(engine, oracle, monkeypatch):
         assert_bits_equal(idx, eidx, "idx")
         assert_bits_equal(diff, ediff, "diff")
         assert_bits_equal(nf, eret, "ret")
+
+
+def test_vfind_trials_over_the_visible_gpus():
+    """vfind: independent trials, one stream of trials per GPU, (error, trial) pairs gathered and the
+    winner's map broadcast over NCCL -- the same map, bit for bit, as the single-process search
+    (tools/vfind_multi.py under torchrun; needs two GPUs)"""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    n = min(n, 4)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(ROOT, "tools", "vfind_multi.py"), "8"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "identical to the single-process search: True" in p.stdout
