@@ -56,6 +56,9 @@ struct Nccl {
 
 int nccl_load() {
   if (g_nccl.h) return BMU_OK;
+  // NCCL writes its version banner and debug lines to STDOUT unless told otherwise; the hosts' stdout is compared byte
+  // for byte with the reference's, so the log goes to stderr (a user's own NCCL_DEBUG_FILE is respected)
+  setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
   // A copy that the process has loaded already (PyTorch ships its own libnccl.so.2) is reused: two NCCL
   // builds in one process, the second one opened RTLD_GLOBAL, made a later `import torch` bind to the wrong
   // one.  Otherwise the system library is opened with local scope.

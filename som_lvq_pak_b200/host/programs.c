@@ -90,11 +90,14 @@ static int find_winners(const struct pak_entries *codes, const struct pak_entrie
   if (!w->idx || !w->diff || !w->nfound) { fprintf(stderr, "out of memory\n"); return 1; }
   if (data->n == 0) return 0;
   {
-    /* small searches (the demo recipes) stay on one GPU: opening every device and a communicator costs
-     * more than they take; $SOMLVQ_GPUS overrides */
+    /* Opening every device and an NCCL communicator costs one to two seconds; one B200 streams 54 GB/s of rows over
+     * PCIe and searches 4e14 distance elements a second.  The rows are sharded over all visible GPUs only when one
+     * GPU would need longer than that; $SOMLVQ_GPUS overrides. */
     const char *env = getenv("SOMLVQ_GPUS");
     const double work = (double)data->n * (double)codes->n * (double)codes->dim;
-    const int shards = (env && atoi(env) > 0) ? atoi(env) : (work < 2e10 ? 1 : 0);
+    const double bytes = (double)data->n * (double)codes->dim * 4.0;
+    const double one_gpu_s = work / 4e14 > bytes / 5e10 ? work / 4e14 : bytes / 5e10;
+    const int shards = (env && atoi(env) > 0) ? atoi(env) : (one_gpu_s < 2.0 ? 1 : 0);
     if (bmu_multi_init(shards)) return engine_failed("bmu_multi_init");
   }
   cb = bmu_mcodebook_create(codes->points, codes->n, codes->dim);
