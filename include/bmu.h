@@ -141,7 +141,8 @@ typedef struct bmu_stats {
  * (logical) shards round-robin on the devices, each with its own streams and scratch (used by the
  * tests to run the sharded path on one GPU; statistics of shards that share a device are added on
  * the device, devices are combined by NCCL).  Needs libnccl.so.2 at run time when > 1 device. */
-int bmu_multi_init(int nshards);
+int bmu_multi_init(int nshards);          /* a different shard count than before closes the old contexts: destroy
+                                             the bmu_mcodebook handles made with them first */
 int bmu_multi_shards(void);
 int bmu_multi_devices(void);
 /* rows [lo, hi) of shard `shard`: contiguous, balanced, cut at multiples of 512 rows */
