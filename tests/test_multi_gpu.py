@@ -245,3 +245,24 @@ def test_vfind_trials_over_the_visible_gpus():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:]
     assert "identical to the single-process search: True" in p.stdout
+
+
+@pytest.mark.parametrize("N", [0, 1, 3, 130])
+def test_fewer_rows_than_shards(engine, oracle, N):
+    """empty and nearly empty shards: 4 shards for 0 / 1 / 3 / 130 rows (find_qerror on an empty file adds nothing,
+    som_rout.c:710-721)"""
+    M, D, L = 50, 7, 3
+    codes, data, mask, cl, dl = _inputs(41, M, D, max(N, 8), L, masked=False)
+    data, dl = data[:N], dl[:N]
+    mc = engine.MultiCodebook(codes, nshards=4, code_label=cl)
+    try:
+        idx, diff, nf, st = mc.find_winners(data, 2, None, stats=True, hist=True, sample_label=dl, n_labels=L)
+    finally:
+        mc.close()
+    assert idx.shape == (N, 2) and st["n_found"] == N and int(st["hist"].sum()) == N
+    if N:
+        eidx, ediff, eret = oracle.search(codes, data, 2)
+        assert_bits_equal(idx, eidx, "idx")
+        assert_bits_equal(diff, ediff, "diff")
+        assert_bits_equal(nf, eret, "ret")
+        assert int(st["confusion"].sum()) == N
