@@ -503,18 +503,176 @@ fail:
   return NULL;
 }
 
+/* ------------------------------------------------------------------ binary cache of a parsed file (opt-in)
+ * $BMU_PAK_CACHE=1 keeps `<file>.bmuc` next to a regular .dat / .cod file after its first parse: the flat arrays
+ * as they are in memory plus the label STRINGS in the order they first appear, so that loading the cache interns
+ * them exactly as the parse would have.  The cache is used only while the source's size and modification time,
+ * the mask string and the two loader flags are the ones it was made with.  ($BMU_PAK_CACHE=<directory> puts the
+ * caches there instead.)  A 577 MB file of 1 M x 64 values loads in ~0.1 s instead of ~1.3 s. */
+#include <sys/stat.h>
+struct cache_head {
+  char magic[8];                       /* "BMUC0001" */
+  long long src_size, src_mtime_s, src_mtime_ns;
+  int labels_needed, skip_empty, dim, topol, neigh, xdim, ydim, has_mask;
+  long long n, nlab, nstrings, string_bytes;
+  char mask_str[32];
+};
+
+static int cache_path(const char *name, char *out, size_t outsz) {
+  const char *env = getenv("BMU_PAK_CACHE");
+  const char *dot = strrchr(name, '.');
+  if (!env || !env[0] || strcmp(env, "0") == 0) return 0;
+  if (strcmp(name, "-") == 0 || name[0] == '|') return 0;
+  if (dot && (strcmp(dot, ".gz") == 0 || strcmp(dot, ".z") == 0 || strcmp(dot, ".Z") == 0)) return 0;
+  if (strcmp(env, "1") == 0) return snprintf(out, outsz, "%s.bmuc", name) < (int)outsz;
+  {
+    const char *base = strrchr(name, '/');
+    return snprintf(out, outsz, "%s/%s.bmuc", env, base ? base + 1 : name) < (int)outsz;
+  }
+}
+
+static void cache_fill_head(struct cache_head *h, const struct stat *sb, int labels_needed, int skip_empty) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h->magic, "BMUC0001", 8);
+  h->src_size = (long long)sb->st_size;
+  h->src_mtime_s = (long long)sb->st_mtim.tv_sec;
+  h->src_mtime_ns = (long long)sb->st_mtim.tv_nsec;
+  h->labels_needed = labels_needed;
+  h->skip_empty = skip_empty;
+  strncpy(h->mask_str, pak_mask_string, sizeof(h->mask_str) - 1);
+}
+
+static struct pak_entries *cache_load(const char *name, const char *cpath, int labels_needed, int skip_empty) {
+  struct stat sb;
+  struct cache_head h, want;
+  struct pak_entries *e = NULL;
+  char *strings = NULL;
+  int *map = NULL;
+  long long i;
+  FILE *fp;
+  if (stat(name, &sb) != 0 || !S_ISREG(sb.st_mode)) return NULL;
+  fp = fopen(cpath, "rb");
+  if (!fp) return NULL;
+  cache_fill_head(&want, &sb, labels_needed, skip_empty);
+  if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, want.magic, 8) != 0 || h.src_size != want.src_size ||
+      h.src_mtime_s != want.src_mtime_s || h.src_mtime_ns != want.src_mtime_ns || h.labels_needed != labels_needed ||
+      h.skip_empty != skip_empty || strcmp(h.mask_str, want.mask_str) != 0 || h.n < 0 || h.dim < 1)
+    goto bad;
+  e = (struct pak_entries *)calloc(1, sizeof(*e));
+  if (!e) goto bad;
+  e->dim = h.dim; e->topol = h.topol; e->neigh = h.neigh; e->xdim = h.xdim; e->ydim = h.ydim; e->n = (long)h.n;
+  {
+    const size_t n1 = (size_t)(h.n > 0 ? h.n : 1);
+    e->points = (float *)malloc(sizeof(float) * n1 * h.dim);
+    e->lab_off = (long *)malloc(sizeof(long) * ((size_t)h.n + 1));
+    e->lab_pool = (int *)malloc(sizeof(int) * (size_t)(h.nlab > 0 ? h.nlab : 1));
+    e->weight = (short *)malloc(sizeof(short) * n1);
+    e->fixed_xy = (short *)malloc(sizeof(short) * 2 * n1);
+    if (h.has_mask) e->mask = (unsigned char *)malloc(n1 * h.dim);
+    strings = (char *)malloc((size_t)(h.string_bytes > 0 ? h.string_bytes : 1));
+    map = (int *)malloc(sizeof(int) * (size_t)(h.nstrings > 0 ? h.nstrings : 1));
+    if (!e->points || !e->lab_off || !e->lab_pool || !e->weight || !e->fixed_xy || (h.has_mask && !e->mask) || !strings || !map)
+      goto bad;
+    if (fread(e->points, sizeof(float) * h.dim, (size_t)h.n, fp) != (size_t)h.n) goto bad;
+    if (h.has_mask && fread(e->mask, (size_t)h.dim, (size_t)h.n, fp) != (size_t)h.n) goto bad;
+    if (fread(e->lab_off, sizeof(long), (size_t)h.n + 1, fp) != (size_t)h.n + 1) goto bad;
+    if (h.nlab && fread(e->lab_pool, sizeof(int), (size_t)h.nlab, fp) != (size_t)h.nlab) goto bad;
+    if (fread(e->weight, sizeof(short), (size_t)h.n, fp) != (size_t)h.n) goto bad;
+    if (fread(e->fixed_xy, sizeof(short) * 2, (size_t)h.n, fp) != (size_t)h.n) goto bad;
+    if (h.string_bytes && fread(strings, 1, (size_t)h.string_bytes, fp) != (size_t)h.string_bytes) goto bad;
+  }
+  /* intern the label strings in first-appearance order, then map the cache's local ids to table ids */
+  {
+    const char *p = strings, *end = strings + h.string_bytes;
+    for (i = 0; i < h.nstrings; i++) {
+      if (p >= end) goto bad;
+      map[i] = label_index(p);
+      p += strlen(p) + 1;
+    }
+    for (i = 0; i < h.nlab; i++) {
+      if (e->lab_pool[i] < 0 || e->lab_pool[i] >= h.nstrings) goto bad;
+      e->lab_pool[i] = map[e->lab_pool[i]];
+    }
+  }
+  fclose(fp);
+  free(strings); free(map);
+  return e;
+bad:
+  fclose(fp);
+  free(strings); free(map);
+  pak_free(e);
+  return NULL;
+}
+
+static void cache_save(const char *name, const char *cpath, const struct pak_entries *e, int labels_needed, int skip_empty) {
+  struct stat sb;
+  struct cache_head h;
+  char tmp[4200];
+  FILE *fp;
+  int *local = NULL, *ids = NULL, nids = 0, idcap = 0, ok = 1;
+  long i;
+  size_t bytes = 0;
+  const long nlab = e->lab_off[e->n];
+  if (stat(name, &sb) != 0 || !S_ISREG(sb.st_mode)) return;
+  if (snprintf(tmp, sizeof tmp, "%s.tmp%d", cpath, (int)getpid()) >= (int)sizeof tmp) return;
+  /* local ids in first-appearance order */
+  local = (int *)malloc(sizeof(int) * (size_t)(nlab > 0 ? nlab : 1));
+  if (!local) return;
+  for (i = 0; i < nlab; i++) {
+    int j, id = e->lab_pool[i];
+    for (j = 0; j < nids; j++)
+      if (ids[j] == id) break;
+    if (j == nids) {
+      if (nids >= 4096) { free(local); free(ids); return; }      /* files with that many distinct labels are not cached */
+      if (nids == idcap) {
+        int *t = (int *)realloc(ids, sizeof(int) * (size_t)(idcap + 256));
+        if (!t) { free(local); free(ids); return; }
+        ids = t;
+        idcap += 256;
+      }
+      ids[nids++] = id;
+    }
+    local[i] = j;
+  }
+  for (i = 0; i < nids; i++) bytes += strlen(label_string(ids[i])) + 1;
+  cache_fill_head(&h, &sb, labels_needed, skip_empty);
+  h.dim = e->dim; h.topol = e->topol; h.neigh = e->neigh; h.xdim = e->xdim; h.ydim = e->ydim; h.has_mask = e->mask != NULL;
+  h.n = e->n; h.nlab = nlab; h.nstrings = nids; h.string_bytes = (long long)bytes;
+  fp = fopen(tmp, "wb");
+  if (!fp) { free(local); free(ids); return; }
+  ok = fwrite(&h, sizeof(h), 1, fp) == 1;
+  ok = ok && fwrite(e->points, sizeof(float) * e->dim, (size_t)e->n, fp) == (size_t)e->n;
+  if (e->mask) ok = ok && fwrite(e->mask, (size_t)e->dim, (size_t)e->n, fp) == (size_t)e->n;
+  ok = ok && fwrite(e->lab_off, sizeof(long), (size_t)e->n + 1, fp) == (size_t)e->n + 1;
+  if (nlab) ok = ok && fwrite(local, sizeof(int), (size_t)nlab, fp) == (size_t)nlab;
+  ok = ok && fwrite(e->weight, sizeof(short), (size_t)e->n, fp) == (size_t)e->n;
+  ok = ok && fwrite(e->fixed_xy, sizeof(short) * 2, (size_t)e->n, fp) == (size_t)e->n;
+  for (i = 0; i < nids && ok; i++) {
+    const char *str = label_string(ids[i]);
+    ok = fwrite(str, 1, strlen(str) + 1, fp) == strlen(str) + 1;
+  }
+  ok = (fclose(fp) == 0) && ok;
+  if (ok) ok = rename(tmp, cpath) == 0;         /* atomic: a reader never sees half a cache */
+  if (!ok) remove(tmp);
+  free(local); free(ids);
+}
+
 struct pak_entries *pak_load(const char *name, int labels_needed, int skip_empty) {
   int piped = 0;
-  FILE *fp = pak_open(name, 0, &piped);
+  FILE *fp;
   struct pak_entries *e;
-  char *buf;
+  char *buf, cpath[4200];
   size_t len = 0;
+  const int cached = cache_path(name, cpath, sizeof cpath);
+  if (cached && (e = cache_load(name, cpath, labels_needed, skip_empty)) != NULL) return e;
+  fp = pak_open(name, 0, &piped);
   if (!fp) return NULL;
   buf = slurp(fp, &len);
   pak_close(fp, piped);
   if (!buf) { fprintf(stderr, "Can't read file %s", name); return NULL; }
   e = parse_text(buf, len, name, labels_needed, skip_empty, NULL, NULL);
   free(buf);
+  if (e && cached) cache_save(name, cpath, e, labels_needed, skip_empty);
   return e;
 }
 

@@ -130,6 +130,36 @@ def test_streamed_reader_equals_whole_file_load(tmp_path):
     assert outs[0] == outs[1] == outs[2] == "3\n1 2 3 a b \n4 x 6 c \n7 8 9 \n"
 
 
+def test_binary_cache_of_parsed_files(tmp_path):
+    """$BMU_PAK_CACHE=1: `<file>.bmuc` next to the file after the first parse; a second load comes from the cache and
+    gives the same entries, masks and labels (label table order included: two files loaded in a row); touching the
+    source invalidates it; other loader flags do not share a cache"""
+    text = _big_file(20_000, 12)
+    src = tmp_path / "c.dat"
+    src.write_text(text)
+    env = dict(os.environ, BMU_PAK_CACHE="1")
+    plain = tmp_path / "plain.out"
+    subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(plain)], check=True)
+    assert not (tmp_path / "c.dat.bmuc").exists()
+    outs = []
+    for i in range(2):
+        dst = tmp_path / ("o%d.out" % i)
+        subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(dst)], check=True, env=env)
+        assert (tmp_path / "c.dat.bmuc").exists()
+        outs.append(dst.read_bytes())
+    assert outs[0] == outs[1] == plain.read_bytes()
+    # -noskip keeps the all-masked lines: another flag set, the cache made above must not be used
+    noskip_plain, noskip_cached = tmp_path / "n0.out", tmp_path / "n1.out"
+    subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(noskip_plain), "-noskip"], check=True)
+    subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(noskip_cached), "-noskip"], check=True, env=env)
+    assert noskip_plain.read_bytes() == noskip_cached.read_bytes() != plain.read_bytes()
+    # a changed source (other size and time) is parsed again
+    src.write_text(text + "1 2 3 4 5 6 7 8 9 10 11 12 newlabel\n")
+    dst = tmp_path / "o2.out"
+    subprocess.run([PAK, "pakcat", "-din", str(src), "-dout", str(dst), "-noskip"], check=True, env=env)
+    assert dst.read_bytes().endswith(b"1 2 3 4 5 6 7 8 9 10 11 12 newlabel \n")
+
+
 def test_parallel_loader_reports_the_file_line(tmp_path):
     text = _big_file(60_000, 24).splitlines()
     bad_line = 41_234
