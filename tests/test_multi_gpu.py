@@ -266,3 +266,23 @@ def test_fewer_rows_than_shards(engine, oracle, N):
         assert_bits_equal(diff, ediff, "diff")
         assert_bits_equal(nf, eret, "ret")
         assert int(st["confusion"].sum()) == N
+
+
+def test_process_per_gpu_mode_vs_oracle():
+    """the launcher-per-GPU mode bench.py --gpus N uses (bmu_comm_unique_id / bmu_comm_init_rank / bmu_comm_broadcast_dev /
+    bmu_search_stats_dev / bmu_comm_allreduce_stats_dev), under torchrun on every visible GPU (at most 4), rows and
+    statistics against the oracle (tests/sharded_search_check.py; needs two GPUs)"""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    n = min(n, 4)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29578",
+                        os.path.join(ROOT, "tests", "sharded_search_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "identical to the oracle: True" in p.stdout
