@@ -425,6 +425,10 @@ int bmu_qerror2(bmu_codebook *cb, int xdim, int ydim, int topol, int neigh, floa
     k1_count_launch(1);
   }
   long chunk = (64L << 20) / ((long)D * 4);
+  {
+    const char *env = getenv("SOMLVQ_CHUNK_ROWS");       // tests: many chunks from a small call
+    if (env && atol(env) > 0) chunk = atol(env);
+  }
   if (chunk < 1) chunk = 1;
   if (chunk > N) chunk = N;
   Scratch *q2[2] = {&c->q2_out, &c->stage_lab[0]};          // per-sample values of the two slots

@@ -64,3 +64,18 @@ def test_qerror2_larger_map_property(engine):
     assert np.array_equal(per0.view(np.int32), (d * d).view(np.int32))
     _, per2 = engine.find_qerror2(codes, data, xdim, ydim, 3, 1, 2.0)
     assert (per2 >= per0).all() and (per2 > per0).any()
+
+
+def test_qerror2_many_chunks(engine, oracle, monkeypatch):
+    """bmu_qerror2's double-buffered chunk loop (copy of chunk c+1 || search + weighted pass of chunk c || values of
+    chunk c-1 back): seven chunks with masks, the same per-sample values and float sum as one chunk / the oracle"""
+    rng = np.random.default_rng(23)
+    xdim, ydim, D, N = 13, 9, 7, 700
+    codes = rng.random((xdim * ydim, D), dtype=np.float32)
+    data = rng.random((N, D), dtype=np.float32)
+    mask = (rng.random((N, D)) < 0.2).astype(np.uint8)
+    whole, per_whole = engine.find_qerror2(codes, data, xdim, ydim, 3, 1, 2.5, mask)
+    monkeypatch.setenv("SOMLVQ_CHUNK_ROWS", "101")
+    got, per = engine.find_qerror2(codes, data, xdim, ydim, 3, 1, 2.5, mask)
+    assert np.array_equal(per.view(np.int32), per_whole.view(np.int32)) and same_float(got, whole)
+    assert same_float(got, oracle.qerror(codes, data, xdim, ydim, 3, 1, 1, 2.5, mask))
