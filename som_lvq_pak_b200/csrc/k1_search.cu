@@ -428,12 +428,14 @@ k1_warp_kernel(const float *__restrict__ data, const unsigned char *__restrict__
 // lvq_pak.c:79 -- and the warp that finishes a group last writes the results and resets the scratch.
 __global__ void __launch_bounds__(256, 2)
 k1_list8_kernel(const float *__restrict__ data, const float *__restrict__ cT, long M, int D,
-                const int *__restrict__ list, const int *__restrict__ count, u64 *__restrict__ keys,
+                const int *__restrict__ list, const int *__restrict__ count, const unsigned char *__restrict__ flags,
+                const unsigned *__restrict__ cb_flags, u64 *__restrict__ keys,
                 int *__restrict__ done, int32_t *__restrict__ idx, float *__restrict__ diff,
                 int32_t *__restrict__ nfound) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cnt = *count;
   if (cnt <= 0) return;
+  const bool cb_plain = *cb_flags == 0;                  // no tiny / non-finite code vector
   const long W = (long)gridDim.x * 8, wid = (long)blockIdx.x * 8 + warp;
   const long groups = (cnt + 7) / 8;
   const int nct = (int)((M + K1_TC - 1) / K1_TC);
@@ -451,27 +453,65 @@ k1_list8_kernel(const float *__restrict__ data, const float *__restrict__ cT, lo
       if (w >= cnt) w = gidx * 8;                          // harmless duplicate, never written
       xp[r] = data + (long)list[w] * D;
     }
+    // Rows without tiny magnitudes (the K2 certificate failures; flags bit ROW_TINY clear) against a plain codebook
+    // take the PACKED arithmetic of k1_fast_kernel -- sub / mul / ftz-add on two rows at a time, the same results
+    // bit for bit (common.cuh) in 56 instead of 96 issue slots per component and code quad; any tiny row in the
+    // group sends the whole group through the scalar non-ftz sequence.
+    bool packed = cb_plain;
+    {
+      long w = gidx * 8 + (lane & 7);
+      if (w >= cnt) w = gidx * 8;
+      const bool tiny = (flags[list[w]] & ROW_TINY) != 0;
+      packed = packed && !__any_sync(0xffffffffu, tiny);
+    }
     u64 best[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) best[r] = ~0ull;
     for (int ct = ct0; ct < ct1; ct++) {
       const float *cbase = cT + (long)ct * D * K1_TC + lane;
       float acc[8][4];
+      if (packed) {
+        u64 a2[4][4];
 #pragma unroll
-      for (int r = 0; r < 8; r++)
+        for (int p = 0; p < 4; p++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+          for (int q = 0; q < 4; q++) a2[p][q] = pack2(0.0f, 0.0f);
 #pragma unroll 4
-      for (int i = 0; i < D; i++) {
-        const float *cr = cbase + (long)i * K1_TC;
-        const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+        for (int i = 0; i < D; i++) {
+          const float *cr = cbase + (long)i * K1_TC;
+          const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+          const u64 cc[4] = {pack2(c0, c0), pack2(c1, c1), pack2(c2, c2), pack2(c3, c3)};
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-          const float xi = __ldg(xp[r] + i);
-          acc[r][0] = sq_acc(acc[r][0], c0, xi);
-          acc[r][1] = sq_acc(acc[r][1], c1, xi);
-          acc[r][2] = sq_acc(acc[r][2], c2, xi);
-          acc[r][3] = sq_acc(acc[r][3], c3, xi);
+          for (int p = 0; p < 4; p++) {
+            const u64 xx = pack2(__ldg(xp[2 * p] + i), __ldg(xp[2 * p + 1] + i));
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const u64 d = sub2(cc[q], xx);                 // code - sample (lvq_pak.c:70)
+              a2[p][q] = add2_ftz(a2[p][q], mul2(d, d));
+            }
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) unpack2(a2[p][q], acc[2 * p][q], acc[2 * p + 1][q]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[r][q] = 0.0f;
+#pragma unroll 4
+        for (int i = 0; i < D; i++) {
+          const float *cr = cbase + (long)i * K1_TC;
+          const float c0 = cr[0], c1 = cr[32], c2 = cr[64], c3 = cr[96];
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const float xi = __ldg(xp[r] + i);
+            acc[r][0] = sq_acc(acc[r][0], c0, xi);
+            acc[r][1] = sq_acc(acc[r][1], c1, xi);
+            acc[r][2] = sq_acc(acc[r][2], c2, xi);
+            acc[r][3] = sq_acc(acc[r][3], c3, xi);
+          }
         }
       }
 #pragma unroll
@@ -811,8 +851,8 @@ cudaError_t k1_run_warp_list(const K1Args &a, cudaStream_t st) {
   // warp, code tiles sliced over the whole grid, 2 CTAs per SM); 2 <= k <= 5 without masks: k1_listk_kernel
   // (four rows per warp); larger k or masks: k1_warp_kernel, whose warps share a row.  Both are persistent over the list and return at once when it is empty.
   if (a.k == 1 && a.mask == nullptr && a.lkeys) {
-    k1_list8_kernel<<<a.num_sms * 2, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, a.lkeys, a.ldone,
-                                                  a.idx, a.diff, a.nfound);
+    k1_list8_kernel<<<a.num_sms * 2, 256, 0, st>>>(a.data, a.cT, a.M, a.D, a.listW, a.counters + 0, a.flags, a.cb_flags,
+                                                  a.lkeys, a.ldone, a.idx, a.diff, a.nfound);
     k1_count_launch(1);
     return cudaGetLastError();
   }
