@@ -641,16 +641,27 @@ int bmu_sammon(const float *codes, const unsigned char *mask, long M, int D, lon
 // FIXED order -- per-thread grid-stride partial, xor-shuffle tree, warp partials in warp order, block
 // partials in block order by the last block to finish -- so it is bit-identical from run to run for a
 // given (N, grid).  It is NOT the reference's sequential float sum; bmu_replay_qerror is.
-#define STATS_THREADS 256
-__global__ void __launch_bounds__(STATS_THREADS)
+}  // extern "C"
+// SH: BMU hit counts go to a shared-memory histogram first (M <= STATS_SMEM_BINS: 48 KB of 32-bit counters, one CTA
+// of 1024 threads per SM) and reach the global int64 counters once per CTA and bin -- 10 M global atomics become
+// 148 x M; larger maps count with global atomics directly.
+#define STATS_SMEM_BINS 12288
+template <int THREADS, bool SH>
+__global__ void __launch_bounds__(THREADS)
 stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
              const int32_t *__restrict__ nfound, long N, int k, long M, double *__restrict__ sum_out,
              unsigned long long *__restrict__ nfound_out, unsigned long long *__restrict__ hist,
              const int32_t *__restrict__ slabel, const int32_t *__restrict__ clabel, int L,
              unsigned long long *__restrict__ conf, double *__restrict__ part, unsigned *__restrict__ ticket) {
-  __shared__ double ws[STATS_THREADS / 32];
-  __shared__ unsigned long long wc[STATS_THREADS / 32];
+  extern __shared__ unsigned sh_hist[];
+  __shared__ double ws[THREADS / 32];
+  __shared__ unsigned long long wc[THREADS / 32];
   __shared__ bool last;
+  const bool shist = SH && hist != nullptr;
+  if (shist) {
+    for (long b = threadIdx.x; b < M; b += THREADS) sh_hist[b] = 0u;
+    __syncthreads();
+  }
   double s = 0.0;
   unsigned long long cnt = 0;
   for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < N; n += (long)gridDim.x * blockDim.x) {
@@ -658,7 +669,10 @@ stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
     if (nfound[n] == 0 || j < 0) continue;
     s += sqrt((double)diff[n * k]);
     cnt++;
-    if (hist && j < M) atomicAdd(&hist[j], 1ull);
+    if (hist && j < M) {
+      if (shist) atomicAdd(&sh_hist[j], 1u);
+      else atomicAdd(&hist[j], 1ull);
+    }
     if (conf) {
       const int a = slabel[n], b = clabel[j];
       if (a >= 0 && a < L && b >= 0 && b < L) atomicAdd(&conf[(long)a * L + b], 1ull);
@@ -670,10 +684,15 @@ stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
   }
   if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wc[threadIdx.x >> 5] = cnt; }
   __syncthreads();
+  if (shist)
+    for (long b = threadIdx.x; b < M; b += THREADS) {
+      const unsigned v = sh_hist[b];
+      if (v) atomicAdd(&hist[b], (unsigned long long)v);
+    }
   if (threadIdx.x == 0) {
     double bs = 0.0;
     unsigned long long bc = 0;
-    for (int w = 0; w < STATS_THREADS / 32; w++) { bs += ws[w]; bc += wc[w]; }
+    for (int w = 0; w < THREADS / 32; w++) { bs += ws[w]; bc += wc[w]; }
     part[blockIdx.x] = bs;
     if (bc) atomicAdd(nfound_out, bc);
     __threadfence();
@@ -689,23 +708,32 @@ stats_kernel(const int32_t *__restrict__ idx, const float *__restrict__ diff,
   }
 }
 
-}  // extern "C"
 namespace bmu {
 int stats_accumulate(DevCtx *c, const int32_t *d_idx, const float *d_diff, const int32_t *d_nfound, long N, int k,
                      long M, double *d_sum, long long *d_nfound_total, long long *d_hist, const int32_t *d_slabel,
                      const int32_t *d_clabel, int L, long long *d_conf, cudaStream_t st) {
   if (N <= 0) return BMU_OK;
-  const int grid = c->sms * 4;
-  if (c->stat_part.bytes < (size_t)(grid + 2) * 8) {
-    int rc = c->stat_part.ensure((size_t)(grid + 2) * 8);
+  const bool sh = d_hist != nullptr && M <= STATS_SMEM_BINS;
+  const int grid = sh ? c->sms : c->sms * 4;
+  if (c->stat_part.bytes < (size_t)(c->sms * 4 + 2) * 8) {
+    int rc = c->stat_part.ensure((size_t)(c->sms * 4 + 2) * 8);
     if (rc) return rc;
     CK(cudaMemsetAsync(c->stat_part.p, 0, c->stat_part.bytes, st));
   }
   double *part = (double *)c->stat_part.p;
-  stats_kernel<<<grid, STATS_THREADS, 0, st>>>(d_idx, d_diff, d_nfound, N, k, M, d_sum,
-                                               (unsigned long long *)d_nfound_total, (unsigned long long *)d_hist,
-                                               d_slabel, d_clabel, L, (unsigned long long *)d_conf, part + 1,
-                                               (unsigned *)part);
+  if (sh) {
+    const size_t smem = (size_t)M * sizeof(unsigned);
+    CK(cudaFuncSetAttribute(stats_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stats_kernel<1024, true><<<grid, 1024, smem, st>>>(d_idx, d_diff, d_nfound, N, k, M, d_sum,
+                                                      (unsigned long long *)d_nfound_total, (unsigned long long *)d_hist,
+                                                      d_slabel, d_clabel, L, (unsigned long long *)d_conf, part + 1,
+                                                      (unsigned *)part);
+  } else {
+    stats_kernel<256, false><<<grid, 256, 0, st>>>(d_idx, d_diff, d_nfound, N, k, M, d_sum,
+                                                  (unsigned long long *)d_nfound_total, (unsigned long long *)d_hist,
+                                                  d_slabel, d_clabel, L, (unsigned long long *)d_conf, part + 1,
+                                                  (unsigned *)part);
+  }
   k1_count_launch(1);
   CK(cudaGetLastError());
   return BMU_OK;
