@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
   const int u0 = blockIdx.x * U;
   const int ucount = max(0, min(U, (int)p.M - u0));
   const bool active = tid < ucount;
+  const bool warp_live = (tid & ~31) < ucount;                    // this warp owns at least one unit
   const int gidx = u0 + tid;
   const bool gaussian = p.mode == K3_SOM_GAUSSIAN;
   const bool small_map = p.xdim <= 1024 && p.ydim <= 1024 && p.xdim > 0;
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     if (p.nsteps > 1) stage(1, p.sample[1]);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    acc = pass(xs, xs, false, 0.0f);              // distances to the first sample, no update
+    if (warp_live) acc = pass(xs, xs, false, 0.0f);   // distances to the first sample, no update
   }
   // phase cycles of thread 0 ($BMU_K3_PROF): [0] CTA minimum, [1] grid exchange (own key stored -> global minimum
   // known), [2] barrier after the exchange (waiting for warp 0 + the staged sample), [3] lattice distance and
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     // ---- update of step t fused with the search of step t+1
     bool upd = false;
     float a = talp;
-    if (g1 != K3_NOKEY) {                                  // no winner (all distances NaN/Inf): step skipped
+    if (g1 != K3_NOKEY && warp_live) {                     // no winner (all distances NaN/Inf): step skipped
       const u64 bxy = gw[1];
       const int bx = (int)(unsigned)bxy, by = (int)(bxy >> 32);
       float dd;
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     const float *xt = xs + b0 * Dp;
     const float *xn = (t + 1 < p.nsteps) ? xs + b1 * Dp : xt;
     K3_TICK(3);
-    acc = pass(xt, xn, upd, a);
+    if (warp_live) acc = pass(xt, xn, upd, a);             // warps without a unit (512 threads, 443 units at C5) sit out
     K3_TICK(4);
     b0 = b1;
   }
