@@ -170,3 +170,63 @@ def test_search_extreme_shapes(engine, oracle, M, D, N, k, path):
     assert_bits_equal(diff[sub], e[1], "diff")
     assert (nf == k).all()
     assert idx[3, 0] == M - 1 and diff[3, 0] == 0.0 and idx[4, 0] == 0
+
+
+@pytest.mark.parametrize("path", [1, 0, 2])
+@pytest.mark.parametrize("M,D", [(1000, 64), (700, 33), (600, 200)])
+def test_search_dev_writes_stay_inside_outputs(engine, oracle, M, D, path):
+    """device-pointer entry point with the three output arrays embedded in guard bands: every
+    kernel of every path (tile / warp / list kernels, record and streaming filter, re-rank) must
+    write rows [0, N) x k only — ragged N around the 128-row tile and 512-row pass sizes"""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(M + D + path)
+    codes = rng.random((M, D), dtype=np.float32)
+    cb = engine.Codebook(codes)
+    G = 4096
+    SENT = 0x5A5A5A5A
+    engine.set_search_path(path)
+    try:
+        for N in (1, 127, 129, 511, 513, 2049):
+            data = rng.random((N, D), dtype=np.float32)
+            data[::7] = codes[rng.integers(0, M, len(data[::7]))]          # zero distances
+            d_data = torch.from_numpy(data).to(dev)
+            for k in (1, 2, 5):
+                bufs = [torch.full((N * w + 2 * G,), SENT, dtype=torch.int32, device=dev) for w in (k, k, 1)]
+                ptr = [b.data_ptr() + 4 * G for b in bufs]
+                cb.search_dev(d_data.data_ptr(), N, k, ptr[0], ptr[1], ptr[2])
+                torch.cuda.synchronize()
+                host = [b.cpu().numpy() for b in bufs]
+                for h, name in zip(host, ("idx", "diff", "nfound")):
+                    assert (h[:G] == SENT).all() and (h[-G:] == SENT).all(), \
+                        "%s written outside [0, N*k): N=%d k=%d path=%d" % (name, N, k, path)
+                exp = oracle.search(codes, data, k)
+                assert_bits_equal(host[0][G:-G].reshape(N, k), exp[0], "idx N=%d k=%d" % (N, k))
+                assert_bits_equal(host[1][G:-G].view(np.float32).reshape(N, k), exp[1], "diff N=%d k=%d" % (N, k))
+                assert_bits_equal(host[2][G:-G], exp[2], "ret N=%d k=%d" % (N, k))
+    finally:
+        engine.set_search_path(0)
+
+
+def test_host_search_writes_stay_inside_outputs(engine, oracle):
+    """bmu_search with caller arrays embedded in guard bands: the staged chunks' drain copies
+    (several chunks, the last one ragged) write rows [0, N) x k only"""
+    import ctypes as C
+    from som_lvq_pak_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    M, D, G = 200, 256, 1024
+    codes = rng.random((M, D), dtype=np.float32)
+    cb = engine.Codebook(codes)
+    for N, k in ((1, 1), (70001, 1), (130003, 5)):       # 58 MB chunks: 56 832 rows of 1 KB each
+        data = rng.random((N, D), dtype=np.float32)
+        outs = [np.full(N * w + 2 * G, 0x5A5A5A5A, np.int32) for w in (k, k, 1)]
+        ptr = [C.c_void_p(o.ctypes.data + 4 * G) for o in outs]
+        _lib.check(lib.bmu_search(cb._h, data.ctypes.data_as(C.c_void_p), None, N, k, ptr[0], ptr[1], ptr[2]))
+        for o in outs:
+            assert (o[:G] == 0x5A5A5A5A).all() and (o[-G:] == 0x5A5A5A5A).all()
+        sub = np.unique(np.r_[0:min(N, 500), max(0, N - 500):N, rng.integers(0, N, 500)])
+        e = oracle.search(codes, data[sub], k)
+        assert_bits_equal(outs[0][G:-G].reshape(N, k)[sub], e[0])
+        assert_bits_equal(outs[1][G:-G].view(np.float32).reshape(N, k)[sub], e[1])
+        assert_bits_equal(outs[2][G:-G][sub], e[2])
