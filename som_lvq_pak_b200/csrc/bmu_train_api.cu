@@ -176,7 +176,7 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
   p.prof = d_prof;
   {
     const char *env = getenv("BMU_K3_POLL_DELAY_NS");
-    p.poll_delay_ns = env ? atoi(env) : K3_POLL_DELAY_NS;
+    p.poll_delay_ns = env ? atoi(env) : K3_POLL_DELAY_AUTO;
   }
   CK(cudaEventRecord(t->ev0, g_compute));
   cudaError_t e = k3_launch(p, t->plan, t->has_mask, g_compute);
@@ -189,13 +189,13 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
     const int G = t->plan.grid;
     long long *h = (long long *)malloc(sizeof(long long) * 8 * (size_t)G);
     if (h && cudaMemcpy(h, d_prof, sizeof(long long) * 8 * (size_t)G, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      static const char *names[5] = {"cta_min", "exchange", "barrier", "weights", "pass"};
+      static const char *names[6] = {"cta_min", "exchange", "barrier", "weights", "pass", "polls x1000"};
       fprintf(stderr, "K3 phase cycles per step (mean over %d CTAs / min / max), %ld steps, %.3f us per step:\n", G, nsteps,
               1e3 * t->last_ms / (double)nsteps);
-      for (int i = 0; i < 5; i++) {
+      for (int i = 0; i < 6; i++) {
         double sum = 0, mn = 1e300, mx = 0;
         for (int g = 0; g < G; g++) {
-          const double v = (double)h[(size_t)g * 8 + i] / (double)nsteps;
+          const double v = (double)h[(size_t)g * 8 + i] * (i == 5 ? 1000.0 : 1.0) / (double)nsteps;
           sum += v; mn = v < mn ? v : mn; mx = v > mx ? v : mx;
         }
         fprintf(stderr, "  %-9s %8.0f %8.0f %8.0f\n", names[i], sum / G, mn, mx);

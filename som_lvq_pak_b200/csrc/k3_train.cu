@@ -22,6 +22,7 @@ namespace bmu {
 
 #define K3_NOKEY 0xFFFFFFFFFFFFFF00ull
 #define K3_SLOT_STRIDE 16          // u64 per CTA slot: one 128-byte line each, spread over L2 slices
+#define K3F_SLOT_STRIDE 8          // fused kernel: two slots per line (measured 2-3 % of the C5 step over 16, 4 and 1)
 
 __device__ __forceinline__ u64 make_key(float d, int idx, bool maxidx) {
   unsigned f = (unsigned)(maxidx ? (0xFFFFFF - idx) : idx) & 0xFFFFFFu;
@@ -232,6 +233,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
             st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, b1 | tag);
             if (TOP2) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x + 1, b2 | tag);
           }
+          if (p.poll_delay_ns > 0) __nanosleep((unsigned)p.poll_delay_ns);          // see the fused kernel
+          else if (p.poll_delay_ns < 0) { const long long w0 = clock64(); while (clock64() - w0 < -p.poll_delay_ns) { } }
           constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
           u64 v1[NQ], v2[NQ];
           unsigned pending = 0;
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
   // phase cycles of thread 0 ($BMU_K3_PROF): [0] CTA minimum, [1] grid exchange (own key stored -> global minimum
   // known), [2] barrier after the exchange (waiting for warp 0 + the staged sample), [3] lattice distance and
   // gaussian weight, [4] fused update + search pass
-  long long pc[5] = {0, 0, 0, 0, 0}, c0 = 0, c1;
+  long long pc[6] = {0, 0, 0, 0, 0, 0}, c0 = 0, c1;
   const bool prof = p.prof != nullptr && tid == 0;
 #define K3_TICK(i) do { if (prof) { c1 = clock64(); pc[i] += c1 - c0; c0 = c1; } } while (0)
   if (prof) c0 = clock64();
@@ -584,12 +587,17 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
       K3_TICK(0);
       if (G > 1) {
         const u64 tag = (u64)((bstep + 1) & 0xFFu);
+        constexpr int SS = K3F_SLOT_STRIDE;
         u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
-        if (lane == 0) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, bk | tag);
+        if (lane == 0) st_relaxed_u64(slot + SS * blockIdx.x, bk | tag);
         // All CTAs publish within ~50 cycles of each other and a store needs a few hundred cycles to reach L2:
-        // polls issued at once arrive BEFORE the keys and cost a whole extra L2 round trip, so the first poll
-        // waits a moment (tuned with $BMU_K3_POLL_DELAY_NS, profiles/r02_k3_phase_cycles.txt)
+        // polls issued at once arrive BEFORE the keys and cost a whole extra round trip (650-900 cycles for the
+        // five strong loads of a lane, tools/ubench/grid_exchange.cu), and every poll wave in flight delays the
+        // stores it is waiting for, so the first poll waits.  A busy wait in cycles (negative value) is steadier
+        // than __nanosleep, whose 100 ns are 260 cycles and whose 300 ns are 1200; tuned with
+        // $BMU_K3_POLL_DELAY_NS, profiles/r02_k3_phase_cycles.txt, r02_k3_exchange_ubench.txt
         if (p.poll_delay_ns > 0) __nanosleep((unsigned)p.poll_delay_ns);
+        else if (p.poll_delay_ns < 0) { const long long w0 = clock64(); while (clock64() - w0 < -p.poll_delay_ns) { } }
         constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
         u64 v1[NQ];
         unsigned pending = 0;
@@ -599,9 +607,10 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
           if (lane + 32 * q < G) pending |= 1u << q;
         }
         while (pending) {
+          if (prof) pc[5]++;
 #pragma unroll
           for (int q = 0; q < NQ; q++)
-            if (pending & (1u << q)) v1[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q));
+            if (pending & (1u << q)) v1[q] = ld_relaxed_u64(slot + SS * (lane + 32 * q));
 #pragma unroll
           for (int q = 0; q < NQ; q++)
             if ((pending & (1u << q)) && (v1[q] & 0xFFu) == tag) pending &= ~(1u << q);
@@ -648,7 +657,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     b0 = b1;
   }
   if (prof)
-    for (int i = 0; i < 5; i++) p.prof[(size_t)blockIdx.x * 8 + i] = pc[i];
+    for (int i = 0; i < 6; i++) p.prof[(size_t)blockIdx.x * 8 + i] = pc[i];
 #undef K3_TICK
 
   // ---- write the unit back
@@ -753,6 +762,7 @@ cudaError_t k3_launch(const K3Params &p, const K3Plan &plan, bool has_mask, cuda
       e = cudaMemsetAsync(p.slots, 0, sizeof(u64) * 2 * K3_SLOT_STRIDE * plan.grid, st);
       if (e != cudaSuccess) return e;
       K3Params pp = p;
+      if (pp.poll_delay_ns == K3_POLL_DELAY_AUTO) pp.poll_delay_ns = K3_POLL_DELAY_FUSED;
       void *args[] = {&pp};
       return cudaLaunchCooperativeKernel((void *)k3_som_fused_kernel, dim3(plan.grid), dim3(K3F_THREADS), args, smem, st);
     }
@@ -770,6 +780,7 @@ cudaError_t k3_launch(const K3Params &p, const K3Plan &plan, bool has_mask, cuda
   e = cudaMemsetAsync(p.slots, 0, sizeof(u64) * 2 * K3_SLOT_STRIDE * plan.grid, st);
   if (e != cudaSuccess) return e;
   K3Params pp = p;
+  if (pp.poll_delay_ns == K3_POLL_DELAY_AUTO) pp.poll_delay_ns = plan.grid > 64 ? K3_POLL_DELAY_GENERIC : 0;
   void *args[] = {&pp};
   // cooperative launch only for its guarantee that all CTAs are co-resident (the slot
   // exchange spins on other CTAs)

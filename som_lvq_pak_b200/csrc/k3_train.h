@@ -8,7 +8,11 @@ namespace bmu {
 enum K3Mode { K3_SOM_BUBBLE = 0, K3_SOM_GAUSSIAN = 1, K3_LVQ1 = 2, K3_LVQ2 = 3, K3_LVQ3 = 4, K3_OLVQ1 = 5 };
 
 #define K3_THREADS 256
-#define K3_POLL_DELAY_NS 100           // default pause before the first poll of the fused kernel's exchange (see k3_train.cu)
+// Pause between publishing a CTA's key and the first poll of the grid exchange (see k3_train.cu): > 0 nanoseconds of
+// __nanosleep, < 0 cycles of busy waiting, K3_POLL_DELAY_AUTO = the measured default of the kernel that is launched
+#define K3_POLL_DELAY_AUTO (-2147483647)
+#define K3_POLL_DELAY_GENERIC 100      // generic kernel, grids of more than 64 CTAs (smaller grids poll at once)
+#define K3_POLL_DELAY_FUSED (-525)     // fused large-map kernel: 525 cycles
 #define K3_MAX_GRID 160              // CTA slots the grid exchange polls (5 x 32 lanes)
 #define K3_MASK_SENTINEL 0x7fc00b00u   // quiet NaN payload that marks a masked component
 
