@@ -22,6 +22,7 @@ namespace bmu {
 
 #define K3_NOKEY 0xFFFFFFFFFFFFFF00ull
 #define K3_SLOT_STRIDE 16          // u64 per CTA slot: one 128-byte line each, spread over L2 slices
+#define K3F_POLL_WARPS 5          // fused kernel: 5 x 32 lanes >= K3_MAX_GRID slots, one per lane
 #define K3F_SLOT_STRIDE 8          // fused kernel: two slots per line (measured 2-3 % of the C5 step over 16, 4 and 1)
 
 __device__ __forceinline__ u64 make_key(float d, int idx, bool maxidx) {
@@ -475,8 +476,8 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
   const int nsp = (Dp - K3F_DR) / 2;                               // component pairs kept in shared memory
   float *xs = reinterpret_cast<float *>(smem_raw);                 // [3][Dp]
   u64 *wred = reinterpret_cast<u64 *>(xs + 3 * Dp);                // [16] per-warp keys
-  u64 *gw = wred + 16;                                             // [2] global winner (+pad)
-  u64 *sl2 = gw + 2;                                               // [nsp][512] component pairs
+  u64 *gw = wred + 16;                                             // [K3F_POLL_WARPS] partial minima of the exchange (+pad)
+  u64 *sl2 = gw + 8;                                               // [nsp][512] component pairs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x;
@@ -577,57 +578,47 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     // the ~9200 cycles of a step: $BMU_K3_PROF, profiles/r02_k3_phase_cycles.txt.)
     const long srow2 = (t + 2 < p.nsteps) ? (long)p.sample[t + 2] : 0;
     // ---- winner of step t: CTA minimum, then the grid exchange
-    u64 k1 = (active && acc < FLT_MAX) ? make_key(acc, gidx, false) : K3_NOKEY;   // lvq_pak.c:57,79
+    // The key carries the unit's lattice position instead of its index, (ty, tx) in index order (index = ty * xdim + tx,
+    // tx < xdim), so the minimum still prefers the lower index (lvq_pak.c:79) and nobody divides after the exchange
+    u64 k1 = (active && acc < FLT_MAX) ? make_key(acc, (ty << 12) | tx, false) : K3_NOKEY;   // lvq_pak.c:57,79
     k1 = warp_min_u64(k1);
     if (lane == 0) wred[warp] = k1;
     __syncthreads();
-    if (warp == 0) {
-      u64 bk = lane < K3F_THREADS / 32 ? wred[lane] : K3_NOKEY;
-      bk = warp_min_u64(bk);
-      K3_TICK(0);
+    if (warp < K3F_POLL_WARPS) {
+      // Split polling (tools/ubench/grid_exchange.cu): warp w watches the slots of CTAs 32 w .. 32 w + 31, ONE strong
+      // load per lane and wave, instead of one warp with five loads per lane; the five partial minima meet in shared
+      // memory behind the barrier below.  Warp 0 publishes the CTA's key.
+      u64 part = K3_NOKEY;
+      if (warp == 0) {
+        part = lane < K3F_THREADS / 32 ? wred[lane] : K3_NOKEY;
+        part = warp_min_u64(part);
+        K3_TICK(0);
+      }
       if (G > 1) {
         const u64 tag = (u64)((bstep + 1) & 0xFFu);
         constexpr int SS = K3F_SLOT_STRIDE;
         u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
-        if (lane == 0) st_relaxed_u64(slot + SS * blockIdx.x, bk | tag);
+        if (tid == 0) st_relaxed_u64(slot + SS * blockIdx.x, part | tag);
         // All CTAs publish within ~50 cycles of each other and a store needs a few hundred cycles to reach L2:
-        // polls issued at once arrive BEFORE the keys and cost a whole extra round trip (650-900 cycles for the
-        // five strong loads of a lane, tools/ubench/grid_exchange.cu), and every poll wave in flight delays the
-        // stores it is waiting for, so the first poll waits.  A busy wait in cycles (negative value) is steadier
-        // than __nanosleep, whose 100 ns are 260 cycles and whose 300 ns are 1200; tuned with
-        // $BMU_K3_POLL_DELAY_NS, profiles/r02_k3_phase_cycles.txt, r02_k3_exchange_ubench.txt
+        // polls issued at once arrive BEFORE the keys and cost a whole extra round trip (600-900 cycles), and
+        // every poll wave in flight delays the stores it is waiting for, so the first poll waits.  A busy wait
+        // in cycles (negative value) is steadier than __nanosleep, whose 100 ns are 260 cycles and whose 300 ns
+        // are 1200; tuned with $BMU_K3_POLL_DELAY_NS, profiles/r02_k3_phase_cycles.txt, r02_k3_exchange_ubench.txt
         if (p.poll_delay_ns > 0) __nanosleep((unsigned)p.poll_delay_ns);
         else if (p.poll_delay_ns < 0) { const long long w0 = clock64(); while (clock64() - w0 < -p.poll_delay_ns) { } }
-        constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
-        u64 v1[NQ];
-        unsigned pending = 0;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          v1[q] = K3_NOKEY;
-          if (lane + 32 * q < G) pending |= 1u << q;
-        }
-        while (pending) {
+        const int c = warp * 32 + lane;
+        bool pend = c < G;
+        u64 v = K3_NOKEY;
+        while (__any_sync(0xffffffffu, pend)) {
           if (prof) pc[5]++;
-#pragma unroll
-          for (int q = 0; q < NQ; q++)
-            if (pending & (1u << q)) v1[q] = ld_relaxed_u64(slot + SS * (lane + 32 * q));
-#pragma unroll
-          for (int q = 0; q < NQ; q++)
-            if ((pending & (1u << q)) && (v1[q] & 0xFFu) == tag) pending &= ~(1u << q);
+          if (pend) {
+            v = ld_relaxed_u64(slot + SS * c);
+            if ((v & 0xFFu) == tag) pend = false;
+          }
         }
-        u64 m1 = K3_NOKEY;
-#pragma unroll
-        for (int q = 0; q < NQ; q++)
-          if (lane + 32 * q < G) { const u64 a1 = v1[q] & ~0xFFull; m1 = a1 < m1 ? a1 : m1; }
-        bk = warp_min_u64(m1);
+        part = warp_min_u64(c < G ? (v & ~0xFFull) : K3_NOKEY);
       }
-      if (lane == 0) {
-        gw[0] = bk;
-        // the winner's lattice position (som_rout.c:641-642) is the same for every unit: the two integer
-        // divisions are done once here instead of by all 512 threads behind the barrier
-        const int w = bk != K3_NOKEY ? key_idx(bk, false) : 0;
-        gw[1] = (u64)(unsigned)(w % p.xdim) | ((u64)(unsigned)(w / p.xdim) << 32);
-      }
+      if (lane == 0) gw[warp] = part;                      // G == 1: warp 0's CTA minimum, the others K3_NOKEY
       K3_TICK(1);
     }
     bstep++;
@@ -635,14 +626,15 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     K3_TICK(2);
-    const u64 g1 = gw[0];
+    u64 g1 = gw[0];
+#pragma unroll
+    for (int w = 1; w < K3F_POLL_WARPS; w++) { const u64 o = gw[w]; g1 = o < g1 ? o : g1; }
     if (t + 2 < p.nsteps) stage(b2, srow2);                // buffer b2 was last read two passes ago
     // ---- update of step t fused with the search of step t+1
     bool upd = false;
     float a = talp;
     if (g1 != K3_NOKEY && warp_live) {                     // no winner (all distances NaN/Inf): step skipped
-      const u64 bxy = gw[1];
-      const int bx = (int)(unsigned)bxy, by = (int)(bxy >> 32);
+      const int bx = (int)(g1 >> 8) & 0xFFF, by = (int)(g1 >> 20) & 0xFFF;     // som_rout.c:641-642
       float dd;
       if (small_map) dd = p.topol == 4 ? rect_dist_small(bx, by, tx, ty) : hexa_dist_small(bx, by, tx, ty);
       else dd = p.topol == 4 ? rect_dist_dev(bx, by, tx, ty) : hexa_dist_dev(bx, by, tx, ty);
@@ -683,12 +675,13 @@ __global__ void __launch_bounds__(K3F_THREADS, 1) k3_som_fused_kernel(const K3Pa
 
 static size_t k3f_smem_bytes(int D) {
   const int Dp = (D + 3) & ~3;
-  return (size_t)3 * Dp * 4 + 18 * 8 + (size_t)((Dp - K3F_DR) / 2) * K3F_THREADS * 8;
+  return (size_t)3 * Dp * 4 + 24 * 8 + (size_t)((Dp - K3F_DR) / 2) * K3F_THREADS * 8;
 }
 
 bool k3_fused_eligible(const K3Params &p, const K3Plan &plan, bool has_mask, size_t smem_optin) {
   return p.mode <= K3_SOM_GAUSSIAN && !has_mask && p.fixed_xy == nullptr && p.D >= K3F_DR && plan.U <= K3F_THREADS &&
-         plan.grid <= 160 && p.talp && p.trad && p.xdim > 0 && k3f_smem_bytes(p.D) <= smem_optin;
+         plan.grid <= 32 * K3F_POLL_WARPS && p.talp && p.trad && p.xdim > 0 && p.xdim <= 4096 && p.ydim <= 4096 &&   // key: 12 bits each
+         k3f_smem_bytes(p.D) <= smem_optin;
 }
 
 // ---------------------------------------------------------------- mask encoding

@@ -12,7 +12,7 @@ enum K3Mode { K3_SOM_BUBBLE = 0, K3_SOM_GAUSSIAN = 1, K3_LVQ1 = 2, K3_LVQ2 = 3, 
 // __nanosleep, < 0 cycles of busy waiting, K3_POLL_DELAY_AUTO = the measured default of the kernel that is launched
 #define K3_POLL_DELAY_AUTO (-2147483647)
 #define K3_POLL_DELAY_GENERIC 100      // generic kernel, grids of more than 64 CTAs (smaller grids poll at once)
-#define K3_POLL_DELAY_FUSED (-525)     // fused large-map kernel: 525 cycles
+#define K3_POLL_DELAY_FUSED (-475)     // fused large-map kernel: 475 cycles (split polling; -450 is the measured optimum, -400 starts to miss)
 #define K3_MAX_GRID 160              // CTA slots the grid exchange polls (5 x 32 lanes)
 #define K3_MASK_SENTINEL 0x7fc00b00u   // quiet NaN payload that marks a masked component
 

@@ -174,6 +174,44 @@ __global__ void __launch_bounds__(512) exch_stagger(Params p, int K, int gap) {
   if (threadIdx.x == 0) { p.out[me * 4] = cyc; p.out[me * 4 + 1] = polls; p.out[me * 4 + 2] = (long long)sink; p.out[me * 4 + 3] = 0; }
 }
 
+// Split polling: warp w of five polls slots 32 w .. 32 w + 31 (ONE strong load per lane and wave), the five partial
+// minima meet in shared memory behind the CTA barrier that follows the exchange anyway.
+__global__ void __launch_bounds__(512) exch_split(Params p) {
+  const int G = gridDim.x, lane = threadIdx.x & 31, me = blockIdx.x, warp = threadIdx.x >> 5;
+  __shared__ u64 part[2][8];
+  long long cyc = 0, polls = 0;
+  u64 sink = 0;
+  for (int it = 0; it < p.iters; it++) {
+    long long t = clock64();
+    while (clock64() - t < p.work) { }
+    __syncthreads();
+    const u64 tag = (u64)((it + 1) & 0xFF);
+    const u64 key = ((u64)((me * 2654435761u + it * 40503u) & 0xFFFFFF) << 8);
+    u64 *slot = p.slots + (size_t)(it & 1) * (G * p.stride + 4096);
+    const long long t0 = clock64();
+    if (threadIdx.x == 0) st_relaxed(slot + (size_t)me * p.stride, key | tag);
+    if (warp < 5) {
+      while (clock64() - t0 < -p.delay_ns) { }
+      const int c = warp * 32 + lane;
+      u64 v = ~0ull;
+      bool pend = c < G;
+      while (__any_sync(0xffffffffu, pend)) {
+        if (warp == 0) polls++;
+        if (pend) { v = ld_relaxed(slot + (size_t)c * p.stride); if ((v & 0xFF) == tag) pend = false; }
+      }
+      u64 m = c < G ? (v & ~0xFFull) : ~0ull;
+      m = warp_min(m);
+      if (lane == 0) part[it & 1][warp] = m;
+    }
+    __syncthreads();
+    u64 m = part[it & 1][0];
+    for (int w = 1; w < 5; w++) m = part[it & 1][w] < m ? part[it & 1][w] : m;
+    sink += m;
+    cyc += clock64() - t0;
+  }
+  if (threadIdx.x == 0) { p.out[me * 4] = cyc; p.out[me * 4 + 1] = polls; p.out[me * 4 + 2] = (long long)sink; p.out[me * 4 + 3] = 0; }
+}
+
 int main(int argc, char **argv) {
   int G = 148, iters = 20000;
   cudaDeviceProp prop;
@@ -224,6 +262,33 @@ int main(int argc, char **argv) {
     double a = 0, pl = 0;
     for (int g = 0; g < G; g++) { a += (double)h[g * 4] / iters; pl += (double)h[g * 4 + 1] / iters; }
     printf("K %-3d gap %-4d d0 %-4d stride %-3d | cyc %-8.0f warp-0 polls %.2f\n", c.K, c.gap, c.d0, c.stride, a / G, pl / G);
+  }
+  printf("split polling: five warps, one load per lane and wave; first wave at d0 cycles, slot stride\n");
+  struct { int d0, stride; } pc[] = {{0, 16}, {300, 16}, {500, 16}, {600, 16}, {700, 16}, {0, 8}, {300, 8}, {500, 8}, {600, 8}, {700, 8}, {500, 4}, {600, 4}};
+  for (auto &c : pc) {
+    cudaMemset(slots, 0, nslot * 8);
+    Params p{slots, out, iters, 6000, -c.d0, c.stride, 0, 0, 0};
+    void *args[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)exch_split, dim3(G), dim3(512), args, 0, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(h, out, sizeof(long long) * 4 * G, cudaMemcpyDeviceToHost);
+    double a = 0, pl = 0;
+    for (int g = 0; g < G; g++) { a += (double)h[g * 4] / iters; pl += (double)h[g * 4 + 1] / iters; }
+    printf("d0 %-4d stride %-3d | cyc %-8.0f warp-0 waves %.2f\n", c.d0, c.stride, a / G, pl / G);
+  }
+  // the same CTA shape (512 threads, barrier before and after) with ONE polling warp, for comparison
+  for (int d0 : {500, 600}) {
+    cudaMemset(slots, 0, nslot * 8);
+    Params p{slots, out, iters, 6000, -d0, 8, 0, 0, 0};
+    int K = 1, gap = 0;
+    void *args[] = {&p, &K, &gap};
+    cudaLaunchCooperativeKernel((void *)exch_stagger, dim3(G), dim3(512), args, 0, 0);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof(long long) * 4 * G, cudaMemcpyDeviceToHost);
+    double a = 0;
+    for (int g = 0; g < G; g++) a += (double)h[g * 4] / iters;
+    printf("one warp, d0 %d stride 8 | cyc %.0f\n", d0, a / G);
   }
   return 0;
 }
