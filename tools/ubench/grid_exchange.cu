@@ -187,9 +187,14 @@ __global__ void __launch_bounds__(512) exch_split(Params p) {
     __syncthreads();
     const u64 tag = (u64)((it + 1) & 0xFF);
     const u64 key = ((u64)((me * 2654435761u + it * 40503u) & 0xFFFFFF) << 8);
-    u64 *slot = p.slots + (size_t)(it & 1) * (G * p.stride + 4096);
+    u64 *slot = p.slots + (size_t)(it & 1) * (size_t)(32 * (G * 16 + 64));
     const long long t0 = clock64();
-    if (threadIdx.x == 0) st_relaxed(slot + (size_t)me * p.stride, key | tag);
+    // replicas (p.pollers = R > 1): lane r of warp 0 publishes into copy r of the slot array, CTA c polls copy c % R, so a
+    // line is asked for by 1/R of the CTAs
+    const int R = p.pollers > 1 ? p.pollers : 1;
+    const size_t copy = (size_t)G * p.stride + 64;
+    if (threadIdx.x < R) st_relaxed(slot + threadIdx.x * copy + (size_t)me * p.stride, key | tag);
+    slot += (me % R) * copy;
     if (warp < 5) {
       while (clock64() - t0 < -p.delay_ns) { }
       const int c = warp * 32 + lane;
@@ -219,7 +224,7 @@ int main(int argc, char **argv) {
   if (prop.multiProcessorCount < G) G = prop.multiProcessorCount;
   u64 *slots;
   long long *out, *h = (long long *)malloc(sizeof(long long) * 4 * G);
-  const size_t nslot = 2 * ((size_t)G * 16 + 4096);
+  const size_t nslot = 2 * (size_t)(32 * (G * 16 + 64)) + 8192;
   cudaMalloc(&slots, nslot * 8);
   cudaMalloc(&out, sizeof(long long) * 4 * G);
   struct { int mode, stride, pollers, delay, work, sk; } cfg[] = {
@@ -277,6 +282,21 @@ int main(int argc, char **argv) {
     for (int g = 0; g < G; g++) { a += (double)h[g * 4] / iters; pl += (double)h[g * 4 + 1] / iters; }
     printf("d0 %-4d stride %-3d | cyc %-8.0f warp-0 waves %.2f\n", c.d0, c.stride, a / G, pl / G);
   }
+  printf("split polling with R copies of the slot array (CTA c polls copy c %% R)\n");
+  for (int stride : {8, 16})
+    for (int R : {1, 2, 4, 8, 16, 32})
+      for (int d0 : {200, 300, 400, 500}) {
+        cudaMemset(slots, 0, nslot * 8);
+        Params p{slots, out, iters, 6000, -d0, stride, 0, R, 0};
+        void *args[] = {&p};
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)exch_split, dim3(G), dim3(512), args, 0, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h, out, sizeof(long long) * 4 * G, cudaMemcpyDeviceToHost);
+        double a = 0, pl = 0;
+        for (int g = 0; g < G; g++) { a += (double)h[g * 4] / iters; pl += (double)h[g * 4 + 1] / iters; }
+        printf("stride %-3d R %-3d d0 %-4d | cyc %-8.0f warp-0 waves %.2f\n", stride, R, d0, a / G, pl / G);
+      }
   // the same CTA shape (512 threads, barrier before and after) with ONE polling warp, for comparison
   for (int d0 : {500, 600}) {
     cudaMemset(slots, 0, nslot * 8);
