@@ -97,6 +97,15 @@ int ctx_open(DevCtx *c, int device) {
   c->dev = device;
   c->sms = p.multiProcessorCount;
   c->smem_optin = p.sharedMemPerBlockOptin;
+  {
+    // the trainers allocate from the stream-ordered pool (bmu_train_api.cu): keep up to 1 GiB of freed blocks in it
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->out, cudaStreamNonBlocking));
@@ -116,6 +125,11 @@ void ctx_close(DevCtx *c) {
   cudaSetDevice(c->dev);
   cudaDeviceSynchronize();
   host_ring_free(c);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+  }
   c->ss.xT.release(); c->ss.flags.release(); c->ss.listW.release();
   c->ss.listS.release(); c->ss.counters.release(); c->ss.k2.release(); c->ss.lkeys.release(); c->ss.ldone.release(); c->ss.lparts.release();
   for (int i = 0; i < BMU_NSLOT; i++) {

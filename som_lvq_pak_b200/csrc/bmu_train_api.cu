@@ -11,9 +11,20 @@
 
 using namespace bmu;
 
+// Device memory of a trainer comes from the device's stream-ordered pool (cudaMallocAsync on the context's compute
+// stream; ctx_open keeps up to 1 GiB of freed blocks cached in it).  Creating and destroying trainers back to back --
+// vfind's trials, the Python wrappers -- otherwise pays cudaMalloc/cudaFree every time, and on a busy host a single
+// cudaFree was measured at 0.4-1.2 s (tools/probe/olvq_probe.py) next to a 50 ms training run.
+struct TBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
 struct bmu_trainer {
   long M, N;
   int D;
+  DevCtx *owner = nullptr;       // context (device, compute stream) the trainer lives on
+  cudaStream_t st = nullptr;
   float *d_codes = nullptr, *d_data = nullptr, *d_unit_alpha = nullptr, *d_gslice = nullptr;
   unsigned char *d_valid = nullptr;
   short *d_fixed = nullptr;
@@ -24,20 +35,42 @@ struct bmu_trainer {
   int xdim = 0, ydim = 0, topol = 0;
   float win_thr = 0, epsilon = 0, alpha_cap = 0;
   K3Plan plan{};
-  Scratch sched_sample, sched_talp, sched_trad;
+  TBuf sched_sample, sched_talp, sched_trad;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.0f;
 };
 
 namespace {
-template <typename T>
-int dev_upload(T **dst, const T *src, size_t count) {
-  if (*dst) { cudaFree(*dst); *dst = nullptr; }
-  if (cudaMalloc((void **)dst, count * sizeof(T)) != cudaSuccess) {
+int t_malloc(bmu_trainer *t, void **p, size_t bytes) {
+  if (cudaMallocAsync(p, bytes, t->st) != cudaSuccess) {
     cudaGetLastError();
-    return fail(BMU_ERR_NOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+    *p = nullptr;
+    return fail(BMU_ERR_NOMEM, "cudaMallocAsync of %zu bytes failed", bytes);
   }
-  CK(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, g_compute));
+  return BMU_OK;
+}
+void t_free(bmu_trainer *t, void *p) {
+  if (!p) return;
+  // the context may have been closed (or reopened) since: then the stream is gone and plain cudaFree does it
+  if (t->owner && t->owner->compute == t->st && t->st) {
+    if (cudaFreeAsync(p, t->st) == cudaSuccess) return;
+    cudaGetLastError();
+  }
+  cudaFree(p);
+}
+int t_ensure(bmu_trainer *t, TBuf *b, size_t need) {
+  if (need <= b->bytes) return BMU_OK;
+  t_free(t, b->p);
+  b->p = nullptr; b->bytes = 0;
+  int rc = t_malloc(t, &b->p, need + need / 8);
+  if (!rc) b->bytes = need + need / 8;
+  return rc;
+}
+template <typename T>
+int dev_upload(bmu_trainer *t, T **dst, const T *src, size_t count) {
+  if (*dst) { t_free(t, *dst); *dst = nullptr; }
+  if (int rc = t_malloc(t, (void **)dst, count * sizeof(T))) return rc;
+  CK(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, t->st));
   return BMU_OK;
 }
 }  // namespace
@@ -53,37 +86,31 @@ bmu_trainer *bmu_trainer_create(const float *codes, long M, int D, const float *
   }
   bmu_trainer *t = new bmu_trainer();
   t->M = M; t->N = N; t->D = D;
-  int rc = dev_upload(&t->d_codes, codes, (size_t)M * D);
-  if (!rc) rc = dev_upload(&t->d_data, data, (size_t)N * D);
+  t->owner = ctx(); t->st = g_compute;
+  int rc = dev_upload(t, &t->d_codes, codes, (size_t)M * D);
+  if (!rc) rc = dev_upload(t, &t->d_data, data, (size_t)N * D);
   if (!rc && mask) {
     // masks travel inside the data as a NaN sentinel (k3_train.h); only done if any bit is set
     bool any = false;
     for (size_t i = 0; i < (size_t)N * D && !any; i++) any = mask[i] != 0;
     if (any) {
       unsigned char *d_mask = nullptr;
-      rc = dev_upload(&d_mask, mask, (size_t)N * D);
-      if (!rc && cudaMalloc((void **)&t->d_valid, (size_t)N) != cudaSuccess) {
-        cudaGetLastError();
-        rc = fail(BMU_ERR_NOMEM, "cudaMalloc failed");
-      }
+      rc = dev_upload(t, &d_mask, mask, (size_t)N * D);
+      if (!rc) rc = t_malloc(t, (void **)&t->d_valid, (size_t)N);
       if (!rc) {
         cudaError_t e = k3_encode_mask(t->d_data, d_mask, t->d_valid, N, D, g_compute);
         k1_count_launch(1);
         if (e == cudaSuccess) e = cudaStreamSynchronize(g_compute);
         if (e != cudaSuccess) rc = fail(BMU_ERR_CUDA, "mask encoding: %s", cudaGetErrorString(e));
       }
-      if (d_mask) cudaFree(d_mask);
+      t_free(t, d_mask);
       t->has_mask = true;
     }
   }
   if (!rc) {
     t->plan = k3_plan(M, D, g_sms, g_smem_optin);
-    if (cudaMalloc((void **)&t->d_slots, sizeof(unsigned long long) * 2 * 16 * t->plan.grid) != cudaSuccess ||
-        (t->plan.gslice_floats &&
-         cudaMalloc((void **)&t->d_gslice, t->plan.gslice_floats * sizeof(float)) != cudaSuccess)) {
-      cudaGetLastError();
-      rc = fail(BMU_ERR_NOMEM, "cudaMalloc failed");
-    }
+    rc = t_malloc(t, (void **)&t->d_slots, sizeof(unsigned long long) * 2 * 16 * t->plan.grid);
+    if (!rc && t->plan.gslice_floats) rc = t_malloc(t, (void **)&t->d_gslice, t->plan.gslice_floats * sizeof(float));
   }
   if (!rc && (cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess))
     rc = fail(BMU_ERR_CUDA, "cudaEventCreate failed");
@@ -101,9 +128,9 @@ int bmu_trainer_set_som(bmu_trainer *t, int xdim, int ydim, int topol, int neigh
   if (neigh != BMU_NEIGH_BUBBLE && neigh != BMU_NEIGH_GAUSSIAN) return fail(BMU_ERR_ARG, "bad neighbourhood %d", neigh);
   t->mode = neigh == BMU_NEIGH_GAUSSIAN ? K3_SOM_GAUSSIAN : K3_SOM_BUBBLE;
   t->xdim = xdim; t->ydim = ydim; t->topol = topol;
-  if (t->d_fixed) { cudaFree(t->d_fixed); t->d_fixed = nullptr; }
+  if (t->d_fixed) { t_free(t, t->d_fixed); t->d_fixed = nullptr; }
   if (fixed_xy) {
-    int rc = dev_upload(&t->d_fixed, (const short *)fixed_xy, (size_t)t->N * 2);
+    int rc = dev_upload(t, &t->d_fixed, (const short *)fixed_xy, (size_t)t->N * 2);
     if (rc) return rc;
     CK(cudaStreamSynchronize(g_compute));
   }
@@ -125,9 +152,9 @@ int bmu_trainer_set_lvq(bmu_trainer *t, int algo, const int32_t *code_label,
   if (algo == BMU_OLVQ1 && !unit_alpha) return fail(BMU_ERR_ARG, "OLVQ1 needs unit_alpha");
   if ((algo == BMU_LVQ2 || algo == BMU_LVQ3) && t->M < 2) return fail(BMU_ERR_ARG, "LVQ2/3 need M >= 2");
   t->win_thr = win_thr; t->epsilon = epsilon; t->alpha_cap = alpha_cap;
-  int rc = dev_upload(&t->d_code_label, (const int *)code_label, (size_t)t->M);
-  if (!rc) rc = dev_upload(&t->d_data_label, (const int *)data_label, (size_t)t->N);
-  if (!rc && unit_alpha) rc = dev_upload(&t->d_unit_alpha, unit_alpha, (size_t)t->M);
+  int rc = dev_upload(t, &t->d_code_label, (const int *)code_label, (size_t)t->M);
+  if (!rc) rc = dev_upload(t, &t->d_data_label, (const int *)data_label, (size_t)t->N);
+  if (!rc && unit_alpha) rc = dev_upload(t, &t->d_unit_alpha, unit_alpha, (size_t)t->M);
   if (rc) return rc;
   CK(cudaStreamSynchronize(g_compute));
   return BMU_OK;
@@ -145,14 +172,14 @@ int bmu_trainer_steps(bmu_trainer *t, const int32_t *sample, const float *talp,
   for (long i = 0; i < nsteps; i++)
     if (sample[i] < 0 || sample[i] >= t->N) return fail(BMU_ERR_ARG, "sample[%ld]=%d out of range", i, sample[i]);
   int rc;
-  if ((rc = t->sched_sample.ensure((size_t)nsteps * 4))) return rc;
+  if ((rc = t_ensure(t, &t->sched_sample, (size_t)nsteps * 4))) return rc;
   CK(cudaMemcpyAsync(t->sched_sample.p, sample, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
   if (talp) {
-    if ((rc = t->sched_talp.ensure((size_t)nsteps * 4))) return rc;
+    if ((rc = t_ensure(t, &t->sched_talp, (size_t)nsteps * 4))) return rc;
     CK(cudaMemcpyAsync(t->sched_talp.p, talp, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
   }
   if (trad) {
-    if ((rc = t->sched_trad.ensure((size_t)nsteps * 4))) return rc;
+    if ((rc = t_ensure(t, &t->sched_trad, (size_t)nsteps * 4))) return rc;
     CK(cudaMemcpyAsync(t->sched_trad.p, trad, (size_t)nsteps * 4, cudaMemcpyHostToDevice, g_compute));
   }
   K3Params p{};
@@ -229,8 +256,12 @@ void bmu_trainer_destroy(bmu_trainer *t) {
   if (!t) return;
   void *ptrs[] = {t->d_codes, t->d_data, t->d_unit_alpha, t->d_gslice, t->d_valid, t->d_fixed,
                   t->d_code_label, t->d_data_label, t->d_slots};
-  for (void *q : ptrs) if (q) cudaFree(q);
-  t->sched_sample.release(); t->sched_talp.release(); t->sched_trad.release();
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (t->owner && t->owner->dev >= 0 && t->owner->dev != cur) cudaSetDevice(t->owner->dev);
+  for (void *q : ptrs) t_free(t, q);
+  t_free(t, t->sched_sample.p); t_free(t, t->sched_talp.p); t_free(t, t->sched_trad.p);
+  if (t->owner && t->owner->dev >= 0 && t->owner->dev != cur && cur >= 0) cudaSetDevice(cur);
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
   delete t;

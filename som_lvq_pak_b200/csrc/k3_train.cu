@@ -22,6 +22,7 @@ namespace bmu {
 
 #define K3_NOKEY 0xFFFFFFFFFFFFFF00ull
 #define K3_SLOT_STRIDE 16          // u64 per CTA slot: one 128-byte line each, spread over L2 slices
+#define K3_POLL_WARPS 5           // generic kernel: the same split of the slots over five of its eight warps
 #define K3F_POLL_WARPS 5          // fused kernel: 5 x 32 lanes >= K3_MAX_GRID slots, one per lane
 #define K3F_SLOT_STRIDE 8          // fused kernel: two slots per line (measured 2-3 % of the C5 step over 16, 4 and 1)
 
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
   const int Dpad = (D + 3) & ~3;
   float *xs = reinterpret_cast<float *>(smem_raw);                // [2][Dpad]
   u64 *wred = reinterpret_cast<u64 *>(xs + 2 * Dpad);            // [2][16] per-warp keys
-  u64 *gw = wred + 32;                                            // [2] global winners
-  float *ua_s = reinterpret_cast<float *>(gw + 2);                // [U] OLVQ1 rates
+  u64 *gw = wred + 32;                                            // [K3_POLL_WARPS][2] partial winners of the exchange
+  float *ua_s = reinterpret_cast<float *>(gw + 2 * K3_POLL_WARPS + 2);   // [U] OLVQ1 rates
   float *sl;                                                      // [D][Us] component-major slice
   if (SLICE_SMEM) sl = ua_s + ((U + 3) & ~3);
   else sl = p.gslice + (size_t)blockIdx.x * D * Us;
@@ -212,78 +213,67 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_kernel(const K3Params p) {
       }
       if (lane == 0) { wred[warp] = k1; if (TOP2) wred[16 + warp] = k2; }
       __syncthreads();
-      if (warp == 0) {
-        u64 b1 = lane < K3_THREADS / 32 ? wred[lane] : K3_NOKEY;
-        u64 b2 = (TOP2 && lane < K3_THREADS / 32) ? wred[16 + lane] : K3_NOKEY;
-        if (TOP2) {
+      if (warp < K3_POLL_WARPS) {
+        // CTA minimum (warp 0), then the grid exchange: tagged slot per CTA, double buffered by exchange parity.
+        // Split polling as in the fused kernel: warp w watches the slots of CTAs 32 w .. 32 w + 31, one strong
+        // load (two for the two keys of LVQ2/3) per lane and wave; the partial results meet in gw[] behind the barrier.
+        u64 b1 = K3_NOKEY, b2 = K3_NOKEY;
+        if (warp == 0) {
+          b1 = lane < K3_THREADS / 32 ? wred[lane] : K3_NOKEY;
+          b2 = (TOP2 && lane < K3_THREADS / 32) ? wred[16 + lane] : K3_NOKEY;
+          if (TOP2) {
 #pragma unroll
-          for (int off = 4; off >= 1; off >>= 1) {
-            u64 o1 = __shfl_xor_sync(0xffffffffu, b1, off);
-            u64 o2 = __shfl_xor_sync(0xffffffffu, b2, off);
-            merge2(b1, b2, o1, o2);
+            for (int off = 4; off >= 1; off >>= 1) {
+              u64 o1 = __shfl_xor_sync(0xffffffffu, b1, off);
+              u64 o2 = __shfl_xor_sync(0xffffffffu, b2, off);
+              merge2(b1, b2, o1, o2);
+            }
+          } else {
+            b1 = warp_min_u64(b1);
           }
-        } else {
-          b1 = warp_min_u64(b1);
         }
         if (G > 1) {
-          // ---- grid exchange: tagged slot per CTA, double buffered by exchange parity.
-          // All of a lane's slots are requested in one batch; only the late ones are re-polled.
           const u64 tag = (u64)((bstep + 1) & 0xFFu);
           u64 *slot = p.slots + ((size_t)(bstep & 1) * G) * K3_SLOT_STRIDE;
-          if (lane == 0) {
+          if (tid == 0) {
             st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x, b1 | tag);
             if (TOP2) st_relaxed_u64(slot + K3_SLOT_STRIDE * blockIdx.x + 1, b2 | tag);
           }
           if (p.poll_delay_ns > 0) __nanosleep((unsigned)p.poll_delay_ns);          // see the fused kernel
           else if (p.poll_delay_ns < 0) { const long long w0 = clock64(); while (clock64() - w0 < -p.poll_delay_ns) { } }
-          constexpr int NQ = 5;                              // 5 x 32 lanes >= 148 CTAs
-          u64 v1[NQ], v2[NQ];
-          unsigned pending = 0;
-#pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            v1[q] = K3_NOKEY; v2[q] = K3_NOKEY;
-            if (lane + 32 * q < G) pending |= 1u << q;
-          }
-          while (pending) {
-#pragma unroll
-            for (int q = 0; q < NQ; q++)
-              if (pending & (1u << q)) {
-                v1[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q));
-                if (TOP2) v2[q] = ld_relaxed_u64(slot + K3_SLOT_STRIDE * (lane + 32 * q) + 1);
-              }
-#pragma unroll
-            for (int q = 0; q < NQ; q++)
-              if (pending & (1u << q)) {
-                const bool ok = (v1[q] & 0xFFu) == tag && (!TOP2 || (v2[q] & 0xFFu) == tag);
-                if (ok) pending &= ~(1u << q);
-              }
-          }
-          u64 m1 = K3_NOKEY, m2 = K3_NOKEY;
-#pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            if (lane + 32 * q < G) {
-              const u64 a1 = v1[q] & ~0xFFull;
-              if (TOP2) merge2(m1, m2, a1, v2[q] & ~0xFFull);
-              else m1 = a1 < m1 ? a1 : m1;
+          const int c = warp * 32 + lane;
+          bool pend = c < G;
+          u64 v1 = K3_NOKEY, v2 = K3_NOKEY;
+          while (__any_sync(0xffffffffu, pend)) {
+            if (pend) {
+              v1 = ld_relaxed_u64(slot + K3_SLOT_STRIDE * c);
+              if (TOP2) v2 = ld_relaxed_u64(slot + K3_SLOT_STRIDE * c + 1);
+              if ((v1 & 0xFFu) == tag && (!TOP2 || (v2 & 0xFFu) == tag)) pend = false;
             }
           }
+          b1 = c < G ? (v1 & ~0xFFull) : K3_NOKEY;
+          b2 = (TOP2 && c < G) ? (v2 & ~0xFFull) : K3_NOKEY;
           if (TOP2) {
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
-              u64 o1 = __shfl_xor_sync(0xffffffffu, m1, off);
-              u64 o2 = __shfl_xor_sync(0xffffffffu, m2, off);
-              merge2(m1, m2, o1, o2);
+              u64 o1 = __shfl_xor_sync(0xffffffffu, b1, off);
+              u64 o2 = __shfl_xor_sync(0xffffffffu, b2, off);
+              merge2(b1, b2, o1, o2);
             }
           } else {
-            m1 = warp_min_u64(m1);
+            b1 = warp_min_u64(b1);
           }
-          b1 = m1; b2 = m2;
         }
-        if (lane == 0) { gw[0] = b1; gw[1] = b2; }
+        if (lane == 0) { gw[2 * warp] = b1; gw[2 * warp + 1] = b2; }    // G == 1: warp 0's pair, the others K3_NOKEY
       }
       bstep++;
       __syncthreads();
       g1 = gw[0]; g2 = gw[1];
+#pragma unroll
+      for (int w = 1; w < K3_POLL_WARPS; w++) {
+        if (TOP2) merge2(g1, g2, gw[2 * w], gw[2 * w + 1]);
+        else { const u64 o = gw[2 * w]; g1 = o < g1 ? o : g1; }
+      }
     }
 
     // ---- update
@@ -710,7 +700,7 @@ cudaError_t k3_encode_mask(float *d_data, const unsigned char *d_mask, unsigned 
 // ---------------------------------------------------------------- planning + launch
 static size_t k3_fixed_smem(int D, int U) {
   int Dpad = (D + 3) & ~3;
-  return (size_t)2 * Dpad * 4 + 34 * 8 + (size_t)((U + 3) & ~3) * 4;
+  return (size_t)2 * Dpad * 4 + (34 + 2 * K3_POLL_WARPS) * 8 + (size_t)((U + 3) & ~3) * 4;
 }
 
 K3Plan k3_plan(long M, int D, int num_sms, size_t smem_optin) {
